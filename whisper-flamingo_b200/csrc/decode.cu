@@ -1,0 +1,487 @@
+// KV-cached decode step kernels: split-K attention over cached K/V, greedy sampling with the logit
+// filters fused, beam top-k, KV-row gather for beam reordering, device-side step bookkeeping.
+//
+// The reference recomputes the whole decoder (and the cross / x-attn K,V projections of all 1500 / T_x
+// source frames) at every step (whisper/decoding.py:155-164, "disable kv cache"); these kernels give the
+// same per-step result from cached K/V: softmax_fp32(q k^T / 8) v per head (model.py:93-108), then the
+// filters + GreedyDecoder.update of decoding.py:432-442, 281-297.
+//
+// The step is HBM-bound: per (audio, head) the kernel streams 2 x len x 128 B of K/V exactly once, each
+// thread pulling whole 128-byte rows (K) or 16-byte row slices (V) with many loads in flight; the G
+// query rows of one audio (beams) share that single pass.  Everything position-dependent (current
+// length, write offsets) is read from device memory so one captured CUDA graph serves every step.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace wf {
+
+static constexpr int HD = 64;
+static constexpr int DT = 128;       // threads per block == keys per tile
+static constexpr int PART = HD + 2;  // floats per split partial: m, l, o[64]
+
+__device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void ld8(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  v[0] = bf16lo(u.x); v[1] = bf16hi(u.x); v[2] = bf16lo(u.y); v[3] = bf16hi(u.y);
+  v[4] = bf16lo(u.z); v[5] = bf16hi(u.z); v[6] = bf16lo(u.w); v[7] = bf16hi(u.w);
+}
+
+template <typename T, int NQ>
+__global__ void __launch_bounds__(DT)
+attn_decode_kernel(const T* __restrict__ q, long long ldq, const T* __restrict__ kc, const T* __restrict__ vc,
+                   long long ld_kv, long long kv_batch_stride, T* __restrict__ o, long long ldo, int H,
+                   const int* __restrict__ len_ptr, int len_add, int len_const, int n_splits,
+                   float* __restrict__ partials) {
+  __shared__ float sq[NQ][HD];
+  __shared__ float sp[NQ][DT];
+  __shared__ float sred[NQ][DT / 32];
+  __shared__ float sacc[DT / 32][NQ][HD];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int kvb = blockIdx.x / H, h = blockIdx.x % H;
+  const int split = blockIdx.y;
+  const int len = len_ptr ? (*len_ptr + len_add) : len_const;
+  const int n_tiles = (len + DT - 1) / DT;
+  const int tiles_per_split = (n_tiles + n_splits - 1) / n_splits;
+  const int tile_begin = split * tiles_per_split;
+  const int tile_end = min(n_tiles, tile_begin + tiles_per_split);
+
+  for (int i = tid; i < NQ * HD; i += DT) {
+    const int qi = i / HD, d = i % HD;
+    sq[qi][d] = to_f32(q[(static_cast<long long>(kvb) * NQ + qi) * ldq + h * HD + d]) * 0.125f;
+  }
+  __syncthreads();
+
+  const T* kbase = kc + kvb * kv_batch_stride + h * HD;
+  const T* vbase = vc + kvb * kv_batch_stride + h * HD;
+  const int dgrp = lane & 7, ksub = lane >> 3;
+
+  float m_run[NQ], l_run[NQ], acc[NQ][8];
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) {
+    m_run[i] = -INFINITY;
+    l_run[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  }
+
+  for (int tile = tile_begin; tile < tile_end; ++tile) {
+    const int key = tile * DT + tid;
+    // ---- scores for this thread's key against the NQ queries
+    float s[NQ];
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) s[i] = 0.f;
+    if (key < len) {
+      const T* kr = kbase + key * ld_kv;
+      float kv[8][8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) ld8(kr + c * 8, kv[c]);
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+          for (int i = 0; i < NQ; ++i) s[i] = fmaf(sq[i][c * 8 + j], kv[c][j], s[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < NQ; ++i) s[i] = -INFINITY;
+    }
+    // ---- tile max per query (block reduce)
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) {
+      const float wm = warp_max(s[i]);
+      if (lane == 0) sred[i][warp] = wm;
+    }
+    __syncthreads();
+    float corr[NQ];
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) {
+      float tm = sred[i][0];
+#pragma unroll
+      for (int w = 1; w < DT / 32; ++w) tm = fmaxf(tm, sred[i][w]);
+      const float mn = fmaxf(m_run[i], tm);  // finite: every tile in range holds at least one valid key
+      corr[i] = expf(m_run[i] - mn);
+      m_run[i] = mn;
+      const float p = expf(s[i] - mn);
+      sp[i][tid] = p;
+      l_run[i] = l_run[i] * corr[i] + p;  // per-thread partial sum of its own keys (reduced at the end)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] *= corr[i];
+    }
+    __syncthreads();
+    // ---- acc += P V : warp w takes keys [32w, 32w+32) of the tile, 4 keys per instruction, 8 dims per lane
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+      const int kt = warp * 32 + kk * 4 + ksub;
+      const int vkey = tile * DT + kt;
+      if (vkey < len) {
+        float vv[8];
+        ld8(vbase + vkey * ld_kv + dgrp * 8, vv);
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) {
+          const float p = sp[i][kt];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(p, vv[j], acc[i][j]);
+        }
+      }
+    }
+    // sp / sred are rewritten only after the next tile's first barrier; reads above are complete by then
+    __syncthreads();
+  }
+
+  // ---- reduce: l over all threads, acc over the 4 key sub-groups of a warp and the 4 warps
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) {
+    const float wl = warp_sum(l_run[i]);
+    if (lane == 0) sred[i][warp] = wl;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float a = acc[i][j];
+      a += __shfl_xor_sync(0xffffffffu, a, 8);
+      a += __shfl_xor_sync(0xffffffffu, a, 16);
+      acc[i][j] = a;
+    }
+    if (ksub == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sacc[warp][i][dgrp * 8 + j] = acc[i][j];
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < NQ * HD; idx += DT) {
+    const int i = idx / HD, d = idx % HD;
+    float a = 0.f, l = 0.f;
+#pragma unroll
+    for (int w = 0; w < DT / 32; ++w) { a += sacc[w][i][d]; l += sred[i][w]; }
+    const long long row = static_cast<long long>(kvb) * NQ + i;
+    if (n_splits == 1) {
+      o[row * ldo + h * HD + d] = from_f32<T>(a / l);
+    } else {
+      float* pp = partials + ((row * H + h) * n_splits + split) * PART;
+      pp[2 + d] = a;
+      if (d == 0) { pp[0] = m_run[i]; pp[1] = l; }
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(HD)
+attn_decode_combine_kernel(const float* __restrict__ partials, T* __restrict__ o, long long ldo, int H, int n_splits) {
+  const long long row = blockIdx.x / H;
+  const int h = blockIdx.x % H, d = threadIdx.x;
+  const float* pp = partials + (row * H + h) * n_splits * PART;
+  float M = -INFINITY;
+  for (int s = 0; s < n_splits; ++s) M = fmaxf(M, pp[s * PART]);
+  float num = 0.f, den = 0.f;
+  for (int s = 0; s < n_splits; ++s) {
+    const float ms = pp[s * PART];
+    const float w = (ms == -INFINITY) ? 0.f : expf(ms - M);
+    num += w * pp[s * PART + 2 + d];
+    den += w * pp[s * PART + 1];
+  }
+  o[row * ldo + h * HD + d] = from_f32<T>(num / den);
+}
+
+long long attention_decode_workspace_bytes(int R, int H) {
+  return static_cast<long long>(R) * H * 32 /* max splits */ * PART * sizeof(float);
+}
+
+template <typename T, int NQ>
+static int launch_decode_attn(const T* q, long long ldq, const T* kc, const T* vc, long long ld_kv,
+                              long long kv_batch_stride, T* o, long long ldo, int R, int H, const int* len_ptr,
+                              int len_add, int len_max, float* ws, long long ws_bytes, cudaStream_t stream) {
+  const int kvb = R / NQ;
+  const int blocks = kvb * H;
+  const int max_tiles = (len_max + DT - 1) / DT;
+  int n_splits = (2 * num_sms() + blocks - 1) / blocks;
+  if (n_splits > max_tiles) n_splits = max_tiles;
+  if (n_splits > 32) n_splits = 32;
+  if (n_splits < 1) n_splits = 1;
+  if (n_splits > 1)
+    WF_REQUIRE(ws && ws_bytes >= static_cast<long long>(R) * H * n_splits * PART * (long long)sizeof(float),
+               "attention_decode: workspace too small (need %lld bytes)",
+               static_cast<long long>(R) * H * n_splits * PART * (long long)sizeof(float));
+  dim3 grid(blocks, n_splits);
+  attn_decode_kernel<T, NQ><<<grid, DT, 0, stream>>>(q, ldq, kc, vc, ld_kv, kv_batch_stride, o, ldo, H, len_ptr,
+                                                     len_add, len_max, n_splits, ws);
+  WF_CHECK_LAUNCH();
+  if (n_splits > 1) {
+    attn_decode_combine_kernel<T><<<R * H, HD, 0, stream>>>(ws, o, ldo, H, n_splits);
+    WF_CHECK_LAUNCH();
+  }
+  return WF_OK;
+}
+
+template <typename T>
+static int dispatch_decode_attn(const void* q, long long ldq, const void* kc, const void* vc, long long ld_kv,
+                                long long kv_batch_stride, void* o, long long ldo, int R, int G, int H,
+                                const int* len_ptr, int len_add, int len_max, void* ws, long long ws_bytes,
+                                cudaStream_t stream) {
+#define WF_DA(NQ)                                                                                              \
+  case NQ:                                                                                                     \
+    return launch_decode_attn<T, NQ>((const T*)q, ldq, (const T*)kc, (const T*)vc, ld_kv, kv_batch_stride,     \
+                                     (T*)o, ldo, R, H, len_ptr, len_add, len_max, (float*)ws, ws_bytes, stream)
+  switch (G) {
+    WF_DA(1); WF_DA(2); WF_DA(3); WF_DA(4); WF_DA(5); WF_DA(6); WF_DA(8);
+    default:
+      set_error("attention_decode: unsupported queries-per-audio G=%d (supported 1,2,3,4,5,6,8)", G);
+      return WF_ERR_UNSUPPORTED;
+  }
+#undef WF_DA
+}
+
+int attention_decode(int dtype, const void* q, long long ldq, const void* kc, const void* vc, long long ld_kv,
+                     long long kv_batch_stride, void* o, long long ldo, int R, int G, int H, const int* len_ptr,
+                     int len_add, int len_const, void* workspace, long long workspace_bytes, cudaStream_t stream) {
+  WF_REQUIRE(R > 0 && G > 0 && H > 0 && R % G == 0, "attention_decode: bad shape R=%d G=%d H=%d", R, G, H);
+  WF_REQUIRE(len_const > 0, "attention_decode: len (or max len) must be positive");
+  const int al = dtype == WF_BF16 ? 8 : 4;
+  WF_REQUIRE(ld_kv % al == 0 && kv_batch_stride % al == 0, "attention_decode: K/V strides must keep 16-byte alignment");
+  WF_REQUIRE((reinterpret_cast<uintptr_t>(kc) & 15) == 0 && (reinterpret_cast<uintptr_t>(vc) & 15) == 0,
+             "attention_decode: K/V base must be 16-byte aligned");
+  if (dtype == WF_F32)
+    return dispatch_decode_attn<float>(q, ldq, kc, vc, ld_kv, kv_batch_stride, o, ldo, R, G, H, len_ptr, len_add,
+                                       len_const, workspace, workspace_bytes, stream);
+  if (dtype == WF_BF16)
+    return dispatch_decode_attn<__nv_bfloat16>(q, ldq, kc, vc, ld_kv, kv_batch_stride, o, ldo, R, G, H, len_ptr,
+                                               len_add, len_const, workspace, workspace_bytes, stream);
+  WF_REQUIRE(false, "attention_decode: bad dtype %d", dtype);
+}
+
+// ============================================================================ sampling
+struct ArgMax {
+  float v;
+  int i;
+};
+__device__ __forceinline__ ArgMax better(ArgMax a, ArgMax b) {
+  // larger value wins; ties -> lower index (torch.argmax convention)
+  if (b.v > a.v || (b.v == a.v && b.i < a.i)) return b;
+  return a;
+}
+__device__ __forceinline__ ArgMax block_argmax(ArgMax x, ArgMax* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ArgMax y;
+    y.v = __shfl_xor_sync(0xffffffffu, x.v, o);
+    y.i = __shfl_xor_sync(0xffffffffu, x.i, o);
+    x = better(x, y);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (lane == 0) sh[warp] = x;
+  __syncthreads();
+  ArgMax r = sh[0];
+  for (int w = 1; w < nw; ++w) r = better(r, sh[w]);
+  return r;
+}
+__device__ __forceinline__ float block_sum(float x, float* sh) {
+  x = warp_sum(x);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (lane == 0) sh[warp] = x;
+  __syncthreads();
+  float r = 0.f;
+  for (int w = 0; w < nw; ++w) r += sh[w];
+  return r;
+}
+
+// ---- logit filters as a per-row predicate (decoding.py:427-509).  Every rule of ApplyTimestampRules
+// masks an index range, so a row's filter state is four integers computed once per row.
+struct RowMask {
+  int text_end;   // mask [0, text_end)
+  int ts_upto;    // mask [timestamp_begin, ts_upto)
+  int ts_from;    // mask [ts_from, V)
+  int no_ts;      // single masked id or -1
+  int tb;         // timestamp_begin (V when the rules are off)
+  bool first;     // first sampled token -> SuppressBlank mask applies
+};
+__device__ __forceinline__ bool is_masked(const RowMask& m, int i, const uint8_t* __restrict__ suppress,
+                                          const uint8_t* __restrict__ suppress_first) {
+  if (suppress[i]) return true;
+  if (m.first && suppress_first && suppress_first[i]) return true;
+  if (i == m.no_ts || i < m.text_end || i >= m.ts_from) return true;
+  return i >= m.tb && i < m.ts_upto;
+}
+// row = token history of this hypothesis, cur_len tokens of which the first n_init are the prompt
+__device__ RowMask make_row_mask(const int* row, int n_init, int cur_len, int V, int eot, int tb, int no_ts,
+                                 int max_initial_ts) {
+  RowMask m;
+  m.text_end = 0; m.ts_upto = 0; m.ts_from = V; m.no_ts = -1; m.tb = V;
+  m.first = (cur_len == n_init);
+  if (tb < 0) return m;
+  m.tb = tb; m.ts_upto = tb; m.no_ts = no_ts;
+  const int n_s = cur_len - n_init;
+  const bool last_ts = n_s >= 1 && row[cur_len - 1] >= tb;
+  const bool pen_ts = n_s < 2 || row[cur_len - 2] >= tb;
+  if (last_ts) {
+    if (pen_ts) m.ts_from = tb;   // has to be non-timestamp
+    else m.text_end = eot;        // cannot be normal text tokens
+  }
+  int ts_val = -1;
+  for (int j = cur_len - 1; j >= n_init; --j)
+    if (row[j] >= tb) { ts_val = row[j]; break; }
+  if (ts_val >= 0) m.ts_upto = (last_ts && !pen_ts) ? ts_val : ts_val + 1;  // timestamps must not decrease
+  if (m.first) {
+    m.text_end = tb;  // the first sampled token must be a timestamp
+    if (max_initial_ts >= 0) m.ts_from = min(m.ts_from, tb + max_initial_ts + 1);
+  }
+  return m;
+}
+// "if the probability mass over timestamps exceeds every single text token, sample a timestamp" (decoding.py:501-509)
+__device__ void apply_timestamp_mass_rule(RowMask& m, const float* lg, int V, const uint8_t* suppress,
+                                          const uint8_t* suppress_first, ArgMax* sh_am, float* sh_f) {
+  if (m.tb >= V) return;
+  ArgMax text{-INFINITY, 0x7fffffff}, ts{-INFINITY, 0x7fffffff};
+  for (int i = threadIdx.x; i < V; i += blockDim.x) {
+    if (is_masked(m, i, suppress, suppress_first)) continue;
+    if (i < m.tb) text = better(text, ArgMax{lg[i], i});
+    else ts = better(ts, ArgMax{lg[i], i});
+  }
+  text = block_argmax(text, sh_am);
+  ts = block_argmax(ts, sh_am);
+  if (ts.v == -INFINITY) return;  // no timestamp allowed at all
+  float se = 0.f;
+  for (int i = m.tb + threadIdx.x; i < V; i += blockDim.x)
+    if (!is_masked(m, i, suppress, suppress_first)) se += expf(lg[i] - ts.v);
+  se = block_sum(se, sh_f);
+  // logsumexp(ts) > max(text)  (both sides share the softmax normaliser)
+  if (ts.v + logf(se) > text.v) m.text_end = m.tb;
+}
+
+// state: [0]=t (position of the token fed this step) [1]=n_init [2]=all_done [3]=#rows at EOT this step [4]=sot_index
+__global__ void __launch_bounds__(256) sample_greedy_kernel(SampleArgs a) {
+  __shared__ ArgMax sh_am[8];
+  __shared__ float sh_f[8];
+  const int r = blockIdx.x;
+  const float* lg = a.logits + r * a.ld;
+  const int t = a.state[0], n_init = a.state[1], sot_index = a.state[4];
+
+  if (a.no_speech >= 0 && t == sot_index) {
+    // no_speech_prob = softmax(raw logits at the SOT position)[no_speech]   (decoding.py:697-701)
+    ArgMax am{-INFINITY, 0x7fffffff};
+    for (int i = threadIdx.x; i < a.V; i += blockDim.x) am = better(am, ArgMax{lg[i], i});
+    am = block_argmax(am, sh_am);
+    float se = 0.f;
+    for (int i = threadIdx.x; i < a.V; i += blockDim.x) se += expf(lg[i] - am.v);
+    se = block_sum(se, sh_f);
+    if (threadIdx.x == 0) a.no_speech_prob[r] = expf(lg[a.no_speech] - am.v) / se;
+  }
+  if (t + 1 < n_init) return;  // still feeding the forced initial tokens
+
+  int* row = a.tokens + static_cast<long long>(r) * a.T_cap;
+  RowMask m = make_row_mask(row, n_init, t + 1, a.V, a.eot, a.timestamp_begin, a.no_timestamps, a.max_initial_ts);
+  apply_timestamp_mass_rule(m, lg, a.V, a.suppress, a.suppress_first, sh_am, sh_f);
+
+  ArgMax am{-INFINITY, 0x7fffffff};
+  for (int i = threadIdx.x; i < a.V; i += blockDim.x)
+    if (!is_masked(m, i, a.suppress, a.suppress_first)) am = better(am, ArgMax{lg[i], i});
+  am = block_argmax(am, sh_am);
+  float se = 0.f;
+  for (int i = threadIdx.x; i < a.V; i += blockDim.x)
+    if (!is_masked(m, i, a.suppress, a.suppress_first)) se += expf(lg[i] - am.v);
+  se = block_sum(se, sh_f);
+  if (threadIdx.x == 0) {
+    const int prev = row[t];
+    int next = am.i;
+    if (prev == a.eot) {
+      next = a.eot;  // finished rows keep emitting EOT and stop accumulating (decoding.py:291-293)
+    } else {
+      a.sum_logprobs[r] += -logf(se);  // log_softmax at the argmax = -(log sum exp(x - max))
+    }
+    row[t + 1] = next;
+    if (next == a.eot) atomicAdd(&a.state[3], 1);
+  }
+}
+
+int sample_greedy(const SampleArgs& a, cudaStream_t stream) {
+  WF_REQUIRE(a.R > 0 && a.V > 0 && a.logits && a.tokens && a.state && a.suppress, "sample_greedy: bad arguments");
+  sample_greedy_kernel<<<a.R, 256, 0, stream>>>(a);
+  WF_CHECK_LAUNCH();
+  return WF_OK;
+}
+
+__global__ void step_advance_kernel(int* state, int R) {
+  const int t = state[0], n_init = state[1];
+  if (t + 1 >= n_init && state[3] == R) state[2] = 1;
+  state[3] = 0;
+  state[0] = t + 1;
+}
+int step_advance(int* state, int R, cudaStream_t stream) {
+  step_advance_kernel<<<1, 1, 0, stream>>>(state, R);
+  WF_CHECK_LAUNCH();
+  return WF_OK;
+}
+
+// log_softmax over the filtered logits + top-k per row (BeamSearchDecoder.update, decoding.py:337-347)
+__global__ void __launch_bounds__(256) topk_logprobs_kernel(TopkArgs a) {
+  __shared__ ArgMax sh_am[8];
+  __shared__ float sh_f[8];
+  __shared__ int picked[32];
+  const int r = blockIdx.x;
+  const float* lg = a.logits + r * a.ld;
+  RowMask m;
+  if (a.tokens) {
+    m = make_row_mask(a.tokens + static_cast<long long>(r) * a.T_cap, a.n_init, a.cur_len, a.V, a.eot,
+                      a.timestamp_begin, a.no_timestamps, a.max_initial_ts);
+  } else {
+    m.text_end = 0; m.ts_upto = 0; m.ts_from = a.V; m.no_ts = -1; m.tb = a.V; m.first = (a.cur_len == a.n_init);
+  }
+  apply_timestamp_mass_rule(m, lg, a.V, a.suppress, a.suppress_first, sh_am, sh_f);
+  float lse = 0.f, vmax = 0.f;
+  for (int it = 0; it < a.k; ++it) {
+    ArgMax am{-INFINITY, 0x7fffffff};
+    for (int i = threadIdx.x; i < a.V; i += blockDim.x) {
+      bool skip = is_masked(m, i, a.suppress, a.suppress_first);
+      for (int p = 0; p < it && !skip; ++p) skip = (picked[p] == i);
+      if (!skip) am = better(am, ArgMax{lg[i], i});
+    }
+    am = block_argmax(am, sh_am);
+    if (it == 0) {
+      vmax = am.v;
+      float se = 0.f;
+      for (int i = threadIdx.x; i < a.V; i += blockDim.x)
+        if (!is_masked(m, i, a.suppress, a.suppress_first)) se += expf(lg[i] - vmax);
+      lse = logf(block_sum(se, sh_f));
+    }
+    if (threadIdx.x == 0) {
+      picked[it] = am.i;
+      a.out_vals[r * a.k + it] = (am.v - vmax) - lse;  // -inf when fewer than k tokens are allowed
+      a.out_idx[r * a.k + it] = am.i == 0x7fffffff ? 0 : am.i;
+    }
+    __syncthreads();
+  }
+}
+int topk_logprobs(const TopkArgs& a, cudaStream_t stream) {
+  WF_REQUIRE(a.R > 0 && a.V > 0 && a.k > 0 && a.k <= 32, "topk: bad arguments (k=%d)", a.k);
+  WF_REQUIRE(a.logits && a.suppress && a.out_vals && a.out_idx, "topk: null buffer");
+  topk_logprobs_kernel<<<a.R, 256, 0, stream>>>(a);
+  WF_CHECK_LAUNCH();
+  return WF_OK;
+}
+
+// dst[r] = src[src_index[r]] for the first used_bytes of each row (beam reordering of the self-attention KV cache)
+__global__ void __launch_bounds__(256)
+kv_gather_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, const int* __restrict__ idx, long long row_vec,
+                 long long used_vec) {
+  const int r = blockIdx.y;
+  const uint4* s = src + static_cast<long long>(idx[r]) * row_vec;
+  uint4* d = dst + static_cast<long long>(r) * row_vec;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < used_vec; i += stride)
+    d[i] = s[i];
+}
+int kv_gather_rows(const void* src, void* dst, const int* src_index, int R, long long row_bytes, long long used_bytes,
+                   cudaStream_t stream) {
+  WF_REQUIRE(R > 0 && R <= 65535 && row_bytes % 16 == 0 && used_bytes % 16 == 0 && used_bytes <= row_bytes,
+             "kv_gather: bad arguments");
+  if (used_bytes == 0) return WF_OK;
+  long long bx = (used_bytes / 16 + 255) / 256;
+  if (bx > 64) bx = 64;
+  dim3 grid(static_cast<unsigned>(bx), R);
+  kv_gather_kernel<<<grid, 256, 0, stream>>>((const uint4*)src, (uint4*)dst, src_index, row_bytes / 16, used_bytes / 16);
+  WF_CHECK_LAUNCH();
+  return WF_OK;
+}
+
+}  // namespace wf

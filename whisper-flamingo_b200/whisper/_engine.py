@@ -1,0 +1,590 @@
+"""Host side of the CUDA engine: weight packing, encoder / decoder passes, KV-cached decode sessions.
+
+Everything numeric is a call into ``libwf.so`` (see ``_native.py`` / ``include/wf.h``); torch only
+allocates device buffers, owns the streams and captures the decode step into a CUDA graph.
+
+Data layout in HBM
+  activations        [rows, d] row-major, rows = batch * time; bf16 (tensor-core engine) or fp32
+  packed weights     [N, K] row-major ("K-major" for both GEMM operands), biases / LN affine fp32
+  cross / x-attn KV  per layer one [B * T_src, 2d] buffer: K in columns [0,d), V in [d,2d); a head is a
+                     64-column slice, so one (audio, head) K or V row is one 128-byte line
+  self-attn KV       per layer [R, T_cap, 2d], appended in place by the K/V projection GEMM
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import torch
+from torch import Tensor, nn
+
+from . import _native as nv
+
+_ENGINE_DTYPES = (torch.float32, torch.bfloat16)
+
+
+def _engine_dtype(dt: torch.dtype) -> torch.dtype:
+    if dt in _ENGINE_DTYPES:
+        return dt
+    if dt == torch.float16:
+        return torch.bfloat16  # half precision is served by the bf16 tensor-core engine
+    raise nv.WfError(f"unsupported activation dtype {dt}")
+
+
+def _to_dtype(t: Tensor, dt: torch.dtype) -> Tensor:
+    """Device-side cast through wf_cast (fp32 <-> bf16); other pairs only for API glue (fp16 in/out)."""
+    if t.dtype == dt:
+        return t
+    if {t.dtype, dt} == {torch.float32, torch.bfloat16}:
+        src = t.contiguous()
+        return nv.cast(src, torch.empty(src.shape, dtype=dt, device=src.device))
+    return t.to(dt)  # fp16 boundary conversion only
+
+
+# ============================================================================ weight packing
+def _version_key(module: nn.Module):
+    return tuple((p.data_ptr(), p._version) for p in module.parameters())
+
+
+def _pack_w(w: Tensor, dt: torch.dtype) -> Tensor:
+    w = w.detach()
+    if w.dim() > 2:
+        w = w.reshape(w.shape[0], -1)
+    return _to_dtype(w.contiguous().float(), dt).contiguous()
+
+
+def _f32(t: Optional[Tensor], n: Optional[int] = None, device=None) -> Tensor:
+    if t is None:
+        return torch.zeros(n, dtype=torch.float32, device=device)
+    return t.detach().float().contiguous()
+
+
+@dataclass
+class _MhaPack:
+    qkv_w: Tensor  # [3d, d]  (rows: query | key | value)
+    qkv_b: Tensor  # [3d] fp32, key part zero (the key projection has no bias)
+    o_w: Tensor
+    o_b: Tensor
+    d: int
+
+    @property
+    def q_w(self):
+        return self.qkv_w[: self.d]
+
+    @property
+    def q_b(self):
+        return self.qkv_b[: self.d]
+
+    @property
+    def kv_w(self):
+        return self.qkv_w[self.d:]
+
+    @property
+    def kv_b(self):
+        return self.qkv_b[self.d:]
+
+
+def _pack_mha(m, dt) -> _MhaPack:
+    d = m.query.weight.shape[0]
+    dev = m.query.weight.device
+    w = torch.cat([m.query.weight.detach(), m.key.weight.detach(), m.value.weight.detach()], dim=0)
+    b = torch.cat([_f32(m.query.bias), torch.zeros(d, dtype=torch.float32, device=dev), _f32(m.value.bias)])
+    return _MhaPack(_pack_w(w, dt), b.contiguous(), _pack_w(m.out.weight, dt), _f32(m.out.bias), d)
+
+
+@dataclass
+class _MlpPack:
+    w1: Tensor
+    b1: Tensor
+    w2: Tensor
+    b2: Tensor
+
+
+def _pack_mlp(seq, dt) -> _MlpPack:
+    return _MlpPack(_pack_w(seq[0].weight, dt), _f32(seq[0].bias), _pack_w(seq[2].weight, dt), _f32(seq[2].bias))
+
+
+@dataclass
+class _LnPack:
+    w: Tensor
+    b: Tensor
+
+
+def _pack_ln(ln) -> _LnPack:
+    return _LnPack(_f32(ln.weight), _f32(ln.bias))
+
+
+@dataclass
+class _BlockPack:
+    attn_ln: _LnPack
+    attn: _MhaPack
+    mlp_ln: _LnPack
+    mlp: _MlpPack
+    cross_ln: Optional[_LnPack] = None
+    cross: Optional[_MhaPack] = None
+    x_ln: List[_LnPack] = field(default_factory=list)
+    x_attn: List[_MhaPack] = field(default_factory=list)
+    x_gate: List[Tensor] = field(default_factory=list)
+    ff_ln: Optional[_LnPack] = None
+    ff: Optional[_MlpPack] = None
+    ff_gate: Optional[Tensor] = None
+
+
+def _pack_block(blk, dt) -> _BlockPack:
+    bp = _BlockPack(_pack_ln(blk.attn_ln), _pack_mha(blk.attn, dt), _pack_ln(blk.mlp_ln), _pack_mlp(blk.mlp, dt))
+    if blk.cross_attn is not None:
+        bp.cross_ln, bp.cross = _pack_ln(blk.cross_attn_ln), _pack_mha(blk.cross_attn, dt)
+    if blk.add_gated_x_attn != 0:
+        for sub in blk.gated_x_attn_layers:
+            bp.x_ln.append(_pack_ln(sub.attn_ln))
+            bp.x_attn.append(_pack_mha(sub.attn, dt))
+            bp.x_gate.append(_f32(sub.attn_gate))
+        bp.ff_ln, bp.ff, bp.ff_gate = _pack_ln(blk.ff_ln), _pack_mlp(blk.ff, dt), _f32(blk.ff_gate)
+    return bp
+
+
+@dataclass
+class _EncoderPack:
+    conv1_w: Tensor
+    conv1_b: Tensor
+    conv2_w: Tensor
+    conv2_b: Tensor
+    pos: Tensor      # [n_ctx, d] activation dtype (fused into the conv2 epilogue)
+    pos_f32: Tensor  # fp32 copy for the unfused diagnostic path
+    blocks: List[_BlockPack]
+    ln_post: _LnPack
+    d: int
+    n_head: int
+
+
+@dataclass
+class _DecoderPack:
+    tok_emb: Tensor      # fp32 master [V, d] (embedding lookup)
+    pos_emb: Tensor      # fp32 master [n_ctx, d]
+    tok_emb_t: Tensor    # activation dtype copy for the logits GEMM
+    pos_emb_t: Tensor    # activation dtype copy (feature positional add)
+    xt_w: Optional[Tensor]
+    xt_b: Optional[Tensor]
+    blocks: List[_BlockPack]
+    ln: _LnPack
+    d: int
+    n_head: int
+    n_ctx: int
+    n_vocab: int
+
+
+def _cached_pack(module: nn.Module, dt: torch.dtype, builder):
+    nv.require_cuda(next(module.parameters()))
+    key = (dt, _version_key(module))
+    cache = module.__dict__.setdefault("_wf_pack_cache", {})
+    hit = cache.get(dt)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    pack = builder(module, dt)
+    cache[dt] = (key, pack)
+    return pack
+
+
+def _build_encoder_pack(enc, dt) -> _EncoderPack:
+    d = enc.conv1.weight.shape[0]
+    pos = enc.positional_embedding.detach().float().contiguous()
+    return _EncoderPack(_pack_w(enc.conv1.weight, dt), _f32(enc.conv1.bias), _pack_w(enc.conv2.weight, dt),
+                        _f32(enc.conv2.bias), _to_dtype(pos, dt), pos,
+                        [_pack_block(b, dt) for b in enc.blocks], _pack_ln(enc.ln_post), d, enc.n_head)
+
+
+def _build_decoder_pack(dec, dt) -> _DecoderPack:
+    d = dec.token_embedding.weight.shape[1]
+    tok = dec.token_embedding.weight.detach().float().contiguous()
+    pos = dec.positional_embedding.detach().float().contiguous()
+    xt_w = xt_b = None
+    if isinstance(dec.xt_projection, nn.Linear):
+        xt_w, xt_b = _pack_w(dec.xt_projection.weight, dt), _f32(dec.xt_projection.bias)
+    return _DecoderPack(tok, pos, _to_dtype(tok, dt), _to_dtype(pos, dt), xt_w, xt_b,
+                        [_pack_block(b, dt) for b in dec.blocks], _pack_ln(dec.ln), d, dec.n_head, pos.shape[0],
+                        tok.shape[0])
+
+
+def encoder_pack(enc, dt) -> _EncoderPack:
+    return _cached_pack(enc, dt, _build_encoder_pack)
+
+
+def decoder_pack(dec, dt) -> _DecoderPack:
+    return _cached_pack(dec, dt, _build_decoder_pack)
+
+
+# ============================================================================ building blocks
+def _empty(rows: int, cols: int, dt, dev) -> Tensor:
+    return torch.empty((rows, cols), dtype=dt, device=dev)
+
+
+def _mlp_inplace(x: Tensor, xn: Tensor, h: Tensor, ln: _LnPack, mlp: _MlpPack, gate: Optional[Tensor] = None):
+    """x += tanh(gate) * W2 gelu(W1 LN(x) + b1) + b2   (reference model.py:149-152, 197, 214)."""
+    nv.layernorm(x, ln.w, ln.b, xn)
+    nv.linear(xn, mlp.w1, h, bias=mlp.b1, act=nv.ACT_GELU)
+    nv.linear(h, mlp.w2, x, bias=mlp.b2, residual=x, gate=gate)
+
+
+# ============================================================================ encoder
+@torch.no_grad()
+def encoder_forward(enc, mel: Tensor, track_norm: bool = False):
+    """AudioEncoder.forward (reference model.py:234-258) on the CUDA engine."""
+    nv.require_cuda(mel)
+    assert mel.dim() == 3, "mel must be (batch, n_mels, n_frames)"
+    out_dtype = mel.dtype
+    dt = _engine_dtype(mel.dtype)
+    with torch.cuda.device(mel.device):
+        p = encoder_pack(enc, dt)
+        if mel.dtype == torch.float16:
+            mel = mel.to(torch.bfloat16)
+        mel = mel.contiguous()
+        B, C, Tm = mel.shape
+        d, dev = p.d, mel.device
+        # conv stem as im2col + GEMM with fused bias / exact GELU (model.py:239-240)
+        a1 = _empty(B * Tm, 3 * C, dt, dev)
+        nv.im2col_k3(mel, C * Tm, Tm, 1, B, C, Tm, 1, a1)
+        h1 = _empty(B * Tm, d, dt, dev)
+        nv.linear(a1, p.conv1_w, h1, bias=p.conv1_b, act=nv.ACT_GELU)
+        del a1
+        T2 = (Tm - 1) // 2 + 1
+        a2 = _empty(B * T2, 3 * d, dt, dev)
+        nv.im2col_k3(h1, Tm * d, 1, d, B, d, Tm, 2, a2)
+        del h1
+        x = _empty(B * T2, d, dt, dev)
+        x_norm = None
+        n_ctx = p.pos.shape[0]
+        if track_norm or T2 > n_ctx:
+            # diagnostics / over-long input: stem without the fused positional add, then crop + add
+            nv.linear(a2, p.conv2_w, x, bias=p.conv2_b, act=nv.ACT_GELU)
+            x3 = x.view(B, T2, d)
+            if track_norm:
+                x_norm = torch.linalg.norm(x3.float(), dim=-1).mean()
+            if T2 > n_ctx:
+                x3 = x3[:, :n_ctx]
+                T2 = n_ctx
+            xc = x3.reshape(B * T2, d).contiguous()
+            x = nv.add_rowmod(xc, p.pos_f32, _empty(B * T2, d, dt, dev), T2)
+        else:
+            nv.linear(a2, p.conv2_w, x, bias=p.conv2_b, act=nv.ACT_GELU, residual=p.pos[:T2], res_row_mod=T2)
+        del a2
+        M = B * T2
+        xn, qkv, att = _empty(M, d, dt, dev), _empty(M, 3 * d, dt, dev), _empty(M, d, dt, dev)
+        hbuf = _empty(M, 4 * d, dt, dev)
+        for bp in p.blocks:
+            nv.layernorm(x, bp.attn_ln.w, bp.attn_ln.b, xn)
+            nv.linear(xn, bp.attn.qkv_w, qkv, bias=bp.attn.qkv_b)
+            nv.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], att, B, T2, T2, p.n_head, causal=False)
+            nv.linear(att, bp.attn.o_w, x, bias=bp.attn.o_b, residual=x)
+            _mlp_inplace(x, xn, hbuf, bp.mlp_ln, bp.mlp)
+        out = _empty(M, d, dt, dev)
+        nv.layernorm(x, p.ln_post.w, p.ln_post.b, out)
+        out = out.view(B, T2, d)
+        if out_dtype != dt:
+            out = out.to(out_dtype)
+    return (out, x_norm) if track_norm else out
+
+
+# ============================================================================ feature preparation (x-attn inputs)
+@torch.no_grad()
+def prepare_features(p: _DecoderPack, xt: Tensor, dt: torch.dtype) -> Tensor:
+    """xt_projection (if widths differ) + learned positional embedding + cast (reference model.py:316-325).
+    Returns [B * T_x, d] in the activation dtype."""
+    B, Tx, w = xt.shape
+    if Tx > p.n_ctx:
+        raise RuntimeError(f"The size of tensor a ({Tx}) must match the size of tensor b ({p.n_ctx}) at "
+                           f"non-singleton dimension 1: feature length exceeds n_text_ctx (reference model.py:322)")
+    x2 = xt.reshape(B * Tx, w)
+    if w != p.d:
+        if p.xt_w is None:
+            raise RuntimeError(f"feature width {w} != n_state {p.d} but the model has no xt_projection")
+        a = _to_dtype(x2.float() if x2.dtype == torch.float16 else x2, dt).contiguous()
+        out = _empty(B * Tx, p.d, dt, xt.device)
+        return nv.linear(a, p.xt_w, out, bias=p.xt_b, residual=p.pos_emb_t[:Tx], res_row_mod=Tx)
+    # width already n_state: only the positional add (fp32 add, one rounding like the reference)
+    src = x2.contiguous()
+    if src.dtype not in (torch.float32, dt):
+        src = src.float()
+    return nv.add_rowmod(src, p.pos_emb, _empty(B * Tx, w, dt, xt.device), Tx)
+
+
+# ============================================================================ teacher-forced decoder pass
+@torch.no_grad()
+def decoder_forward(dec, tokens: Tensor, xa: Tensor, xt_list: Optional[Sequence[Tensor]]):
+    """TextDecoder.forward over all positions (reference model.py:292-340), offset 0, no cache."""
+    nv.require_cuda(tokens, xa)
+    dt = _engine_dtype(xa.dtype)
+    with torch.cuda.device(xa.device):
+        p = decoder_pack(dec, dt)
+        gated = len(p.blocks) > 0 and len(p.blocks[0].x_attn) > 0
+        if gated:
+            if xt_list is None:
+                raise TypeError("object of type 'NoneType' has no len(): a gated x-attn model needs xt_list")
+            if len(xt_list) > len(p.blocks[0].x_attn):
+                raise ValueError(f"Got {len(xt_list)} translations but only support up to {len(p.blocks[0].x_attn)}")
+        B, t = tokens.shape
+        if t > p.n_ctx:
+            raise RuntimeError(f"token length {t} exceeds n_text_ctx {p.n_ctx}")
+        d, H, dev = p.d, p.n_head, xa.device
+        xa2 = _to_dtype(xa, dt).contiguous().view(-1, d)
+        Ta = xa.shape[1]
+        feats = [prepare_features(p, xt, dt) for xt in xt_list] if (gated and xt_list is not None) else []
+        tok32 = tokens.to(torch.int32).contiguous()
+        M = B * t
+        x = _empty(M, d, dt, dev)
+        nv.embed(tok32, t, None, 0, p.tok_emb, p.pos_emb, x, n_pos=t)
+        xn, q, att = _empty(M, d, dt, dev), _empty(M, d, dt, dev), _empty(M, d, dt, dev)
+        qkv, hbuf = _empty(M, 3 * d, dt, dev), _empty(M, 4 * d, dt, dev)
+        kv_a = _empty(B * Ta, 2 * d, dt, dev)
+        for bp in p.blocks:
+            if gated:
+                acc = x if len(feats) <= 1 else x.clone()
+                for i, f in enumerate(feats):
+                    Tx = f.shape[0] // B
+                    nv.layernorm(x, bp.x_ln[i].w, bp.x_ln[i].b, xn)
+                    nv.linear(xn, bp.x_attn[i].q_w, q, bias=bp.x_attn[i].q_b)
+                    kv_x = _empty(B * Tx, 2 * d, dt, dev)
+                    nv.linear(f, bp.x_attn[i].kv_w, kv_x, bias=bp.x_attn[i].kv_b)
+                    nv.attention(q, kv_x[:, :d], kv_x[:, d:], att, B, t, Tx, H, causal=False)
+                    nv.linear(att, bp.x_attn[i].o_w, acc, bias=bp.x_attn[i].o_b, residual=acc, gate=bp.x_gate[i])
+                x = acc
+                _mlp_inplace(x, xn, hbuf, bp.ff_ln, bp.ff, gate=bp.ff_gate)
+            nv.layernorm(x, bp.attn_ln.w, bp.attn_ln.b, xn)
+            nv.linear(xn, bp.attn.qkv_w, qkv, bias=bp.attn.qkv_b)
+            nv.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], att, B, t, t, H, causal=True)
+            nv.linear(att, bp.attn.o_w, x, bias=bp.attn.o_b, residual=x)
+            nv.layernorm(x, bp.cross_ln.w, bp.cross_ln.b, xn)
+            nv.linear(xn, bp.cross.q_w, q, bias=bp.cross.q_b)
+            nv.linear(xa2, bp.cross.kv_w, kv_a, bias=bp.cross.kv_b)
+            nv.attention(q, kv_a[:, :d], kv_a[:, d:], att, B, t, Ta, H, causal=False)
+            nv.linear(att, bp.cross.o_w, x, bias=bp.cross.o_b, residual=x)
+            _mlp_inplace(x, xn, hbuf, bp.mlp_ln, bp.mlp)
+        nv.layernorm(x, p.ln.w, p.ln.b, xn)
+        logits = torch.empty((M, p.n_vocab), dtype=torch.float32, device=dev)
+        nv.linear(xn, p.tok_emb_t, logits)
+    return logits.view(B, t, p.n_vocab)
+
+
+# ============================================================================ KV-cached decode session
+class DecodeSession:
+    """One batch of R = B * G decoder rows stepping one token at a time over cached K/V.
+
+    Cross-attention and gated-x-attention K/V are projected once per clip here (the reference redoes
+    that at every step, decoding.py:155-164); self-attention K/V are appended by the projection GEMM.
+    The whole step is captured once into a CUDA graph and replayed; the step position lives in device
+    memory (``state[0]``), so replay needs no host-side parameter updates.
+    """
+
+    def __init__(self, dec, xa: Tensor, feats: Optional[Sequence[Tensor]], n_group: int, t_cap: int,
+                 use_graph: bool = True):
+        nv.require_cuda(xa)
+        self.dt = dt = _engine_dtype(xa.dtype)
+        self.dev = dev = xa.device
+        self.p = p = decoder_pack(dec, dt)
+        self.G = G = n_group
+        self.B = B = xa.shape[0]
+        self.R = R = B * G
+        self.T_cap = t_cap
+        d, H = p.d, p.n_head
+        self.gated = len(p.blocks) > 0 and len(p.blocks[0].x_attn) > 0
+        if self.gated and feats is None:
+            raise TypeError("object of type 'NoneType' has no len(): a gated x-attn model needs its feature input "
+                            "(pass x_v= to decode())")
+        feats = list(feats) if (self.gated and feats is not None) else []
+        if self.gated and len(feats) > len(p.blocks[0].x_attn):
+            raise ValueError(f"Got {len(feats)} translations but only support up to {len(p.blocks[0].x_attn)}")
+        xa2 = _to_dtype(xa, dt).contiguous().view(-1, d)
+        self.Ta = Ta = xa.shape[1]
+        # ---- per-clip precompute: cross K/V and x-attn K/V for every layer
+        self.cross_kv: List[Tensor] = []
+        self.x_kv: List[List[Tensor]] = []
+        self.Tx: List[int] = []
+        fprep = [prepare_features(p, f, dt) for f in feats]
+        self.Tx = [f.shape[0] // B for f in fprep]
+        for bp in p.blocks:
+            kv = _empty(B * Ta, 2 * d, dt, dev)
+            nv.linear(xa2, bp.cross.kv_w, kv, bias=bp.cross.kv_b)
+            self.cross_kv.append(kv)
+            per = []
+            for i, f in enumerate(fprep):
+                kvx = _empty(f.shape[0], 2 * d, dt, dev)
+                nv.linear(f, bp.x_attn[i].kv_w, kvx, bias=bp.x_attn[i].kv_b)
+                per.append(kvx)
+            self.x_kv.append(per)
+        del fprep
+        # ---- step buffers
+        L = len(p.blocks)
+        self.self_kv = [torch.zeros((R, t_cap, 2 * d), dtype=dt, device=dev) for _ in range(L)]
+        self.x = _empty(R, d, dt, dev)
+        self.xn, self.q, self.att = _empty(R, d, dt, dev), _empty(R, d, dt, dev), _empty(R, d, dt, dev)
+        self.acc = _empty(R, d, dt, dev) if len(feats) > 1 else None
+        self.h = _empty(R, 4 * d, dt, dev)
+        self.v_pad = (p.n_vocab + 7) // 8 * 8
+        self.logits = torch.empty((R, self.v_pad), dtype=torch.float32, device=dev)
+        ws_bytes = nv.attention_decode_workspace_bytes(R, H)
+        self.ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        self.state = torch.zeros(8, dtype=torch.int32, device=dev)
+        self.tokens = torch.zeros((R, t_cap + 1), dtype=torch.int32, device=dev)
+        self.sum_logprobs = torch.zeros(R, dtype=torch.float32, device=dev)
+        self.no_speech_prob = torch.full((R,), float("nan"), dtype=torch.float32, device=dev)
+        self.use_graph = use_graph
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self._sampler = None
+
+    # -- one decoder pass for the token at position state[0]; logits of that position land in self.logits
+    def _forward_token(self):
+        p, d, H, G = self.p, self.p.d, self.p.n_head, self.G
+        st = self.state
+        nv.embed(self.tokens, self.tokens.shape[1], st, 0, p.tok_emb, p.pos_emb, self.x)
+        x, xn, q, att, h = self.x, self.xn, self.q, self.att, self.h
+        for l, bp in enumerate(p.blocks):
+            if self.gated:
+                multi = len(self.x_kv[l]) > 1
+                acc = x
+                if multi:
+                    self.acc.copy_(x)
+                    acc = self.acc
+                for i, kvx in enumerate(self.x_kv[l]):
+                    Tx = self.Tx[i]
+                    nv.layernorm(x, bp.x_ln[i].w, bp.x_ln[i].b, xn)
+                    nv.linear(xn, bp.x_attn[i].q_w, q, bias=bp.x_attn[i].q_b)
+                    nv.attention_decode(q, kvx[:, :d], kvx[:, d:], 2 * d, Tx * 2 * d, att, G, H, None, 0, Tx, self.ws)
+                    nv.linear(att, bp.x_attn[i].o_w, acc, bias=bp.x_attn[i].o_b, residual=acc, gate=bp.x_gate[i])
+                if multi:
+                    x.copy_(acc)
+                _mlp_inplace(x, xn, h, bp.ff_ln, bp.ff, gate=bp.ff_gate)
+            # causal self-attention over the cache; this token's K/V are appended by the GEMM epilogue
+            nv.layernorm(x, bp.attn_ln.w, bp.attn_ln.b, xn)
+            nv.linear(xn, bp.attn.q_w, q, bias=bp.attn.q_b)
+            kv = self.self_kv[l]
+            kv_rows = kv.view(self.R, self.T_cap * 2 * d)[:, : 2 * d]  # row r -> cache[r, 0, :], advanced by c_off
+            nv.linear(xn, bp.attn.kv_w, kv_rows, bias=bp.attn.kv_b, c_off_ptr=st, c_off_mul=2 * d)
+            kv2 = kv.view(self.R * self.T_cap, 2 * d)
+            nv.attention_decode(q, kv2[:, :d], kv2[:, d:], 2 * d, self.T_cap * 2 * d, att, 1, H, st, 1, self.T_cap,
+                                self.ws)
+            nv.linear(att, bp.attn.o_w, x, bias=bp.attn.o_b, residual=x)
+            # cross-attention to the encoder output (K/V cached per audio, shared by its G beams)
+            nv.layernorm(x, bp.cross_ln.w, bp.cross_ln.b, xn)
+            nv.linear(xn, bp.cross.q_w, q, bias=bp.cross.q_b)
+            ckv = self.cross_kv[l]
+            nv.attention_decode(q, ckv[:, :d], ckv[:, d:], 2 * d, self.Ta * 2 * d, att, G, H, None, 0, self.Ta,
+                                self.ws)
+            nv.linear(att, bp.cross.o_w, x, bias=bp.cross.o_b, residual=x)
+            _mlp_inplace(x, xn, h, bp.mlp_ln, bp.mlp)
+        nv.layernorm(x, p.ln.w, p.ln.b, xn)
+        nv.linear(xn, p.tok_emb_t, self.logits, n=p.n_vocab)
+
+    # -- greedy ---------------------------------------------------------------------------------------
+    def configure_greedy(self, initial_tokens: Sequence[int], sot_index: int, suppress: Tensor,
+                         suppress_first: Optional[Tensor], eot: int, no_speech: int, ts: Sequence[int]):
+        n_init = len(initial_tokens)
+        init = torch.tensor(list(initial_tokens), dtype=torch.int32, device=self.dev)
+        self.tokens.zero_()
+        self.tokens[:, :n_init] = init
+        self.state.copy_(torch.tensor([0, n_init, 0, 0, sot_index, 0, 0, 0], dtype=torch.int32))
+        self.sum_logprobs.zero_()
+        self.no_speech_prob.fill_(float("nan"))
+        self._sampler = (suppress, suppress_first, eot, no_speech, tuple(ts))
+        self.n_init = n_init
+
+    def _greedy_step(self):
+        self._forward_token()
+        suppress, suppress_first, eot, no_speech, ts = self._sampler
+        nv.sample_greedy(self.logits, self.p.n_vocab, suppress, suppress_first, self.tokens, self.state,
+                         self.sum_logprobs, self.no_speech_prob, eot, no_speech, ts)
+        nv.step_advance(self.state, self.R)
+
+    def run_greedy(self, n_sample: int, check_every: int = 8) -> int:
+        """Feeds the initial tokens and samples up to ``n_sample`` new ones; returns #graph launches."""
+        total = self.n_init - 1 + n_sample
+        assert self.n_init + n_sample <= self.tokens.shape[1]
+        launches = 0
+        if self.use_graph and self._graph is None:
+            # warm-up outside capture (lazy module init, cudaFuncSetAttribute), then restore the state
+            snap = (self.state.clone(), self.tokens.clone(), self.sum_logprobs.clone(), self.no_speech_prob.clone())
+            side = torch.cuda.Stream(device=self.dev)
+            side.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.stream(side):
+                self._greedy_step()
+            torch.cuda.current_stream(self.dev).wait_stream(side)
+            for dst, src in zip((self.state, self.tokens, self.sum_logprobs, self.no_speech_prob), snap):
+                dst.copy_(src)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._greedy_step()
+            # capture does not execute: state is still at t=0
+            self._graph = g
+        for i in range(total):
+            if self._graph is not None:
+                self._graph.replay()
+            else:
+                self._greedy_step()
+            launches += 1
+            sampled = i - (self.n_init - 1) + 1
+            if sampled > 0 and sampled % check_every == 0 and i + 1 < total:
+                if int(self.state[2].item()) != 0:  # every row has emitted EOT (decoding.py:296, 713)
+                    break
+        return launches
+
+    # -- beam search support (host-driven; see decoding.py) ---------------------------------------------
+    def forward_at(self, pos: int):
+        """Eager single-position pass used by the beam-search driver: sets state[0] = pos first."""
+        self.state[0] = pos
+        self._forward_token()
+
+    def reorder_self_kv(self, src_index: Tensor, used_positions: int):
+        d = self.p.d
+        elt = self.self_kv[0].element_size()
+        row_bytes = self.T_cap * 2 * d * elt
+        used = used_positions * 2 * d * elt
+        new = []
+        for kv in self.self_kv:
+            dst = torch.empty_like(kv)
+            nv.kv_gather_rows(kv, dst, src_index, self.R, row_bytes, used)
+            new.append(dst)
+        self.self_kv = new
+
+
+# ============================================================================ stand-alone sub-module calls
+@torch.no_grad()
+def standalone_layernorm(ln, x: Tensor) -> Tensor:
+    nv.require_cuda(x)
+    dt = _engine_dtype(x.dtype)
+    x2 = _to_dtype(x, dt).reshape(-1, x.shape[-1]).contiguous()
+    out = torch.empty_like(x2)
+    with torch.cuda.device(x.device):
+        nv.layernorm(x2, _f32(ln.weight), _f32(ln.bias), out, ln.eps)
+    return out.view(x.shape).to(x.dtype)
+
+
+@torch.no_grad()
+def standalone_linear(lin, x: Tensor) -> Tensor:
+    nv.require_cuda(x)
+    dt = _engine_dtype(x.dtype)
+    x2 = _to_dtype(x, dt).reshape(-1, x.shape[-1]).contiguous()
+    with torch.cuda.device(x.device):
+        w = _pack_w(lin.weight, dt)
+        out = _empty(x2.shape[0], w.shape[0], dt, x.device)
+        nv.linear(x2, w, out, bias=None if lin.bias is None else _f32(lin.bias))
+    return out.view(*x.shape[:-1], w.shape[0]).to(x.dtype)
+
+
+@torch.no_grad()
+def standalone_mha(mha, x: Tensor, xa: Optional[Tensor], causal: bool) -> Tensor:
+    """MultiHeadAttention.forward (reference model.py:71-91) without kv_cache."""
+    nv.require_cuda(x)
+    dt = _engine_dtype(x.dtype)
+    with torch.cuda.device(x.device):
+        mp = _pack_mha(mha, dt)
+        B, t, d = x.shape
+        src = x if xa is None else xa
+        Ts = src.shape[1]
+        x2 = _to_dtype(x, dt).reshape(B * t, d).contiguous()
+        s2 = x2 if xa is None else _to_dtype(xa, dt).reshape(B * Ts, d).contiguous()
+        q, kv = _empty(B * t, d, dt, x.device), _empty(B * Ts, 2 * d, dt, x.device)
+        nv.linear(x2, mp.q_w, q, bias=mp.q_b)
+        nv.linear(s2, mp.kv_w, kv, bias=mp.kv_b)
+        att = _empty(B * t, d, dt, x.device)
+        nv.attention(q, kv[:, :d], kv[:, d:], att, B, t, Ts, mha.n_head, causal=causal)
+        out = _empty(B * t, d, dt, x.device)
+        nv.linear(att, mp.o_w, out, bias=mp.o_b)
+    return out.view(B, t, d).to(x.dtype)

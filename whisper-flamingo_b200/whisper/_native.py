@@ -1,0 +1,289 @@
+"""ctypes binding of ``libwf.so`` (C ABI in ``include/wf.h``).
+
+There is no fallback: if the shared library is missing, or a call is made without a
+CUDA device, this module raises.  Torch is used only for device memory and streams -
+every function here takes torch CUDA tensors, checks them and forwards raw pointers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+WF_F32, WF_BF16 = 0, 1
+ACT_NONE, ACT_GELU = 0, 1
+LOGMEL_GLOBAL_MAX, LOGMEL_PER_CLIP_MAX = 0, 1
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "lib", "libwf.so")
+_lib = None
+
+
+class WfError(RuntimeError):
+    pass
+
+
+class _Epilogue(C.Structure):
+    _fields_ = [("C", C.c_void_p), ("ldc", C.c_longlong), ("bias", C.c_void_p), ("residual", C.c_void_p),
+                ("ldr", C.c_longlong), ("res_row_mod", C.c_int), ("gate", C.c_void_p), ("act", C.c_int),
+                ("out_f32", C.c_int), ("c_off_ptr", C.c_void_p), ("c_off_mul", C.c_longlong)]
+
+
+class _Sample(C.Structure):
+    _fields_ = [("logits", C.c_void_p), ("ld", C.c_longlong), ("R", C.c_int), ("V", C.c_int),
+                ("suppress", C.c_void_p), ("suppress_first", C.c_void_p), ("tokens", C.c_void_p),
+                ("T_cap", C.c_int), ("state", C.c_void_p), ("sum_logprobs", C.c_void_p),
+                ("no_speech_prob", C.c_void_p), ("eot", C.c_int), ("no_speech", C.c_int),
+                ("timestamp_begin", C.c_int), ("no_timestamps", C.c_int), ("max_initial_ts", C.c_int)]
+
+
+class _Topk(C.Structure):
+    _fields_ = [("logits", C.c_void_p), ("ld", C.c_longlong), ("R", C.c_int), ("V", C.c_int),
+                ("suppress", C.c_void_p), ("suppress_first", C.c_void_p), ("tokens", C.c_void_p),
+                ("T_cap", C.c_int), ("n_init", C.c_int), ("cur_len", C.c_int), ("eot", C.c_int),
+                ("timestamp_begin", C.c_int), ("no_timestamps", C.c_int), ("max_initial_ts", C.c_int),
+                ("k", C.c_int), ("out_vals", C.c_void_p), ("out_idx", C.c_void_p)]
+
+
+_SIGNATURES = {
+    "wf_version": (C.c_int, []),
+    "wf_last_error": (C.c_char_p, []),
+    "wf_device_sms": (C.c_int, []),
+    "wf_logmel_set_filters": (C.c_int, [C.c_int, C.c_void_p]),
+    "wf_logmel_workspace_bytes": (C.c_longlong, [C.c_int]),
+    "wf_logmel_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_void_p,
+                                C.c_void_p, C.c_void_p]),
+    "wf_linear": (C.c_int, [C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int,
+                            C.POINTER(_Epilogue), C.c_int, C.c_void_p]),
+    "wf_layernorm": (C.c_int, [C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong,
+                               C.c_int, C.c_int, C.c_float, C.c_void_p]),
+    "wf_im2col_k3": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong, C.c_int,
+                               C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "wf_embed": (C.c_int, [C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                           C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
+    "wf_add_rowmod": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_longlong,
+                                C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
+    "wf_cast": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
+    "wf_attention": (C.c_int, [C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong,
+                               C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "wf_attention_decode_workspace_bytes": (C.c_longlong, [C.c_int, C.c_int]),
+    "wf_attention_decode": (C.c_int, [C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_longlong,
+                                      C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                      C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p]),
+    "wf_sample_greedy": (C.c_int, [C.POINTER(_Sample), C.c_void_p]),
+    "wf_step_advance": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "wf_topk_logprobs": (C.c_int, [C.POINTER(_Topk), C.c_void_p]),
+    "wf_kv_gather_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_longlong,
+                                    C.c_void_p]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def lib_path() -> str:
+    return os.path.normpath(_LIB_PATH)
+
+
+def load() -> C.CDLL:
+    """Load libwf.so (no compute).  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        path = lib_path()
+        if not os.path.exists(path):
+            raise WfError(f"libwf.so not found at {path}: build it with `python __graft_entry__.py build` "
+                          f"(there is no CPU or PyTorch fallback for the hot path)")
+        lib = C.CDLL(path)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise WfError(f"libwf error {rc}: {load().wf_last_error().decode()}")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(*tensors: torch.Tensor) -> None:
+    if not torch.cuda.is_available():
+        raise WfError("the Whisper-Flamingo B200 engine needs a CUDA device (no CPU fallback exists)")
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise WfError(f"expected a CUDA tensor, got device {t.device}")
+
+
+def dtype_id(dt: torch.dtype) -> int:
+    if dt == torch.float32:
+        return WF_F32
+    if dt == torch.bfloat16:
+        return WF_BF16
+    raise WfError(f"unsupported engine dtype {dt} (float32 or bfloat16)")
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _row_stride(t: torch.Tensor) -> int:
+    assert t.dim() == 2 and t.stride(1) == 1, f"need a row-major 2-D view, got strides {t.stride()}"
+    return t.stride(0)
+
+
+# ----------------------------------------------------------------------------- wrappers
+_filters_loaded = set()
+
+
+def logmel_set_filters(n_mels: int, filters: torch.Tensor) -> None:
+    f = filters.detach().to("cpu", torch.float32).contiguous()
+    assert f.shape == (n_mels, 201)
+    _check(load().wf_logmel_set_filters(n_mels, f.data_ptr()))
+    _filters_loaded.add((torch.cuda.current_device(), n_mels))
+
+
+def logmel_filters_loaded(n_mels: int) -> bool:
+    return (torch.cuda.current_device(), n_mels) in _filters_loaded
+
+
+def logmel(pcm: torch.Tensor, n_mels: int, mode: int) -> torch.Tensor:
+    """pcm [B, N] fp32 CUDA -> [B, n_mels, N // 160] fp32."""
+    require_cuda(pcm)
+    assert pcm.dim() == 2 and pcm.dtype == torch.float32 and pcm.stride(1) == 1
+    b, n = pcm.shape
+    out = torch.empty((b, n_mels, n // 160), dtype=torch.float32, device=pcm.device)
+    ws = torch.empty(int(load().wf_logmel_workspace_bytes(b)), dtype=torch.uint8, device=pcm.device)
+    _check(load().wf_logmel_f32(pcm.data_ptr(), b, n, pcm.stride(0), n_mels, mode, out.data_ptr(), ws.data_ptr(),
+                                _stream()))
+    return out
+
+
+def linear(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias: Optional[torch.Tensor] = None,
+           residual: Optional[torch.Tensor] = None, res_row_mod: int = 0, gate: Optional[torch.Tensor] = None,
+           act: int = ACT_NONE, c_off_ptr: Optional[torch.Tensor] = None, c_off_mul: int = 0,
+           tile_hint: int = 0, n: Optional[int] = None) -> torch.Tensor:
+    """out[M,N] = residual + tanh(gate) * act(a[M,K] @ w[N,K]^T + bias).  All 2-D row-major views."""
+    m, k = a.shape
+    n_w, k_w = w.shape
+    n = n_w if n is None else n
+    assert k == k_w and a.dtype == w.dtype, (a.shape, w.shape, a.dtype, w.dtype)
+    dt = dtype_id(a.dtype)
+    out_f32 = int(dt == WF_BF16 and out.dtype == torch.float32)
+    if not out_f32:
+        assert out.dtype == a.dtype
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.is_contiguous() and bias.numel() >= n
+    if residual is not None:
+        assert residual.dtype == out.dtype
+    if gate is not None:
+        assert gate.dtype == torch.float32
+    ep = _Epilogue(out.data_ptr(), _row_stride(out), _ptr(bias), _ptr(residual),
+                   _row_stride(residual) if residual is not None else 0, res_row_mod, _ptr(gate), act, out_f32,
+                   _ptr(c_off_ptr), c_off_mul)
+    _check(load().wf_linear(dt, a.data_ptr(), _row_stride(a), w.data_ptr(), _row_stride(w), m, n, k, C.byref(ep),
+                            tile_hint, _stream()))
+    return out
+
+
+def layernorm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, out: torch.Tensor,
+              eps: float = 1e-5) -> torch.Tensor:
+    rows, d = x.shape
+    assert weight.dtype == torch.float32 and bias.dtype == torch.float32 and out.dtype == x.dtype
+    _check(load().wf_layernorm(dtype_id(x.dtype), x.data_ptr(), _row_stride(x), weight.data_ptr(), bias.data_ptr(),
+                               out.data_ptr(), _row_stride(out), rows, d, eps, _stream()))
+    return out
+
+
+def im2col_k3(x: torch.Tensor, sb: int, sc: int, st: int, b: int, c: int, t_in: int, stride: int,
+              out: torch.Tensor) -> torch.Tensor:
+    _check(load().wf_im2col_k3(dtype_id(x.dtype), dtype_id(out.dtype), x.data_ptr(), sb, sc, st, b, c, t_in, stride,
+                               out.data_ptr(), _stream()))
+    return out
+
+
+def embed(tokens: torch.Tensor, tok_stride: int, pos_ptr: Optional[torch.Tensor], pos_const: int,
+          tok_emb: torch.Tensor, pos_emb: torch.Tensor, out: torch.Tensor, n_pos: int = 1) -> torch.Tensor:
+    """out [R * n_pos, d]: row r*n_pos + j = tok_emb[tokens[r, pos + j]] + pos_emb[pos + j]."""
+    rows, d = out.shape
+    assert rows % n_pos == 0
+    assert tokens.dtype == torch.int32 and tok_emb.dtype == torch.float32 and pos_emb.dtype == torch.float32
+    assert tok_emb.is_contiguous() and pos_emb.is_contiguous()
+    _check(load().wf_embed(dtype_id(out.dtype), tokens.data_ptr(), tok_stride, _ptr(pos_ptr), pos_const, n_pos,
+                           tok_emb.data_ptr(), pos_emb.data_ptr(), out.data_ptr(), _row_stride(out), rows // n_pos, d,
+                           _stream()))
+    return out
+
+
+def add_rowmod(x: torch.Tensor, table: torch.Tensor, out: torch.Tensor, mod: int) -> torch.Tensor:
+    """out[r] = x[r] + table[r % mod]  (x, out 2-D row-major; table fp32 [>=mod, d] contiguous)."""
+    rows, d = x.shape
+    assert table.dtype == torch.float32 and table.is_contiguous() and table.shape[1] == d and table.shape[0] >= mod
+    _check(load().wf_add_rowmod(dtype_id(x.dtype), dtype_id(out.dtype), x.data_ptr(), _row_stride(x),
+                                table.data_ptr(), out.data_ptr(), _row_stride(out), rows, d, mod, _stream()))
+    return out
+
+
+def cast(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+    assert src.is_contiguous() and dst.is_contiguous() and src.numel() == dst.numel()
+    _check(load().wf_cast(dtype_id(src.dtype), dtype_id(dst.dtype), src.data_ptr(), dst.data_ptr(), src.numel(),
+                          _stream()))
+    return dst
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, b: int, tq: int, tk: int,
+              h: int, causal: bool) -> torch.Tensor:
+    """q [B*Tq, *], k/v [B*Tk, *], out [B*Tq, *] 2-D row-major views (column h*64.. is head h)."""
+    _check(load().wf_attention(dtype_id(q.dtype), q.data_ptr(), _row_stride(q), k.data_ptr(), _row_stride(k),
+                               v.data_ptr(), _row_stride(v), out.data_ptr(), _row_stride(out), b, tq, tk, h,
+                               int(causal), _stream()))
+    return out
+
+
+def attention_decode_workspace_bytes(r: int, h: int) -> int:
+    return int(load().wf_attention_decode_workspace_bytes(r, h))
+
+
+def attention_decode(q: torch.Tensor, kc: torch.Tensor, vc: torch.Tensor, ld_kv: int, kv_batch_stride: int,
+                     out: torch.Tensor, g: int, h: int, len_ptr: Optional[torch.Tensor], len_add: int,
+                     len_const: int, ws: Optional[torch.Tensor]) -> torch.Tensor:
+    r = q.shape[0]
+    _check(load().wf_attention_decode(dtype_id(q.dtype), q.data_ptr(), _row_stride(q), kc.data_ptr(), vc.data_ptr(),
+                                      ld_kv, kv_batch_stride, out.data_ptr(), _row_stride(out), r, g, h,
+                                      _ptr(len_ptr), len_add, len_const, _ptr(ws),
+                                      0 if ws is None else ws.numel() * ws.element_size(), _stream()))
+    return out
+
+
+def sample_greedy(logits: torch.Tensor, v: int, suppress: torch.Tensor, suppress_first: Optional[torch.Tensor],
+                  tokens: torch.Tensor, state: torch.Tensor, sum_logprobs: torch.Tensor,
+                  no_speech_prob: torch.Tensor, eot: int, no_speech: int, ts=(-1, -1, -1)) -> None:
+    """ts = (timestamp_begin | -1, no_timestamps | -1, max_initial_timestamp_index | -1)."""
+    assert logits.dtype == torch.float32 and tokens.dtype == torch.int32 and state.dtype == torch.int32
+    assert suppress.dtype == torch.uint8 and suppress.numel() >= v
+    a = _Sample(logits.data_ptr(), _row_stride(logits), logits.shape[0], v, suppress.data_ptr(),
+                _ptr(suppress_first), tokens.data_ptr(), tokens.shape[1], state.data_ptr(),
+                sum_logprobs.data_ptr(), no_speech_prob.data_ptr(), eot, no_speech, ts[0], ts[1], ts[2])
+    _check(load().wf_sample_greedy(C.byref(a), _stream()))
+
+
+def step_advance(state: torch.Tensor, r: int) -> None:
+    _check(load().wf_step_advance(state.data_ptr(), r, _stream()))
+
+
+def topk_logprobs(logits: torch.Tensor, v: int, suppress: torch.Tensor, suppress_first: Optional[torch.Tensor],
+                  tokens: Optional[torch.Tensor], n_init: int, cur_len: int, eot: int, ts, k: int,
+                  out_vals: torch.Tensor, out_idx: torch.Tensor) -> None:
+    a = _Topk(logits.data_ptr(), _row_stride(logits), logits.shape[0], v, suppress.data_ptr(), _ptr(suppress_first),
+              _ptr(tokens), 0 if tokens is None else tokens.shape[1], n_init, cur_len, eot, ts[0], ts[1], ts[2], k,
+              out_vals.data_ptr(), out_idx.data_ptr())
+    _check(load().wf_topk_logprobs(C.byref(a), _stream()))
+
+
+def kv_gather_rows(src: torch.Tensor, dst: torch.Tensor, index: torch.Tensor, r: int, row_bytes: int,
+                   used_bytes: int, src_off: int = 0, dst_off: int = 0) -> None:
+    assert index.dtype == torch.int32
+    _check(load().wf_kv_gather_rows(src.data_ptr() + src_off, dst.data_ptr() + dst_off, index.data_ptr(), r,
+                                    row_bytes, used_bytes, _stream()))
