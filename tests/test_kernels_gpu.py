@@ -1,0 +1,351 @@
+"""GPU parity tests, kernel level: every libwf entry point against a plain PyTorch fp32 (or numpy fp64)
+restatement of the same op, through the C ABI (ctypes)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import GOLDEN, SAMPLE_IDX
+from oracle import mel as omel
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def nv():
+    from whisper import _native
+    if not torch.cuda.is_available():
+        pytest.fail("GPU test selected but no CUDA device is visible")
+    _native.load()
+    return _native
+
+
+def _randn(*shape, dtype=torch.float32, seed=0, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to("cuda", dtype)
+
+
+# ----------------------------------------------------------------------------- log-mel (tolerance: 1e-4 abs, north star)
+@pytest.mark.parametrize("n_mels", [80, 128])
+def test_logmel_gaussian_and_chirp_vs_oracle_and_golden(nv, n_mels):
+    import whisper
+    from whisper._synthetic import synthetic_pcm
+    g = np.load(f"{GOLDEN}/mel.npz")
+    pcm = synthetic_pcm(2, seed=1234)
+    got = whisper.log_mel_spectrogram(pcm[0].cuda(), n_mels=n_mels)
+    assert got.shape == (n_mels, 3000) and got.dtype == torch.float32 and got.is_cuda
+    want = omel.log_mel_spectrogram(pcm[0].numpy(), n_mels)
+    assert np.abs(got.cpu().numpy() - want).max() <= 1e-4
+    idx = SAMPLE_IDX[SAMPLE_IDX < want.size]
+    assert np.abs(got.cpu().numpy().reshape(-1)[idx] - g[f"gauss{n_mels}_samples"]).max() <= 1e-4
+    chirp = torch.from_numpy(omel.chirp_kat()).cuda()
+    c = whisper.log_mel_spectrogram(chirp, n_mels=n_mels).cpu().numpy()
+    # 80 dB dynamic range: two correct fp32 implementations differ by ~1e-4 in the clamped floor bins, so the
+    # gate is against the fp64 oracle with the reference's own error (6.3e-5) + 5e-5 margin
+    assert np.abs(c - omel.log_mel_spectrogram(omel.chirp_kat(), n_mels)).max() <= 1.2e-4
+    assert abs((c.max() - c.min()) - 2.0) < 1e-5  # max-8 clamp binds: min == max - 8/4
+    assert np.abs(c.reshape(-1)[idx] - g[f"chirp{n_mels}_samples"]).max() <= 2e-4
+
+
+def test_logmel_batched_semantics_padding_and_cpu_input(nv):
+    import whisper
+    from whisper._synthetic import synthetic_pcm
+    g = np.load(f"{GOLDEN}/mel.npz")
+    pcm = synthetic_pcm(2, seed=1234)
+    two = torch.stack([pcm[0], pcm[1] * 1e-3])
+    b = whisper.log_mel_spectrogram(two.cuda(), n_mels=80).cpu().numpy()       # reference: global max
+    assert np.abs(b - omel.log_mel_spectrogram(two.numpy(), 80)).max() <= 1e-4
+    half = b.size // 2
+    idx = SAMPLE_IDX[SAMPLE_IDX < half]
+    got = np.concatenate([b.reshape(-1)[idx], b.reshape(-1)[half + idx]])
+    assert np.abs(got - g["batch2_global_samples"]).max() <= 1e-4
+    pc = whisper.log_mel_spectrogram(two.cuda(), n_mels=80, per_clip_max=True).cpu().numpy()
+    assert np.abs(pc - omel.log_mel_spectrogram(two.numpy(), 80, per_clip_max=True)).max() <= 1e-4
+    assert np.abs(pc[1] - b[1]).max() > 0.1
+    # padding + short ragged clip + numpy / CPU input staged through the GPU, result returned on CPU
+    sp = whisper.log_mel_spectrogram(pcm[0][:16000].numpy(), n_mels=80, padding=4800)
+    assert not sp.is_cuda and sp.shape == (80, 130)
+    assert np.abs(sp.numpy() - g["short_pad_full"]).max() <= 1e-4
+    odd = whisper.log_mel_spectrogram(pcm[0][:12345].cuda(), n_mels=80).cpu().numpy()   # 77 frames, ragged tail
+    assert odd.shape == (80, 77)
+    assert np.abs(odd - omel.log_mel_spectrogram(pcm[0][:12345].numpy(), 80)).max() <= 1e-4
+    assert whisper.log_mel_spectrogram(torch.zeros(80, 7)).shape == (80, 7)  # reference passthrough quirk
+    with pytest.raises(AssertionError):
+        whisper.log_mel_spectrogram(pcm[0].cuda(), n_mels=64)
+    with pytest.raises(RuntimeError):
+        whisper.log_mel_spectrogram(torch.zeros(100).cuda())  # reflect pad needs > 200 samples
+
+
+def test_logmel_large_batch_linearity_property(nv):
+    """Size-independent property at bench scale: scaling the PCM by 10 shifts log-mel by exactly 2/4 = 0.5."""
+    import whisper
+    from whisper._synthetic import synthetic_pcm
+    pcm = synthetic_pcm(64, seed=7).cuda()
+    a = whisper.log_mel_spectrogram(pcm, n_mels=80, per_clip_max=True)
+    b = whisper.log_mel_spectrogram(pcm * 10.0, n_mels=80, per_clip_max=True)
+    assert (b - a - 0.5).abs().max().item() <= 2e-5
+    one = whisper.log_mel_spectrogram(pcm[17], n_mels=80)
+    assert torch.equal(one, a[17])  # batched per-clip result is bit-identical to the single-clip call
+
+
+# ----------------------------------------------------------------------------- linear layers
+def _ref_linear(a, w, bias=None, act=0, gate=None, residual=None, res_row_mod=0):
+    v = a.float() @ w.float().t()
+    if bias is not None:
+        v = v + bias
+    if act == 1:
+        v = F.gelu(v)
+    if gate is not None:
+        v = v * torch.tanh(gate)
+    if residual is not None:
+        r = residual.float()
+        if res_row_mod:
+            r = r[torch.arange(v.shape[0], device=v.device) % res_row_mod]
+        v = v + r
+    return v
+
+
+@pytest.mark.parametrize("m,n,k,hint", [
+    (128, 256, 64, 0), (300, 384, 240, 0), (3000, 1280, 1280, 256), (1500, 1152, 768, 128), (16, 1280, 1280, 0),
+    (5, 51865, 384, 0), (129, 72, 200, 64), (640, 5120, 1280, 256), (100, 1280, 5120, 32),
+])
+def test_linear_bf16_tcgen05_vs_torch(nv, m, n, k, hint):
+    a = _randn(m, k, dtype=torch.bfloat16, seed=1)
+    w = _randn(n, k, dtype=torch.bfloat16, seed=2, scale=0.05)
+    out = torch.full((m, n), float("nan"), dtype=torch.bfloat16, device="cuda")
+    nv.linear(a, w, out, tile_hint=hint)
+    want = _ref_linear(a, w)
+    torch.cuda.synchronize()
+    err = (out.float() - want).abs().max().item()
+    assert err <= 2e-2 * max(1.0, want.abs().max().item()), err  # one bf16 rounding of the output
+    # fp32 output (logits path) is exact up to accumulation order
+    out32 = torch.empty((m, n), dtype=torch.float32, device="cuda")
+    nv.linear(a, w, out32, tile_hint=hint)
+    assert (out32 - want).abs().max().item() <= 1e-3 * max(1.0, want.abs().max().item())
+
+
+def test_linear_bf16_epilogues_and_strided_views(nv):
+    m, n, k = 200, 384, 384
+    a = _randn(m, k, dtype=torch.bfloat16, seed=3)
+    w = _randn(n, k, dtype=torch.bfloat16, seed=4, scale=0.05)
+    bias = _randn(n, seed=5)
+    gate = torch.tensor([0.5], device="cuda")
+    res = _randn(m, n, dtype=torch.bfloat16, seed=6)
+    pos = _randn(50, n, dtype=torch.bfloat16, seed=7)
+    for kw, ref_kw in [
+        (dict(bias=bias), dict(bias=bias)),
+        (dict(bias=bias, act=nv.ACT_GELU), dict(bias=bias, act=1)),
+        (dict(bias=bias, residual=res), dict(bias=bias, residual=res)),
+        (dict(bias=bias, act=nv.ACT_GELU, gate=gate, residual=res), dict(bias=bias, act=1, gate=gate, residual=res)),
+        (dict(bias=bias, act=nv.ACT_GELU, residual=pos, res_row_mod=50), dict(bias=bias, act=1, residual=pos, res_row_mod=50)),
+    ]:
+        out = torch.empty((m, n), dtype=torch.bfloat16, device="cuda")
+        nv.linear(a, w, out, **kw)
+        want = _ref_linear(a, w, **ref_kw)
+        assert (out.float() - want).abs().max().item() <= 3e-2 * max(1.0, want.abs().max().item()), kw.keys()
+    # in-place residual (x += f(x_n)) and column-sliced operands / outputs
+    x = res.clone()
+    nv.linear(a, w, x, bias=bias, residual=x)
+    assert (x.float() - _ref_linear(a, w, bias=bias, residual=res)).abs().max().item() <= 3e-2 * 4
+    big = _randn(m, 3 * k, dtype=torch.bfloat16, seed=8)
+    outbig = torch.zeros((m, 2 * n), dtype=torch.bfloat16, device="cuda")
+    nv.linear(big[:, k:2 * k], w, outbig[:, n:])
+    assert (outbig[:, n:].float() - _ref_linear(big[:, k:2 * k], w)).abs().max().item() <= 3e-2 * 4
+    assert outbig[:, :n].abs().max().item() == 0
+    # KV-cache append: output rows land at column offset p * c_off_mul read from device memory
+    cache = torch.zeros((m, 7, n), dtype=torch.bfloat16, device="cuda")
+    p = torch.tensor([3], dtype=torch.int32, device="cuda")
+    nv.linear(a, w, cache.view(m, 7 * n)[:, :n], bias=bias, c_off_ptr=p, c_off_mul=n)
+    assert (cache[:, 3].float() - _ref_linear(a, w, bias=bias)).abs().max().item() <= 3e-2 * 4
+    assert cache[:, :3].abs().max().item() == 0 and cache[:, 4:].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("m,n,k", [(1, 384, 384), (70, 130, 50), (3000, 384, 240), (64, 51865, 384)])
+def test_linear_f32_vs_torch(nv, m, n, k):
+    a, w = _randn(m, k, seed=1), _randn(n, k, seed=2, scale=0.05)
+    bias, gate, res = _randn(n, seed=3), torch.tensor([0.5], device="cuda"), _randn(m, n, seed=4)
+    out = torch.empty((m, n), device="cuda")
+    nv.linear(a, w, out, bias=bias, act=nv.ACT_GELU, gate=gate, residual=res)
+    want = _ref_linear(a, w, bias=bias, act=1, gate=gate, residual=res)
+    assert (out - want).abs().max().item() <= 2e-5 * max(1.0, want.abs().max().item())
+
+
+# ----------------------------------------------------------------------------- row-wise kernels
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("d", [384, 768, 1024, 1280, 100])
+def test_layernorm_vs_torch(nv, dtype, tol, d):
+    x = _randn(77, d, dtype=dtype, seed=1, scale=3.0)
+    w, b = 1 + 0.1 * _randn(d, seed=2), 0.1 * _randn(d, seed=3)
+    out = torch.empty_like(x)
+    nv.layernorm(x, w, b, out)
+    want = F.layer_norm(x.float(), (d,), w, b, 1e-5)
+    assert (out.float() - want).abs().max().item() <= tol * max(1.0, want.abs().max().item())
+
+
+def test_im2col_embed_addrow_cast(nv):
+    B, C, T = 2, 80, 301
+    mel = _randn(B, C, T, seed=1)
+    w = _randn(64, C, 3, seed=2, scale=0.1)
+    a1 = torch.empty((B * T, 3 * C), device="cuda")
+    nv.im2col_k3(mel, C * T, T, 1, B, C, T, 1, a1)
+    got = (a1 @ w.reshape(64, -1).t()).view(B, T, 64).permute(0, 2, 1)
+    assert (got - F.conv1d(mel, w, padding=1)).abs().max().item() <= 1e-4
+    h = _randn(B * T, 64, seed=3)                                   # NWC activations, stride-2 conv
+    w2 = _randn(32, 64, 3, seed=4, scale=0.1)
+    T2 = (T - 1) // 2 + 1
+    a2 = torch.empty((B * T2, 3 * 64), device="cuda")
+    nv.im2col_k3(h, T * 64, 1, 64, B, 64, T, 2, a2)
+    got = (a2 @ w2.reshape(32, -1).t()).view(B, T2, 32)
+    want = F.conv1d(h.view(B, T, 64).permute(0, 2, 1), w2, stride=2, padding=1).permute(0, 2, 1)
+    assert (got - want).abs().max().item() <= 1e-4
+    a1b = torch.empty((B * T, 3 * C), dtype=torch.bfloat16, device="cuda")
+    nv.im2col_k3(mel, C * T, T, 1, B, C, T, 1, a1b)
+    assert torch.equal(a1b, a1.bfloat16())
+    # embedding
+    tok_emb, pos_emb = _randn(1000, 384, seed=5), _randn(448, 384, seed=6)
+    toks = torch.randint(0, 1000, (3, 10), dtype=torch.int32, device="cuda")
+    out = torch.empty((3 * 10, 384), device="cuda")
+    nv.embed(toks, 10, None, 0, tok_emb, pos_emb, out, n_pos=10)
+    assert torch.equal(out.view(3, 10, 384), tok_emb[toks.long()] + pos_emb[:10])
+    pos = torch.tensor([4], dtype=torch.int32, device="cuda")
+    out1 = torch.empty((3, 384), dtype=torch.bfloat16, device="cuda")
+    nv.embed(toks, 10, pos, 0, tok_emb, pos_emb, out1)
+    assert torch.equal(out1, (tok_emb[toks[:, 4].long()] + pos_emb[4]).bfloat16())
+    # positional add + casts
+    x = _randn(20, 384, seed=7)
+    o = torch.empty((20, 384), dtype=torch.bfloat16, device="cuda")
+    nv.add_rowmod(x, pos_emb, o, 5)
+    assert torch.equal(o, (x + pos_emb[torch.arange(20, device="cuda") % 5]).bfloat16())
+    assert torch.equal(nv.cast(x, torch.empty_like(x, dtype=torch.bfloat16)), x.bfloat16())
+
+
+# ----------------------------------------------------------------------------- attention
+def _ref_attention(q, k, v, B, Tq, Tk, H, causal):
+    d = H * 64
+    qf = q.float().view(B, Tq, H, 64).permute(0, 2, 1, 3)
+    kf = k.float().view(B, Tk, H, 64).permute(0, 2, 1, 3)
+    vf = v.float().view(B, Tk, H, 64).permute(0, 2, 1, 3)
+    s = qf @ kf.transpose(-1, -2) * 0.125
+    if causal:
+        s = s + torch.full((Tq, Tk), float("-inf"), device=q.device).triu_(1)
+    return (s.softmax(-1) @ vf).permute(0, 2, 1, 3).reshape(B * Tq, d)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("B,Tq,Tk,H,causal", [(2, 1500, 1500, 6, False), (3, 37, 37, 6, True), (2, 8, 1500, 12, False),
+                                              (2, 70, 100, 6, False), (1, 130, 130, 20, True)])
+def test_attention_full_vs_torch(nv, dtype, tol, B, Tq, Tk, H, causal):
+    d = H * 64
+    qkv = _randn(B * Tq, 3 * d, dtype=dtype, seed=1)
+    kv = _randn(B * Tk, 2 * d, dtype=dtype, seed=2)
+    q = qkv[:, :d]
+    k, v = (qkv[:, d:2 * d], qkv[:, 2 * d:]) if Tq == Tk else (kv[:, :d], kv[:, d:])
+    out = torch.full((B * Tq, d), float("nan"), dtype=dtype, device="cuda")
+    nv.attention(q, k, v, out, B, Tq, Tk, H, causal)
+    want = _ref_attention(q, k, v, B, Tq, Tk, H, causal)
+    assert (out.float() - want).abs().max().item() <= tol
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("B,G,H,Tk,dyn", [(2, 1, 6, 1500, False), (16, 1, 12, 750, False), (3, 5, 16, 1500, False),
+                                          (4, 1, 6, 37, True), (1, 1, 6, 300, True), (2, 3, 6, 100, False)])
+def test_attention_decode_vs_torch(nv, dtype, tol, B, G, H, Tk, dyn):
+    d, R, cap = H * 64, B * G, 448
+    q = _randn(R, d, dtype=dtype, seed=1)
+    T_alloc = cap if dyn else Tk
+    kv = _randn(B * T_alloc, 2 * d, dtype=dtype, seed=2)
+    out = torch.full((R, d), float("nan"), dtype=dtype, device="cuda")
+    ws = torch.empty(nv.attention_decode_workspace_bytes(R, H), dtype=torch.uint8, device="cuda")
+    if dyn:
+        lp = torch.tensor([Tk - 1], dtype=torch.int32, device="cuda")
+        nv.attention_decode(q, kv[:, :d], kv[:, d:], 2 * d, T_alloc * 2 * d, out, G, H, lp, 1, cap, ws)
+    else:
+        nv.attention_decode(q, kv[:, :d], kv[:, d:], 2 * d, T_alloc * 2 * d, out, G, H, None, 0, Tk, ws)
+    kvv = kv.view(B, T_alloc, 2 * d)[:, :Tk]
+    k = kvv[..., :d].repeat_interleave(G, 0).reshape(R * Tk, d)
+    v = kvv[..., d:].repeat_interleave(G, 0).reshape(R * Tk, d)
+    want = _ref_attention(q, k, v, R, 1, Tk, H, False)
+    assert (out.float() - want).abs().max().item() <= tol
+
+
+# ----------------------------------------------------------------------------- sampling
+def test_sample_greedy_and_topk_vs_torch(nv):
+    R, V, eot, nosp = 6, 51865, 50257, 50362
+    logits = _randn(R, V + 7, seed=1, scale=2.0)
+    sup = torch.zeros(V, dtype=torch.uint8, device="cuda")
+    sup[[5, 17, nosp, 50258]] = 1
+    first = torch.zeros(V, dtype=torch.uint8, device="cuda")
+    first[[220, eot]] = 1
+    logits[0, 5] = 100.0      # suppressed max must be ignored
+    logits[1, 220] = 90.0     # blank is masked on the first sampled step only
+    logits[2, eot] = 80.0     # EOT masked on the first step
+    n_init = 4
+    tokens = torch.zeros((R, 16), dtype=torch.int32, device="cuda")
+    tokens[:, :n_init] = torch.tensor([50258, 50259, 50359, 50363], dtype=torch.int32)
+    state = torch.tensor([0, n_init, 0, 0, 0, 0, 0, 0], dtype=torch.int32, device="cuda")
+    slp = torch.zeros(R, device="cuda")
+    nsp = torch.full((R,), float("nan"), device="cuda")
+    # t = 0: SOT position -> only no_speech_prob is produced
+    nv.sample_greedy(logits, V, sup, first, tokens, state, slp, nsp, eot, nosp)
+    nv.step_advance(state, R)
+    want_nsp = logits[:, :V].softmax(-1)[:, nosp]
+    assert (nsp - want_nsp).abs().max().item() <= 1e-7 + 1e-4 * want_nsp.max().item()
+    assert slp.abs().max().item() == 0 and tokens[:, n_init:].abs().max().item() == 0
+    for _ in range(2):
+        nv.sample_greedy(logits, V, sup, first, tokens, state, slp, nsp, eot, nosp)
+        nv.step_advance(state, R)
+    assert state[0].item() == 3
+    # t = 3: first sampled token
+    nv.sample_greedy(logits, V, sup, first, tokens, state, slp, nsp, eot, nosp)
+    nv.step_advance(state, R)
+    masked = logits[:, :V].clone()
+    masked[:, sup.bool()] = -np.inf
+    masked[:, first.bool()] = -np.inf
+    want_tok = masked.argmax(-1)
+    want_lp = masked.log_softmax(-1).gather(1, want_tok[:, None])[:, 0]
+    assert tokens[:, n_init].tolist() == want_tok.tolist()
+    assert (slp - want_lp).abs().max().item() <= 1e-4
+    # t = 4: blank/EOT allowed again; make row 3 finish and row 4 already finished
+    logits[3, eot] = 95.0
+    tokens[4, n_init] = eot
+    before = slp.clone()
+    nv.sample_greedy(logits, V, sup, first, tokens, state, slp, nsp, eot, nosp)
+    nv.step_advance(state, R)
+    m2 = logits[:, :V].clone()
+    m2[:, sup.bool()] = -np.inf
+    want2 = m2.argmax(-1)
+    want2[4] = eot
+    assert tokens[:, n_init + 1].tolist() == want2.tolist()
+    assert tokens[3, n_init + 1].item() == eot and tokens[1, n_init + 1].item() == 220
+    assert slp[4].item() == before[4].item()  # finished rows stop accumulating
+    assert state[2].item() == 0               # not all rows at EOT
+    # ties resolve to the lowest index (torch.argmax convention)
+    logits2 = torch.zeros((R, V + 7), device="cuda")
+    nv.sample_greedy(logits2, V, sup, None, tokens, state, slp, nsp, eot, nosp)
+    assert tokens[0, n_init + 2].item() == 0 and tokens[4, n_init + 2].item() == eot
+    # top-k log-probabilities (beam search)
+    k = 6
+    vals = torch.empty((R, k), device="cuda")
+    idx = torch.empty((R, k), dtype=torch.int32, device="cuda")
+    nv.topk_logprobs(logits, V, sup, first, None, n_init, n_init + 3, eot, (-1, -1, -1), k, vals, idx)
+    tv, ti = m2.log_softmax(-1).topk(k)
+    assert idx.tolist() == ti.tolist() and (vals - tv).abs().max().item() <= 1e-4
+
+
+def test_kv_gather_rows(nv):
+    src = _randn(8, 10, 128, dtype=torch.bfloat16, seed=1)
+    dst = torch.zeros_like(src)
+    index = torch.tensor([3, 3, 0, 7, 1, 1, 1, 2], dtype=torch.int32, device="cuda")
+    nv.kv_gather_rows(src, dst, index, 8, 10 * 128 * 2, 4 * 128 * 2)
+    assert torch.equal(dst[:, :4], src[index.long(), :4]) and dst[:, 4:].abs().max().item() == 0
+
+
+def test_errors_are_reported_not_swallowed(nv):
+    a = _randn(8, 60, dtype=torch.bfloat16)        # K * 2 bytes = 120: not a multiple of 16 -> TMA cannot map it
+    w = _randn(8, 60, dtype=torch.bfloat16)
+    with pytest.raises(nv.WfError):
+        nv.linear(a, w, torch.empty((8, 8), dtype=torch.bfloat16, device="cuda"))
+    with pytest.raises(nv.WfError):
+        nv.logmel(torch.zeros(1, 100, device="cuda"), 80, 0)
