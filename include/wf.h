@@ -44,6 +44,8 @@ int wf_version(void);
 const char* wf_last_error(void);
 /* Number of SMs of the current device (148 on B200); also forces context/attribute initialisation. */
 int wf_device_sms(void);
+/* Number of kernels this library has launched (or recorded into a CUDA graph under capture) so far. */
+unsigned long long wf_kernel_launch_count(void);
 
 /* ---- log-mel frontend: whisper/audio.py:111-161 (log_mel_spectrogram) ------------------------- */
 /* Uploads the [n_mels, 201] fp32 mel filterbank (audio.py:92-108) from HOST memory; n_mels in {80,128}. */

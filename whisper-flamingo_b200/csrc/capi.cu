@@ -17,6 +17,9 @@ int cuda_fail(cudaError_t e, const char* what) {
   set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
   return WF_ERR_CUDA;
 }
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_add_fetch(&g_launches, 1ull, __ATOMIC_RELAXED); }
+
 int num_sms() {
   static int sms = 0;
   if (!sms) {
@@ -46,6 +49,7 @@ extern "C" {
 int wf_version(void) { return 100; }
 const char* wf_last_error(void) { return g_err; }
 int wf_device_sms(void) { return num_sms(); }
+unsigned long long wf_kernel_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 int wf_logmel_set_filters(int n_mels, const float* filters_host) {
   WF_REQUIRE(filters_host != nullptr, "wf_logmel_set_filters: null filters");

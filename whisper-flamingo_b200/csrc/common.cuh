@@ -32,7 +32,13 @@ int cuda_fail(cudaError_t e, const char* what);
     }                                  \
   } while (0)
 
-#define WF_CHECK_LAUNCH() WF_CHECK_CUDA(cudaPeekAtLastError())
+// every kernel launch goes through this: error check + launch accounting (wf_kernel_launch_count)
+void count_launch();
+#define WF_CHECK_LAUNCH()                   \
+  do {                                      \
+    ::wf::count_launch();                   \
+    WF_CHECK_CUDA(cudaPeekAtLastError());   \
+  } while (0)
 
 int num_sms();
 

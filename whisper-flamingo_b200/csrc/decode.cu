@@ -12,6 +12,7 @@
 // length, write offsets) is read from device memory so one captured CUDA graph serves every step.
 #include "common.cuh"
 #include "kernels.h"
+#include <stdlib.h>
 
 namespace wf {
 
@@ -194,10 +195,19 @@ static int launch_decode_attn(const T* q, long long ldq, const T* kc, const T* v
   const int kvb = R / NQ;
   const int blocks = kvb * H;
   const int max_tiles = (len_max + DT - 1) / DT;
-  int n_splits = (2 * num_sms() + blocks - 1) / blocks;
+  // Granularity: a (audio, head) item streams up to 1500 x 256 B; with one CTA per item a 2560-item grid is
+  // 1.08 waves of 148 x 16 resident CTAs and the tail wave costs ~45 %.  Split every item along the keys until
+  // the grid is >= 8 waves (or one 128-key tile per CTA); partial (m, l, o) triples are merged by a second kernel.
+  const long long want_ctas = 8LL * 16 * num_sms();
+  int n_splits = static_cast<int>((want_ctas + blocks - 1) / blocks);
+  if (const char* e = getenv("WF_DECODE_SPLITS")) { const int v = atoi(e); if (v > 0) n_splits = v; }
   if (n_splits > max_tiles) n_splits = max_tiles;
   if (n_splits > 32) n_splits = 32;
   if (n_splits < 1) n_splits = 1;
+  {  // drop empty splits: ceil(tiles / splits) tiles each
+    const int per = (max_tiles + n_splits - 1) / n_splits;
+    n_splits = (max_tiles + per - 1) / per;
+  }
   if (n_splits > 1)
     WF_REQUIRE(ws && ws_bytes >= static_cast<long long>(R) * H * n_splits * PART * (long long)sizeof(float),
                "attention_decode: workspace too small (need %lld bytes)",

@@ -12,6 +12,7 @@ Data layout in HBM
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence
 
@@ -426,8 +427,9 @@ class DecodeSession:
         self.tokens = torch.zeros((R, t_cap + 1), dtype=torch.int32, device=dev)
         self.sum_logprobs = torch.zeros(R, dtype=torch.float32, device=dev)
         self.no_speech_prob = torch.full((R,), float("nan"), dtype=torch.float32, device=dev)
-        self.use_graph = use_graph
+        self.use_graph = use_graph and os.environ.get("WF_NO_GRAPH", "0") != "1"
         self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self._graph_kernels = 0
         self._sampler = None
 
     # -- one decoder pass for the token at position state[0]; logits of that position land in self.logits
@@ -509,13 +511,16 @@ class DecodeSession:
             for dst, src in zip((self.state, self.tokens, self.sum_logprobs, self.no_speech_prob), snap):
                 dst.copy_(src)
             g = torch.cuda.CUDAGraph()
+            before = nv.kernel_launch_count()
             with torch.cuda.graph(g):
                 self._greedy_step()
-            # capture does not execute: state is still at t=0
+            # capture records but does not execute: state is still at t=0
+            self._graph_kernels = nv.kernel_launch_count() - before
             self._graph = g
         for i in range(total):
             if self._graph is not None:
                 self._graph.replay()
+                nv.note_graph_replay(self._graph_kernels)
             else:
                 self._greedy_step()
             launches += 1

@@ -50,6 +50,7 @@ _SIGNATURES = {
     "wf_version": (C.c_int, []),
     "wf_last_error": (C.c_char_p, []),
     "wf_device_sms": (C.c_int, []),
+    "wf_kernel_launch_count": (C.c_ulonglong, []),
     "wf_logmel_set_filters": (C.c_int, [C.c_int, C.c_void_p]),
     "wf_logmel_workspace_bytes": (C.c_longlong, [C.c_int]),
     "wf_logmel_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_void_p,
@@ -105,6 +106,50 @@ def _check(rc: int) -> None:
         raise WfError(f"libwf error {rc}: {load().wf_last_error().decode()}")
 
 
+_replayed_launches = 0
+
+
+def note_graph_replay(kernels_in_graph: int) -> None:
+    """A CUDA-graph replay launches kernels that never pass through the C entry points again."""
+    global _replayed_launches
+    _replayed_launches += kernels_in_graph
+
+
+def kernel_launch_count() -> int:
+    """Kernels launched by libwf so far: direct launches + kernels inside replayed CUDA graphs."""
+    return int(load().wf_kernel_launch_count()) + _replayed_launches
+
+
+# Optional per-call profiler used by bench.py: when set, every wrapper below brackets its launch with two
+# CUDA events on the launching stream and reports (family, work, start_event, end_event).
+_profiler = None
+
+
+def set_profiler(fn) -> None:
+    global _profiler
+    _profiler = fn
+
+
+class _Prof:
+    __slots__ = ("family", "work", "e0")
+
+    def __init__(self, family: str, **work):
+        self.family, self.work, self.e0 = family, work, None
+
+    def __enter__(self):
+        if _profiler is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.e0 is not None and exc[0] is None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _profiler(self.family, self.work, self.e0, e1)
+        return False
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -156,8 +201,9 @@ def logmel(pcm: torch.Tensor, n_mels: int, mode: int) -> torch.Tensor:
     b, n = pcm.shape
     out = torch.empty((b, n_mels, n // 160), dtype=torch.float32, device=pcm.device)
     ws = torch.empty(int(load().wf_logmel_workspace_bytes(b)), dtype=torch.uint8, device=pcm.device)
-    _check(load().wf_logmel_f32(pcm.data_ptr(), b, n, pcm.stride(0), n_mels, mode, out.data_ptr(), ws.data_ptr(),
-                                _stream()))
+    with _Prof("logmel", bytes=b * (n * 4 + n_mels * (n // 160) * 4)):
+        _check(load().wf_logmel_f32(pcm.data_ptr(), b, n, pcm.stride(0), n_mels, mode, out.data_ptr(),
+                                    ws.data_ptr(), _stream()))
     return out
 
 
@@ -183,8 +229,10 @@ def linear(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias: Optiona
     ep = _Epilogue(out.data_ptr(), _row_stride(out), _ptr(bias), _ptr(residual),
                    _row_stride(residual) if residual is not None else 0, res_row_mod, _ptr(gate), act, out_f32,
                    _ptr(c_off_ptr), c_off_mul)
-    _check(load().wf_linear(dt, a.data_ptr(), _row_stride(a), w.data_ptr(), _row_stride(w), m, n, k, C.byref(ep),
-                            tile_hint, _stream()))
+    fam = ("gemm_tc_bf16" if m > 256 else "gemm_tc_bf16_skinny") if dt == WF_BF16 else "gemm_f32"
+    with _Prof(fam, flops=2 * m * n * k, bytes=(m * k + n * k) * a.element_size() + m * n * out.element_size()):
+        _check(load().wf_linear(dt, a.data_ptr(), _row_stride(a), w.data_ptr(), _row_stride(w), m, n, k,
+                                C.byref(ep), tile_hint, _stream()))
     return out
 
 
@@ -192,15 +240,17 @@ def layernorm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, out: to
               eps: float = 1e-5) -> torch.Tensor:
     rows, d = x.shape
     assert weight.dtype == torch.float32 and bias.dtype == torch.float32 and out.dtype == x.dtype
-    _check(load().wf_layernorm(dtype_id(x.dtype), x.data_ptr(), _row_stride(x), weight.data_ptr(), bias.data_ptr(),
-                               out.data_ptr(), _row_stride(out), rows, d, eps, _stream()))
+    with _Prof("layernorm", bytes=2 * rows * d * x.element_size()):
+        _check(load().wf_layernorm(dtype_id(x.dtype), x.data_ptr(), _row_stride(x), weight.data_ptr(),
+                                   bias.data_ptr(), out.data_ptr(), _row_stride(out), rows, d, eps, _stream()))
     return out
 
 
 def im2col_k3(x: torch.Tensor, sb: int, sc: int, st: int, b: int, c: int, t_in: int, stride: int,
               out: torch.Tensor) -> torch.Tensor:
-    _check(load().wf_im2col_k3(dtype_id(x.dtype), dtype_id(out.dtype), x.data_ptr(), sb, sc, st, b, c, t_in, stride,
-                               out.data_ptr(), _stream()))
+    with _Prof("im2col", bytes=out.numel() * out.element_size() + b * c * t_in * x.element_size()):
+        _check(load().wf_im2col_k3(dtype_id(x.dtype), dtype_id(out.dtype), x.data_ptr(), sb, sc, st, b, c, t_in,
+                                   stride, out.data_ptr(), _stream()))
     return out
 
 
@@ -236,9 +286,11 @@ def cast(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, b: int, tq: int, tk: int,
               h: int, causal: bool) -> torch.Tensor:
     """q [B*Tq, *], k/v [B*Tk, *], out [B*Tq, *] 2-D row-major views (column h*64.. is head h)."""
-    _check(load().wf_attention(dtype_id(q.dtype), q.data_ptr(), _row_stride(q), k.data_ptr(), _row_stride(k),
-                               v.data_ptr(), _row_stride(v), out.data_ptr(), _row_stride(out), b, tq, tk, h,
-                               int(causal), _stream()))
+    with _Prof("attention_full", flops=4 * b * h * tq * tk * 64 // (2 if causal else 1),
+               bytes=(2 * b * tq + 2 * b * tk) * h * 64 * q.element_size()):
+        _check(load().wf_attention(dtype_id(q.dtype), q.data_ptr(), _row_stride(q), k.data_ptr(), _row_stride(k),
+                                   v.data_ptr(), _row_stride(v), out.data_ptr(), _row_stride(out), b, tq, tk, h,
+                                   int(causal), _stream()))
     return out
 
 
@@ -250,10 +302,14 @@ def attention_decode(q: torch.Tensor, kc: torch.Tensor, vc: torch.Tensor, ld_kv:
                      out: torch.Tensor, g: int, h: int, len_ptr: Optional[torch.Tensor], len_add: int,
                      len_const: int, ws: Optional[torch.Tensor]) -> torch.Tensor:
     r = q.shape[0]
-    _check(load().wf_attention_decode(dtype_id(q.dtype), q.data_ptr(), _row_stride(q), kc.data_ptr(), vc.data_ptr(),
-                                      ld_kv, kv_batch_stride, out.data_ptr(), _row_stride(out), r, g, h,
-                                      _ptr(len_ptr), len_add, len_const, _ptr(ws),
-                                      0 if ws is None else ws.numel() * ws.element_size(), _stream()))
+    # algorithmic bytes: K and V rows of every (audio, head) once; dynamic lengths are reported at their bound
+    dyn = len_ptr is not None  # growing self-attention cache: charged at half its bound (average over a decode)
+    with _Prof("attention_decode_self" if dyn else "attention_decode",
+               bytes=2 * (r // g) * h * 64 * (len_const // 2 if dyn else len_const) * q.element_size()):
+        _check(load().wf_attention_decode(dtype_id(q.dtype), q.data_ptr(), _row_stride(q), kc.data_ptr(),
+                                          vc.data_ptr(), ld_kv, kv_batch_stride, out.data_ptr(), _row_stride(out), r,
+                                          g, h, _ptr(len_ptr), len_add, len_const, _ptr(ws),
+                                          0 if ws is None else ws.numel() * ws.element_size(), _stream()))
     return out
 
 
@@ -266,7 +322,8 @@ def sample_greedy(logits: torch.Tensor, v: int, suppress: torch.Tensor, suppress
     a = _Sample(logits.data_ptr(), _row_stride(logits), logits.shape[0], v, suppress.data_ptr(),
                 _ptr(suppress_first), tokens.data_ptr(), tokens.shape[1], state.data_ptr(),
                 sum_logprobs.data_ptr(), no_speech_prob.data_ptr(), eot, no_speech, ts[0], ts[1], ts[2])
-    _check(load().wf_sample_greedy(C.byref(a), _stream()))
+    with _Prof("sample_greedy", bytes=2 * logits.shape[0] * v * 4):
+        _check(load().wf_sample_greedy(C.byref(a), _stream()))
 
 
 def step_advance(state: torch.Tensor, r: int) -> None:

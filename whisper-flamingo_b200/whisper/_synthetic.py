@@ -49,3 +49,21 @@ def synthetic_features(n_clips: int, n_frames: int = 750, dim: int = 1024, seed:
     g = torch.Generator(device="cpu")
     g.manual_seed(seed)
     return torch.randn(n_clips, n_frames, dim, generator=g)
+
+
+@torch.no_grad()
+def init_synthetic_fast_(model: torch.nn.Module, seed: int = 0) -> torch.nn.Module:
+    """Same distributions as ``init_synthetic_`` but drawn on the parameters' own device (benchmarks of the
+    big models: values need not be reproducible across devices, only well-conditioned)."""
+    for name, p in model.named_parameters():
+        g = torch.Generator(device=p.device)
+        g.manual_seed((seed * 1000003 + zlib.crc32(name.encode())) & 0x7FFFFFFF)
+        if name.endswith("attn_gate") or name.endswith("ff_gate"):
+            p.fill_(0.5)
+        elif name == "decoder.positional_embedding":
+            p.copy_(torch.randn(p.shape, generator=g, device=p.device) * 0.01)
+        elif p.dim() < 2 and name.endswith(".weight") and ("_ln" in name or ".ln" in name):
+            p.copy_(1.0 + torch.randn(p.shape, generator=g, device=p.device) * 0.02)
+        else:
+            p.copy_(torch.randn(p.shape, generator=g, device=p.device) * 0.02)
+    return model
