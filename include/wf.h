@@ -68,6 +68,14 @@ typedef struct {
   int out_f32;          /* WF_BF16 only: store fp32 (logits) */
   const int* c_off_ptr; /* device int p or NULL: C += p * c_off_mul elements (KV-cache append) */
   long long c_off_mul;
+  /* head-major output for K/V caches when hm_heads > 0 (then N == 64 * hm_heads, ldc ignored): element (m, n)
+   * goes to (((m / hm_rpb) * hm_heads + n / 64) * hm_T + m % hm_rpb) * 64 + n % 64, so that the K (or V) rows
+   * of one (batch, head) are contiguous 128-byte lines. */
+  int hm_heads, hm_T, hm_rpb;
+  /* optional split-K workspace (WF_BF16, M <= 256): >= 4096 bytes of ZEROED arrival counters followed by
+   * fp32 partial tiles; NULL disables split-K.  Must not be shared by concurrently running wf_linear calls. */
+  void* ws;
+  long long ws_bytes;
 } wf_epilogue_t;
 /* C = residual + tanh(gate) * act(A[M,K] . W[N,K]^T + bias).  tile_hint: 0 = auto, else N-tile 32/64/128/256. */
 int wf_linear(int dtype, const void* A, long long lda, const void* W, long long ldw, int M, int N, int K,
@@ -101,13 +109,15 @@ int wf_attention(int dtype, const void* q, long long ldq, const void* k, long lo
                  wf_stream_t stream);
 
 /* ---- one-token attention over cached K/V (replaces the per-step recompute of decoding.py:155-164) */
-/* q,o [R, *]; rows r = kvb*G + g share cache entry kvb (beams of one audio); K/V row j of entry kvb at
- * kc + kvb*kv_batch_stride + j*ld_kv; length = (*len_ptr + len_add) if len_ptr else len_const
+/* q,o [R, *]; rows r = kvb*G + g share cache entry kvb (beams of one audio); K/V row j of head h of entry kvb at
+ * kc + kvb*kv_batch_stride + h*kv_head_stride + j*ld_kv (row-interleaved cache: head stride 64, ld = 2d;
+ * head-major cache: head stride T*64, ld = 64); length = (*len_ptr + len_add) if len_ptr else len_const
  * (len_const must then hold the maximum possible length). */
 long long wf_attention_decode_workspace_bytes(int R, int H);
 int wf_attention_decode(int dtype, const void* q, long long ldq, const void* kc, const void* vc, long long ld_kv,
-                        long long kv_batch_stride, void* o, long long ldo, int R, int G, int H, const int* len_ptr,
-                        int len_add, int len_const, void* workspace, long long workspace_bytes, wf_stream_t stream);
+                        long long kv_batch_stride, long long kv_head_stride, void* o, long long ldo, int R, int G,
+                        int H, const int* len_ptr, int len_add, int len_const, void* workspace,
+                        long long workspace_bytes, wf_stream_t stream);
 
 /* ---- sampling: whisper/decoding.py:427-442 (SuppressBlank/SuppressTokens), :276-302 (GreedyDecoder),
  *      :697-701 (no_speech_prob), loop bookkeeping of :688-718 ------------------------------------ */

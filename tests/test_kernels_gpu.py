@@ -162,6 +162,53 @@ def test_linear_bf16_epilogues_and_strided_views(nv):
     assert cache[:, :3].abs().max().item() == 0 and cache[:, 4:].abs().max().item() == 0
 
 
+@pytest.mark.parametrize("m,n,k", [(128, 1280, 1280), (128, 1280, 5120), (16, 768, 3072), (130, 384, 1536), (5, 2560, 1280)])
+def test_linear_bf16_split_k_vs_torch(nv, m, n, k):
+    """Decode-shape GEMMs with the split-K workspace: partial tiles reduced by the last-arriving CTA; the
+    arrival counters must be back to zero afterwards (the same workspace is reused by every launch)."""
+    a = _randn(m, k, dtype=torch.bfloat16, seed=1)
+    w = _randn(n, k, dtype=torch.bfloat16, seed=2, scale=0.05)
+    bias, res = _randn(n, seed=3), _randn(m, n, dtype=torch.bfloat16, seed=4)
+    gate = torch.tensor([0.5], device="cuda")
+    ws = torch.zeros(4096 + 8 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    want = _ref_linear(a, w, bias=bias, act=1, gate=gate, residual=res)
+    for _ in range(3):
+        out = torch.full((m, n), float("nan"), dtype=torch.bfloat16, device="cuda")
+        nv.linear(a, w, out, bias=bias, act=nv.ACT_GELU, gate=gate, residual=res, ws=ws)
+        assert (out.float() - want).abs().max().item() <= 3e-2 * max(1.0, want.abs().max().item())
+        assert ws[:4096].view(torch.int32).abs().max().item() == 0
+    out32 = torch.empty((m, n), dtype=torch.float32, device="cuda")
+    nv.linear(a, w, out32, ws=ws)
+    ref = _ref_linear(a, w)
+    assert (out32 - ref).abs().max().item() <= 1e-3 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_linear_head_major_kv_output(nv, dtype):
+    """K/V projection written straight into a head-major cache [B, 2H, T, 64] (+ device-side append offset)."""
+    B, T, H, k = 3, 50, 6, 384
+    n = 2 * H * 64
+    a = _randn(B * T, k, dtype=dtype, seed=1)
+    w = _randn(n, k, dtype=dtype, seed=2, scale=0.05)
+    bias = _randn(n, seed=3)
+    cache = torch.zeros((B, 2 * H, T, 64), dtype=dtype, device="cuda")
+    nv.linear(a, w, cache.view(-1, 64), bias=bias, head_major=(2 * H, T, T))
+    want = _ref_linear(a, w, bias=bias).view(B, T, 2 * H, 64).permute(0, 2, 1, 3)
+    tol = 2e-5 if dtype == torch.float32 else 3e-2
+    assert (cache.float() - want).abs().max().item() <= tol * max(1.0, want.abs().max().item())
+    # decode-step append: one row per batch entry, position read from device memory
+    R, cap = 5, 20
+    a1 = _randn(R, k, dtype=dtype, seed=4)
+    self_kv = torch.zeros((R, 2 * H, cap, 64), dtype=dtype, device="cuda")
+    pos = torch.tensor([7], dtype=torch.int32, device="cuda")
+    ws = torch.zeros(4096 + 1024 * 1024, dtype=torch.uint8, device="cuda") if dtype == torch.bfloat16 else None
+    nv.linear(a1, w, self_kv.view(-1, 64), bias=bias, head_major=(2 * H, cap, 1), c_off_ptr=pos, c_off_mul=64, ws=ws)
+    want1 = _ref_linear(a1, w, bias=bias).view(R, 2 * H, 64)
+    assert (self_kv[:, :, 7].float() - want1).abs().max().item() <= tol * max(1.0, want1.abs().max().item())
+    self_kv[:, :, 7] = 0
+    assert self_kv.abs().max().item() == 0
+
+
 @pytest.mark.parametrize("m,n,k", [(1, 384, 384), (70, 130, 50), (3000, 384, 240), (64, 51865, 384)])
 def test_linear_f32_vs_torch(nv, m, n, k):
     a, w = _randn(m, k, seed=1), _randn(n, k, seed=2, scale=0.05)
@@ -251,18 +298,21 @@ def test_attention_full_vs_torch(nv, dtype, tol, B, Tq, Tk, H, causal):
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 2e-2)])
 @pytest.mark.parametrize("B,G,H,Tk,dyn", [(2, 1, 6, 1500, False), (16, 1, 12, 750, False), (3, 5, 16, 1500, False),
                                           (4, 1, 6, 37, True), (1, 1, 6, 300, True), (2, 3, 6, 100, False)])
-def test_attention_decode_vs_torch(nv, dtype, tol, B, G, H, Tk, dyn):
+@pytest.mark.parametrize("head_major", [False, True])
+def test_attention_decode_vs_torch(nv, dtype, tol, B, G, H, Tk, dyn, head_major):
     d, R, cap = H * 64, B * G, 448
     q = _randn(R, d, dtype=dtype, seed=1)
     T_alloc = cap if dyn else Tk
-    kv = _randn(B * T_alloc, 2 * d, dtype=dtype, seed=2)
+    kv = _randn(B * T_alloc, 2 * d, dtype=dtype, seed=2)   # row-interleaved reference layout [B*T, K | V]
     out = torch.full((R, d), float("nan"), dtype=dtype, device="cuda")
     ws = torch.empty(nv.attention_decode_workspace_bytes(R, H), dtype=torch.uint8, device="cuda")
-    if dyn:
-        lp = torch.tensor([Tk - 1], dtype=torch.int32, device="cuda")
-        nv.attention_decode(q, kv[:, :d], kv[:, d:], 2 * d, T_alloc * 2 * d, out, G, H, lp, 1, cap, ws)
+    lp = torch.tensor([Tk - 1], dtype=torch.int32, device="cuda") if dyn else None
+    len_args = (lp, 1, cap) if dyn else (None, 0, Tk)
+    if head_major:  # [B, 2H, T, 64]: K heads then V heads
+        hm = kv.view(B, T_alloc, 2 * H, 64).permute(0, 2, 1, 3).contiguous()
+        nv.attention_decode(q, hm, hm[:, H:], 64, 2 * H * T_alloc * 64, T_alloc * 64, out, G, H, *len_args, ws)
     else:
-        nv.attention_decode(q, kv[:, :d], kv[:, d:], 2 * d, T_alloc * 2 * d, out, G, H, None, 0, Tk, ws)
+        nv.attention_decode(q, kv[:, :d], kv[:, d:], 2 * d, T_alloc * 2 * d, 64, out, G, H, *len_args, ws)
     kvv = kv.view(B, T_alloc, 2 * d)[:, :Tk]
     k = kvv[..., :d].repeat_interleave(G, 0).reshape(R * Tk, d)
     v = kvv[..., d:].repeat_interleave(G, 0).reshape(R * Tk, d)

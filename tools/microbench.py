@@ -62,6 +62,10 @@ def skinny():
         for hint in (32, 64, 128):
             us = graph_timeit(lambda i: nv.linear(a, ws[i], out, tile_hint=hint), n_rot)
             row += f" bn{hint}: {us:6.2f}us {n * k * 2 / us / 1e3:6.0f}GB/s |"
+        skw = torch.zeros(4096 + 8 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+        for hint in (0, 32, 64):
+            us = graph_timeit(lambda i: nv.linear(a, ws[i], out, tile_hint=hint, ws=skw), n_rot)
+            row += f" splitK bn{hint}: {us:6.2f}us {n * k * 2 / us / 1e3:6.0f}GB/s |"
         if k == 1280:
             def pair(i):
                 nv.layernorm(x, w_ln, b_ln, xn)
@@ -112,8 +116,12 @@ def attn():
         row = f"B={B} H={H} Tk={Tk} G={G}: "
         for splits in (0, 1, 2, 4, 6, 12):
             os.environ["WF_DECODE_SPLITS"] = str(splits)
-            us = timeit(lambda i: nv.attention_decode(q, kvs[i][:, :d], kvs[i][:, d:], 2 * d, Tk * 2 * d, out, G, H,
+            us = timeit(lambda i: nv.attention_decode(q, kvs[i][:, :d], kvs[i][:, d:], 2 * d, Tk * 2 * d, 64, out, G, H,
                                                       None, 0, Tk, ws), n_rot)
+            hm = [kv.view(B, Tk, 2 * H, 64) for kv in kvs]  # same bytes viewed head-major [B, 2H, T, 64]
+            us_hm = timeit(lambda i: nv.attention_decode(q, hm[i].view(B, 2 * H, Tk, 64), hm[i].view(B, 2 * H, Tk, 64)[:, H:], 64,
+                                                         2 * H * Tk * 64, Tk * 64, out, G, H, None, 0, Tk, ws), n_rot)
+            row += f" [hm {us_hm:7.1f}us {B * Tk * 2 * d * 2 / us_hm / 1e3:6.0f}GB/s]"
             row += f" s{splits}: {us:7.1f}us {B * Tk * 2 * d * 2 / us / 1e3:6.0f}GB/s |"
         os.environ["WF_DECODE_SPLITS"] = "0"
         print(row, flush=True)

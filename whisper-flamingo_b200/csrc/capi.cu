@@ -36,6 +36,7 @@ static LinearEpilogue to_cpp(const wf_epilogue_t* e) {
   o.C = e->C; o.ldc = e->ldc; o.bias = e->bias; o.residual = e->residual; o.ldr = e->ldr;
   o.res_row_mod = e->res_row_mod; o.gate = e->gate; o.act = e->act; o.out_f32 = e->out_f32;
   o.c_off_ptr = e->c_off_ptr; o.c_off_mul = e->c_off_mul;
+  o.hm_heads = e->hm_heads; o.hm_T = e->hm_T; o.hm_rpb = e->hm_rpb; o.ws = e->ws; o.ws_bytes = e->ws_bytes;
   return o;
 }
 
@@ -115,11 +116,12 @@ int wf_attention(int dtype, const void* q, long long ldq, const void* k, long lo
 
 long long wf_attention_decode_workspace_bytes(int R, int H) { return attention_decode_workspace_bytes(R, H); }
 int wf_attention_decode(int dtype, const void* q, long long ldq, const void* kc, const void* vc, long long ld_kv,
-                        long long kv_batch_stride, void* o, long long ldo, int R, int G, int H, const int* len_ptr,
-                        int len_add, int len_const, void* workspace, long long workspace_bytes, wf_stream_t stream) {
+                        long long kv_batch_stride, long long kv_head_stride, void* o, long long ldo, int R, int G,
+                        int H, const int* len_ptr, int len_add, int len_const, void* workspace,
+                        long long workspace_bytes, wf_stream_t stream) {
   WF_REQUIRE(q && kc && vc && o, "wf_attention_decode: null buffer");
-  return attention_decode(dtype, q, ldq, kc, vc, ld_kv, kv_batch_stride, o, ldo, R, G, H, len_ptr, len_add, len_const,
-                          workspace, workspace_bytes, S(stream));
+  return attention_decode(dtype, q, ldq, kc, vc, ld_kv, kv_batch_stride, kv_head_stride, o, ldo, R, G, H, len_ptr,
+                          len_add, len_const, workspace, workspace_bytes, S(stream));
 }
 
 int wf_sample_greedy(const wf_sample_t* a, wf_stream_t stream) {

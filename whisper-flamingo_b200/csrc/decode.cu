@@ -33,8 +33,8 @@ __device__ __forceinline__ void ld8(const __nv_bfloat16* p, float (&v)[8]) {
 template <typename T, int NQ>
 __global__ void __launch_bounds__(DT)
 attn_decode_kernel(const T* __restrict__ q, long long ldq, const T* __restrict__ kc, const T* __restrict__ vc,
-                   long long ld_kv, long long kv_batch_stride, T* __restrict__ o, long long ldo, int H,
-                   const int* __restrict__ len_ptr, int len_add, int len_const, int n_splits,
+                   long long ld_kv, long long kv_batch_stride, long long kv_head_stride, T* __restrict__ o,
+                   long long ldo, int H, const int* __restrict__ len_ptr, int len_add, int len_const, int n_splits,
                    float* __restrict__ partials) {
   __shared__ float sq[NQ][HD];
   __shared__ float sp[NQ][DT];
@@ -55,8 +55,8 @@ attn_decode_kernel(const T* __restrict__ q, long long ldq, const T* __restrict__
   }
   __syncthreads();
 
-  const T* kbase = kc + kvb * kv_batch_stride + h * HD;
-  const T* vbase = vc + kvb * kv_batch_stride + h * HD;
+  const T* kbase = kc + kvb * kv_batch_stride + h * kv_head_stride;
+  const T* vbase = vc + kvb * kv_batch_stride + h * kv_head_stride;
   const int dgrp = lane & 7, ksub = lane >> 3;
 
   float m_run[NQ], l_run[NQ], acc[NQ][8];
@@ -166,6 +166,177 @@ attn_decode_kernel(const T* __restrict__ q, long long ldq, const T* __restrict__
   }
 }
 
+// ---- head-major bf16 variant: the K (V) rows of one (audio, head) are contiguous 128-byte lines, so a tile of
+// 128 keys is one contiguous 16 KB block.  Tiles are staged in shared memory by 1-D bulk copies (cp.async.bulk,
+// mbarrier completion) three stages ahead of the math: the memory system always has 2 CTAs x 3 x 32 KB = 192 KB in
+// flight per SM, independent of register pressure and of the softmax barriers.
+static constexpr int HM_KEYS = 128;
+static constexpr int HM_STAGES = 3;
+static constexpr int HM_TILE_BYTES = HM_KEYS * HD * 2;           // 16 KB of K (or V)
+static constexpr int HM_SMEM_BYTES = HM_STAGES * 2 * HM_TILE_BYTES + 128;
+
+template <int NQ>
+__global__ void __launch_bounds__(DT, 2)
+attn_decode_hm_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const __nv_bfloat16* __restrict__ kc,
+                      const __nv_bfloat16* __restrict__ vc, long long kv_batch_stride, long long kv_head_stride,
+                      __nv_bfloat16* __restrict__ o, long long ldo, int H, const int* __restrict__ len_ptr,
+                      int len_add, int len_const, int n_splits, float* __restrict__ partials) {
+  extern __shared__ uint8_t hm_raw[];
+  uint8_t* stage_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(hm_raw) + 127) & ~uintptr_t(127));
+  __shared__ __align__(8) uint64_t full_bar[HM_STAGES];
+  __shared__ __align__(16) float sq[NQ][HD];  // read as float4
+  __shared__ float sp[NQ][DT];
+  __shared__ float sred[NQ][DT / 32];
+  __shared__ float sacc[DT / 32][NQ][HD];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int kvb = blockIdx.x / H, h = blockIdx.x % H;
+  const int split = blockIdx.y;
+  const int len = len_ptr ? (*len_ptr + len_add) : len_const;
+  const int n_tiles = (len + HM_KEYS - 1) / HM_KEYS;
+  const int tiles_per_split = (n_tiles + n_splits - 1) / n_splits;
+  const int tile_begin = split * tiles_per_split;
+  const int tile_end = min(n_tiles, tile_begin + tiles_per_split);
+
+  const __nv_bfloat16* kbase = kc + kvb * kv_batch_stride + h * kv_head_stride;
+  const __nv_bfloat16* vbase = vc + kvb * kv_batch_stride + h * kv_head_stride;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < HM_STAGES; ++s) mbar_init(&full_bar[s], 1);
+    mbar_fence_init();
+  }
+  for (int i = tid; i < NQ * HD; i += DT) {
+    const int qi = i / HD, d = i % HD;
+    sq[qi][d] = __bfloat162float(q[(static_cast<long long>(kvb) * NQ + qi) * ldq + h * HD + d]) * 0.125f;
+  }
+  __syncthreads();
+
+  auto issue = [&](int tile, int stage) {
+    const int rows = min(HM_KEYS, len - tile * HM_KEYS);
+    const uint32_t bytes = static_cast<uint32_t>(rows) * HD * 2;
+    uint8_t* dst = stage_base + stage * 2 * HM_TILE_BYTES;
+    mbar_arrive_expect_tx(&full_bar[stage], 2 * bytes);
+    bulk_load_1d(dst, kbase + static_cast<long long>(tile) * HM_KEYS * HD, bytes, &full_bar[stage]);
+    bulk_load_1d(dst + HM_TILE_BYTES, vbase + static_cast<long long>(tile) * HM_KEYS * HD, bytes, &full_bar[stage]);
+  };
+  if (tid == 0) {
+    for (int s = 0; s < HM_STAGES; ++s)
+      if (tile_begin + s < tile_end) issue(tile_begin + s, s);
+  }
+
+  const int dgrp = lane & 7, ksub = lane >> 3;
+  float m_run[NQ], l_run[NQ], acc[NQ][8];
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) {
+    m_run[i] = -INFINITY;
+    l_run[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  }
+
+  for (int tile = tile_begin; tile < tile_end; ++tile) {
+    const int rel = tile - tile_begin;
+    const int stage = rel % HM_STAGES;
+    const uint32_t parity = (rel / HM_STAGES) & 1;
+    const uint8_t* ks = stage_base + stage * 2 * HM_TILE_BYTES;
+    const uint8_t* vs = ks + HM_TILE_BYTES;
+    mbar_wait(&full_bar[stage], parity);
+    // ---- scores: thread = key; 16-byte chunks visited in a lane-rotated order so a quarter-warp hits 8 banks groups
+    const int key = tile * HM_KEYS + tid;
+    float s[NQ];
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) s[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int cc = (j + tid) & 7;
+      const uint4 u = *reinterpret_cast<const uint4*>(ks + tid * 128 + cc * 16);
+      const float kf[8] = {bf16lo(u.x), bf16hi(u.x), bf16lo(u.y), bf16hi(u.y), bf16lo(u.z), bf16hi(u.z), bf16lo(u.w), bf16hi(u.w)};
+#pragma unroll
+      for (int i = 0; i < NQ; ++i) {
+        const float4 qa = *reinterpret_cast<const float4*>(&sq[i][cc * 8]);
+        const float4 qb = *reinterpret_cast<const float4*>(&sq[i][cc * 8 + 4]);
+        s[i] = fmaf(qa.x, kf[0], s[i]); s[i] = fmaf(qa.y, kf[1], s[i]); s[i] = fmaf(qa.z, kf[2], s[i]);
+        s[i] = fmaf(qa.w, kf[3], s[i]); s[i] = fmaf(qb.x, kf[4], s[i]); s[i] = fmaf(qb.y, kf[5], s[i]);
+        s[i] = fmaf(qb.z, kf[6], s[i]); s[i] = fmaf(qb.w, kf[7], s[i]);
+      }
+    }
+    if (key >= len) {
+#pragma unroll
+      for (int i = 0; i < NQ; ++i) s[i] = -INFINITY;  // stale smem rows of a partial tile
+    }
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) {
+      const float wm = warp_max(s[i]);
+      if (lane == 0) sred[i][warp] = wm;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) {
+      float tm = sred[i][0];
+#pragma unroll
+      for (int w = 1; w < DT / 32; ++w) tm = fmaxf(tm, sred[i][w]);
+      const float mn = fmaxf(m_run[i], tm);
+      const float corr = expf(m_run[i] - mn);
+      m_run[i] = mn;
+      const float p = expf(s[i] - mn);
+      sp[i][tid] = p;
+      l_run[i] = l_run[i] * corr + p;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] *= corr;
+    }
+    __syncthreads();
+    // ---- acc += P V from shared memory: warp w takes keys [32w, 32w+32), 4 keys x 8 dim-groups per instruction
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+      const int kt = warp * 32 + kk * 4 + ksub;
+      if (tile * HM_KEYS + kt < len) {
+        const uint4 u = *reinterpret_cast<const uint4*>(vs + kt * 128 + dgrp * 16);
+        const float vf[8] = {bf16lo(u.x), bf16hi(u.x), bf16lo(u.y), bf16hi(u.y), bf16lo(u.z), bf16hi(u.z), bf16lo(u.w), bf16hi(u.w)};
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) {
+          const float p = sp[i][kt];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(p, vf[j], acc[i][j]);
+        }
+      }
+    }
+    __syncthreads();  // every thread is done with this stage (and with sp / sred)
+    if (tid == 0 && tile + HM_STAGES < tile_end) issue(tile + HM_STAGES, stage);
+  }
+
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) {
+    const float wl = warp_sum(l_run[i]);
+    if (lane == 0) sred[i][warp] = wl;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float a = acc[i][j];
+      a += __shfl_xor_sync(0xffffffffu, a, 8);
+      a += __shfl_xor_sync(0xffffffffu, a, 16);
+      acc[i][j] = a;
+    }
+    if (ksub == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sacc[warp][i][dgrp * 8 + j] = acc[i][j];
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < NQ * HD; idx += DT) {
+    const int i = idx / HD, d = idx % HD;
+    float a = 0.f, l = 0.f;
+#pragma unroll
+    for (int w = 0; w < DT / 32; ++w) { a += sacc[w][i][d]; l += sred[i][w]; }
+    const long long row = static_cast<long long>(kvb) * NQ + i;
+    if (n_splits == 1) {
+      o[row * ldo + h * HD + d] = __float2bfloat16_rn(a / l);
+    } else {
+      float* pp = partials + ((row * H + h) * n_splits + split) * PART;
+      pp[2 + d] = a;
+      if (d == 0) { pp[0] = m_run[i]; pp[1] = l; }
+    }
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(HD)
 attn_decode_combine_kernel(const float* __restrict__ partials, T* __restrict__ o, long long ldo, int H, int n_splits) {
@@ -190,7 +361,8 @@ long long attention_decode_workspace_bytes(int R, int H) {
 
 template <typename T, int NQ>
 static int launch_decode_attn(const T* q, long long ldq, const T* kc, const T* vc, long long ld_kv,
-                              long long kv_batch_stride, T* o, long long ldo, int R, int H, const int* len_ptr,
+                              long long kv_batch_stride, long long kv_head_stride, T* o, long long ldo, int R, int H,
+                              const int* len_ptr,
                               int len_add, int len_max, float* ws, long long ws_bytes, cudaStream_t stream) {
   const int kvb = R / NQ;
   const int blocks = kvb * H;
@@ -212,9 +384,35 @@ static int launch_decode_attn(const T* q, long long ldq, const T* kc, const T* v
     WF_REQUIRE(ws && ws_bytes >= static_cast<long long>(R) * H * n_splits * PART * (long long)sizeof(float),
                "attention_decode: workspace too small (need %lld bytes)",
                static_cast<long long>(R) * H * n_splits * PART * (long long)sizeof(float));
+  if constexpr (sizeof(T) == 2) {
+    // head-major cache + long key range: bulk-copy pipelined kernel, one CTA streams a whole (audio, head) item
+    // (measured: 5.8 TB/s unsplit vs 4.0 TB/s when the item is cut into 12 one-tile CTAs - the pipeline needs depth)
+    if (ld_kv == HD && len_max >= 512 && getenv("WF_DECODE_NO_BULK") == nullptr) {
+      int hs = 1;
+      if (const char* e = getenv("WF_DECODE_SPLITS")) { const int v = atoi(e); if (v > 0) hs = v < max_tiles ? v : max_tiles; }
+      if (hs > 1)
+        WF_REQUIRE(ws && ws_bytes >= static_cast<long long>(R) * H * hs * PART * (long long)sizeof(float),
+                   "attention_decode: workspace too small");
+      static bool configured = false;
+      if (!configured) {
+        WF_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_hm_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           HM_SMEM_BYTES));
+        configured = true;
+      }
+      dim3 hgrid(blocks, hs);
+      attn_decode_hm_kernel<NQ><<<hgrid, DT, HM_SMEM_BYTES, stream>>>(q, ldq, kc, vc, kv_batch_stride, kv_head_stride,
+                                                                     o, ldo, H, len_ptr, len_add, len_max, hs, ws);
+      WF_CHECK_LAUNCH();
+      if (hs > 1) {
+        attn_decode_combine_kernel<T><<<R * H, HD, 0, stream>>>(ws, o, ldo, H, hs);
+        WF_CHECK_LAUNCH();
+      }
+      return WF_OK;
+    }
+  }
   dim3 grid(blocks, n_splits);
-  attn_decode_kernel<T, NQ><<<grid, DT, 0, stream>>>(q, ldq, kc, vc, ld_kv, kv_batch_stride, o, ldo, H, len_ptr,
-                                                     len_add, len_max, n_splits, ws);
+  attn_decode_kernel<T, NQ><<<grid, DT, 0, stream>>>(q, ldq, kc, vc, ld_kv, kv_batch_stride, kv_head_stride, o, ldo,
+                                                     H, len_ptr, len_add, len_max, n_splits, ws);
   WF_CHECK_LAUNCH();
   if (n_splits > 1) {
     attn_decode_combine_kernel<T><<<R * H, HD, 0, stream>>>(ws, o, ldo, H, n_splits);
@@ -225,13 +423,15 @@ static int launch_decode_attn(const T* q, long long ldq, const T* kc, const T* v
 
 template <typename T>
 static int dispatch_decode_attn(const void* q, long long ldq, const void* kc, const void* vc, long long ld_kv,
-                                long long kv_batch_stride, void* o, long long ldo, int R, int G, int H,
+                                long long kv_batch_stride, long long kv_head_stride, void* o, long long ldo, int R,
+                                int G, int H,
                                 const int* len_ptr, int len_add, int len_max, void* ws, long long ws_bytes,
                                 cudaStream_t stream) {
 #define WF_DA(NQ)                                                                                              \
   case NQ:                                                                                                     \
     return launch_decode_attn<T, NQ>((const T*)q, ldq, (const T*)kc, (const T*)vc, ld_kv, kv_batch_stride,     \
-                                     (T*)o, ldo, R, H, len_ptr, len_add, len_max, (float*)ws, ws_bytes, stream)
+                                     kv_head_stride, (T*)o, ldo, R, H, len_ptr, len_add, len_max, (float*)ws,  \
+                                     ws_bytes, stream)
   switch (G) {
     WF_DA(1); WF_DA(2); WF_DA(3); WF_DA(4); WF_DA(5); WF_DA(6); WF_DA(8);
     default:
@@ -242,20 +442,22 @@ static int dispatch_decode_attn(const void* q, long long ldq, const void* kc, co
 }
 
 int attention_decode(int dtype, const void* q, long long ldq, const void* kc, const void* vc, long long ld_kv,
-                     long long kv_batch_stride, void* o, long long ldo, int R, int G, int H, const int* len_ptr,
-                     int len_add, int len_const, void* workspace, long long workspace_bytes, cudaStream_t stream) {
+                     long long kv_batch_stride, long long kv_head_stride, void* o, long long ldo, int R, int G, int H,
+                     const int* len_ptr, int len_add, int len_const, void* workspace, long long workspace_bytes,
+                     cudaStream_t stream) {
   WF_REQUIRE(R > 0 && G > 0 && H > 0 && R % G == 0, "attention_decode: bad shape R=%d G=%d H=%d", R, G, H);
   WF_REQUIRE(len_const > 0, "attention_decode: len (or max len) must be positive");
   const int al = dtype == WF_BF16 ? 8 : 4;
-  WF_REQUIRE(ld_kv % al == 0 && kv_batch_stride % al == 0, "attention_decode: K/V strides must keep 16-byte alignment");
+  WF_REQUIRE(ld_kv % al == 0 && kv_batch_stride % al == 0 && kv_head_stride % al == 0,
+             "attention_decode: K/V strides must keep 16-byte alignment");
   WF_REQUIRE((reinterpret_cast<uintptr_t>(kc) & 15) == 0 && (reinterpret_cast<uintptr_t>(vc) & 15) == 0,
              "attention_decode: K/V base must be 16-byte aligned");
   if (dtype == WF_F32)
-    return dispatch_decode_attn<float>(q, ldq, kc, vc, ld_kv, kv_batch_stride, o, ldo, R, G, H, len_ptr, len_add,
-                                       len_const, workspace, workspace_bytes, stream);
+    return dispatch_decode_attn<float>(q, ldq, kc, vc, ld_kv, kv_batch_stride, kv_head_stride, o, ldo, R, G, H,
+                                       len_ptr, len_add, len_const, workspace, workspace_bytes, stream);
   if (dtype == WF_BF16)
-    return dispatch_decode_attn<__nv_bfloat16>(q, ldq, kc, vc, ld_kv, kv_batch_stride, o, ldo, R, G, H, len_ptr,
-                                               len_add, len_const, workspace, workspace_bytes, stream);
+    return dispatch_decode_attn<__nv_bfloat16>(q, ldq, kc, vc, ld_kv, kv_batch_stride, kv_head_stride, o, ldo, R, G,
+                                               H, len_ptr, len_add, len_const, workspace, workspace_bytes, stream);
   WF_REQUIRE(false, "attention_decode: bad dtype %d", dtype);
 }
 

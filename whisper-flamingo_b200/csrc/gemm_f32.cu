@@ -95,7 +95,14 @@ gemm_f32_kernel(const float* __restrict__ A, long long lda, const float* __restr
       if (ep.act == 1) v = gelu_erf(v);
       if (ep.gate) v *= gate;
       if (R) v += R[rr * ep.ldr + n];
-      C[static_cast<long long>(m) * ep.ldc + n] = v;
+      long long off;
+      if (ep.hm_heads > 0) {
+        const int b = m / ep.hm_rpb, t = m - b * ep.hm_rpb;
+        off = (static_cast<long long>(b * ep.hm_heads + (n >> 6)) * ep.hm_T + t) * 64 + (n & 63);
+      } else {
+        off = static_cast<long long>(m) * ep.ldc + n;
+      }
+      C[off] = v;
     }
   }
 }
@@ -103,6 +110,9 @@ gemm_f32_kernel(const float* __restrict__ A, long long lda, const float* __restr
 int linear_f32(const float* A, long long lda, const float* W, long long ldw, int M, int N, int K,
                const LinearEpilogue& e, cudaStream_t stream) {
   WF_REQUIRE(M > 0 && N > 0 && K > 0, "linear_f32: empty problem M=%d N=%d K=%d", M, N, K);
+  if (e.hm_heads > 0)
+    WF_REQUIRE(N % 64 == 0 && e.hm_heads * 64 == N && e.hm_T > 0 && e.hm_rpb > 0 && !e.residual,
+               "linear_f32: bad head-major output spec");
   dim3 grid((M + FT - 1) / FT, (N + FT - 1) / FT);
   WF_REQUIRE(grid.y <= 65535, "linear_f32: N=%d too large for this kernel", N);
   gemm_f32_kernel<<<grid, 256, 0, stream>>>(A, lda, W, ldw, M, N, K, e);

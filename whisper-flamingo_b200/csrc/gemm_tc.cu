@@ -30,11 +30,15 @@ struct TcCfg {
   static constexpr int ACC_STAGES = 2;
   static constexpr int TMEM_COLS_RAW = ACC_STAGES * BN;
   static constexpr int TMEM_COLS = TMEM_COLS_RAW <= 32 ? 32 : TMEM_COLS_RAW <= 64 ? 64 : TMEM_COLS_RAW <= 128 ? 128 : TMEM_COLS_RAW <= 256 ? 256 : 512;
-  static constexpr int BAR_BYTES = (2 * STAGES + 2 * ACC_STAGES) * 8 + 16;
+  static constexpr int BAR_BYTES = (2 * STAGES + 2 * ACC_STAGES) * 8 + 32;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment slack
   static_assert(TMEM_COLS_RAW <= 512, "accumulators do not fit TMEM");
   static_assert(B_BYTES % 1024 == 0, "B stage must keep 1024-B alignment");
 };
+
+static constexpr int TC_THREADS = 384;      // 4 control warps + 8 epilogue warps
+static constexpr int EPI_THREADS = 256;
+static constexpr int SPLITK_COUNTER_BYTES = 4096;  // 1024 per-tile arrival counters at the head of the workspace
 
 struct TcEpilogue {
   void* C;
@@ -48,10 +52,91 @@ struct TcEpilogue {
   int out_f32;
   const int* c_off_ptr;
   long long c_off_mul;
+  // head-major output (K/V caches): element (m, n) -> ((m / hm_rpb) * hm_heads + n / 64) * hm_T + m % hm_rpb) * 64 + n % 64
+  int hm_heads, hm_T, hm_rpb;
+  // split-K: S k-slices per tile; fp32 partials + arrival counters in `ws`, the last-arriving CTA finishes the tile
+  int splits;
+  float* ws_part;
+  int* ws_count;
 };
 
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// bias / GELU / gate / residual / convert / store for 32 consecutive columns of one output row
+__device__ __forceinline__ void finish_chunk(float (&v)[32], const TcEpilogue& ep, int m, long long res_row, int n0,
+                                             int N, float gate, long long c_off) {
+  const bool full = (n0 + 32 <= N);
+  if (ep.bias) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] += (full || n0 + j < N) ? __ldg(ep.bias + n0 + j) : 0.f;
+  }
+  if (ep.act == 1) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+  }
+  if (ep.gate) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= gate;
+  }
+  long long off;
+  if (ep.hm_heads > 0) {
+    const int b = m / ep.hm_rpb, t = m - b * ep.hm_rpb;
+    off = (static_cast<long long>(b * ep.hm_heads + (n0 >> 6)) * ep.hm_T + t) * 64 + (n0 & 63);
+  } else {
+    off = static_cast<long long>(m) * ep.ldc + n0;
+  }
+  if (ep.out_f32) {
+    float* crow = reinterpret_cast<float*>(ep.C) + c_off + off;
+    if (ep.residual) {
+      const float* rrow = reinterpret_cast<const float*>(ep.residual) + res_row * ep.ldr + n0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (full || n0 + j < N) v[j] += rrow[j];
+    }
+    if (full && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (n0 + j < N) crow[j] = v[j];
+    }
+  } else {
+    __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(ep.C) + c_off + off;
+    if (ep.residual) {
+      const __nv_bfloat16* rrow = reinterpret_cast<const __nv_bfloat16*>(ep.residual) + res_row * ep.ldr + n0;
+      if (full && ((reinterpret_cast<uintptr_t>(rrow) & 15) == 0)) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          const uint4 u = *reinterpret_cast<const uint4*>(rrow + j);
+          v[j + 0] += bf16lo(u.x); v[j + 1] += bf16hi(u.x);
+          v[j + 2] += bf16lo(u.y); v[j + 3] += bf16hi(u.y);
+          v[j + 4] += bf16lo(u.z); v[j + 5] += bf16hi(u.z);
+          v[j + 6] += bf16lo(u.w); v[j + 7] += bf16hi(u.w);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (n0 + j < N) v[j] += __bfloat162float(rrow[j]);
+      }
+    }
+    if (full && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint4 u;
+        u.x = pack_bf16(v[j + 0], v[j + 1]);
+        u.y = pack_bf16(v[j + 2], v[j + 3]);
+        u.z = pack_bf16(v[j + 4], v[j + 5]);
+        u.w = pack_bf16(v[j + 6], v[j + 7]);
+        *reinterpret_cast<uint4*>(crow + j) = u;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (n0 + j < N) crow[j] = __float2bfloat16_rn(v[j]);
+    }
+  }
+}
+
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                int M, int N, int K, TcEpilogue ep) {
   using Cfg = TcCfg<BN, STAGES>;
@@ -65,6 +150,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* tfull_bar = bars + 2 * STAGES;
   uint64_t* tempty_bar = bars + 2 * STAGES + Cfg::ACC_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * Cfg::ACC_STAGES);
+  volatile int* last_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -73,6 +159,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int n_tiles = (N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
   const int k_blocks = (K + BK - 1) / BK;
+  const int S = ep.splits;
+  const int kb_per = (k_blocks + S - 1) / S;
+  const int num_items = num_tiles * S;  // item = tile * S + split (splits of a tile run on neighbouring CTAs)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -85,7 +174,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     for (int i = 0; i < Cfg::ACC_STAGES; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 128);
+      mbar_init(&tempty_bar[i], EPI_THREADS);
     }
     mbar_fence_init();
   }
@@ -99,9 +188,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const int tile = item / S, split = item - tile * S;
       const int n_blk = tile % n_tiles, m_blk = tile / n_tiles;
-      for (int kb = 0; kb < k_blocks; ++kb) {
+      const int kb0 = split * kb_per, kb1 = min(k_blocks, kb0 + kb_per);
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
         tma_load_2d(smem_a + stage * Cfg::A_BYTES, &map_a, &full_bar[stage], kb * BK, m_blk * BM);
@@ -115,13 +206,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      const int split = item % S;
+      const int kb0 = split * kb_per, kb1 = min(k_blocks, kb0 + kb_per);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * BN;
-      for (int kb = 0; kb < k_blocks; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(smem_a + stage * Cfg::A_BYTES));
@@ -129,104 +222,98 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
         for (int k = 0; k < BK / UMMA_K; ++k) {
           // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the (addr >> 4) field
-          umma_f16(tmem_d, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          umma_f16(tmem_d, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
         }
         umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
-        if (kb == k_blocks - 1) umma_commit(&tfull_bar[acc]);
+        if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------ epilogue (128 threads = 128 TMEM lanes)
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ------------------------------------------------------------ epilogue: 8 warps; warp & 3 = TMEM lane quarter,
+    // the two warps of a quarter take alternate 32-column chunks
+    const int q = warp & 3;
+    const int csel = (warp - 4) >> 2;
+    const int rloc = q * 32 + lane;
     long long c_off = 0;
     if (ep.c_off_ptr) c_off = static_cast<long long>(*ep.c_off_ptr) * ep.c_off_mul;
     const float gate = ep.gate ? tanhf(*ep.gate) : 1.0f;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      const int tile = item / S;
       const int n_blk = tile % n_tiles, m_blk = tile / n_tiles;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int m = m_blk * BM + q * 32 + lane;
+      const int m = m_blk * BM + rloc;
       const bool row_ok = m < M;
       const long long res_row = ep.res_row_mod > 0 ? (m % ep.res_row_mod) : m;
+      const uint32_t tsrc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      if (S == 1) {
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c * 32, r);
-        tmem_ld_wait();
-        const int n0 = n_blk * BN + c * 32;
-        if (row_ok && n0 < N) {
-          float v[32];
+        for (int c = csel; c < BN / 32; c += 2) {
+          uint32_t r[32];
+          tmem_ld_32x32(tsrc + c * 32, r);
+          tmem_ld_wait();
+          const int n0 = n_blk * BN + c * 32;
+          if (row_ok && n0 < N) {
+            float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          const bool full = (n0 + 32 <= N);
-          if (ep.bias) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += (full || n0 + j < N) ? __ldg(ep.bias + n0 + j) : 0.f;
-          }
-          if (ep.act == 1) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-          }
-          if (ep.gate) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= gate;
-          }
-          if (ep.out_f32) {
-            float* crow = reinterpret_cast<float*>(ep.C) + c_off + static_cast<long long>(m) * ep.ldc + n0;
-            if (ep.residual) {
-              const float* rrow = reinterpret_cast<const float*>(ep.residual) + res_row * ep.ldr + n0;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) if (full || n0 + j < N) v[j] += rrow[j];
-            }
-            if (full && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) if (n0 + j < N) crow[j] = v[j];
-            }
-          } else {
-            __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(ep.C) + c_off + static_cast<long long>(m) * ep.ldc + n0;
-            if (ep.residual) {
-              const __nv_bfloat16* rrow = reinterpret_cast<const __nv_bfloat16*>(ep.residual) + res_row * ep.ldr + n0;
-              if (full && ((reinterpret_cast<uintptr_t>(rrow) & 15) == 0)) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                  const uint4 u = *reinterpret_cast<const uint4*>(rrow + j);
-                  v[j + 0] += bf16lo(u.x); v[j + 1] += bf16hi(u.x);
-                  v[j + 2] += bf16lo(u.y); v[j + 3] += bf16hi(u.y);
-                  v[j + 4] += bf16lo(u.z); v[j + 5] += bf16hi(u.z);
-                  v[j + 6] += bf16lo(u.w); v[j + 7] += bf16hi(u.w);
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) if (n0 + j < N) v[j] += __bfloat162float(rrow[j]);
-              }
-            }
-            if (full && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 u;
-                u.x = pack_bf16(v[j + 0], v[j + 1]);
-                u.y = pack_bf16(v[j + 2], v[j + 3]);
-                u.z = pack_bf16(v[j + 4], v[j + 5]);
-                u.w = pack_bf16(v[j + 6], v[j + 7]);
-                *reinterpret_cast<uint4*>(crow + j) = u;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) if (n0 + j < N) crow[j] = __float2bfloat16_rn(v[j]);
-            }
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            finish_chunk(v, ep, m, res_row, n0, N, gate, c_off);
           }
         }
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[acc]);
+      } else {
+        // ---- split-K: publish this slice's fp32 partial, the last slice to arrive reduces and finishes the tile
+        float* part = ep.ws_part + static_cast<long long>(item) * (BM * BN) + rloc * BN;
+#pragma unroll 1
+        for (int c = csel; c < BN / 32; c += 2) {
+          uint32_t r[32];
+          tmem_ld_32x32(tsrc + c * 32, r);
+          tmem_ld_wait();
+          if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<uint4*>(part + c * 32 + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[acc]);  // TMEM stage is free again
+        __threadfence();
+        epi_bar();
+        if (threadIdx.x == 4 * 32) {
+          const int prev = atomicAdd(ep.ws_count + tile, 1);
+          *last_flag = (prev == S - 1);
+        }
+        epi_bar();
+        if (*last_flag) {
+          __threadfence();
+          const float* base = ep.ws_part + static_cast<long long>(tile) * S * (BM * BN) + rloc * BN;
+#pragma unroll 1
+          for (int c = csel; c < BN / 32; c += 2) {
+            const int n0 = n_blk * BN + c * 32;
+            if (row_ok && n0 < N) {
+              float v[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = 0.f;
+              for (int s2 = 0; s2 < S; ++s2) {
+                const float* p = base + static_cast<long long>(s2) * (BM * BN) + c * 32;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 t4 = __ldcg(reinterpret_cast<const float4*>(p + j));
+                  v[j] += t4.x; v[j + 1] += t4.y; v[j + 2] += t4.z; v[j + 3] += t4.w;
+                }
+              }
+              finish_chunk(v, ep, m, res_row, n0, N, gate, c_off);
+            }
+          }
+          if (threadIdx.x == 4 * 32) ep.ws_count[tile] = 0;  // self-resetting: ready for the next launch
+        }
+        epi_bar();  // last_flag is rewritten only after everyone has read it
       }
-      tc_fence_before();
-      mbar_arrive(&tempty_bar[acc]);
     }
   }
 
@@ -280,8 +367,8 @@ static int make_map_bf16(CUtensorMap* map, const void* base, long long rows, lon
 }
 
 template <int BN, int STAGES>
-static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, int M, int N, int K, const TcEpilogue& ep,
-                     cudaStream_t stream) {
+static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, int M, int N, int K, TcEpilogue ep,
+                     void* ws, long long ws_bytes, cudaStream_t stream) {
   using Cfg = TcCfg<BN, STAGES>;
   static bool configured = false;
   if (!configured) {
@@ -290,8 +377,27 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, int M, int N,
     configured = true;
   }
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_tc_kernel<BN, STAGES><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(ma, mb, M, N, K, ep);
+  const int k_blocks = (K + BK - 1) / BK;
+  // split-K only pays for long-K weight-streaming shapes that cannot fill the machine with output tiles
+  // (measured on B200, M=128: K=5120 28 -> 22 us; at K=1280 the partial-tile round trip costs more than it saves)
+  int S = 1;
+  if (ws && M <= 2 * BM && tiles <= 1024 && tiles * 4 <= 3 * num_sms() && k_blocks >= 64) {
+    S = (num_sms() + tiles - 1) / tiles;
+    if (S > k_blocks / 4) S = k_blocks / 4;
+    if (S > 8) S = 8;
+    while (S > 1 && SPLITK_COUNTER_BYTES + static_cast<long long>(tiles) * S * BM * BN * 4 > ws_bytes) --S;
+    if (S > 1) {  // every slice must own at least one k-block
+      const int per = (k_blocks + S - 1) / S;
+      S = (k_blocks + per - 1) / per;
+    }
+    if (S < 1) S = 1;
+  }
+  ep.splits = S;
+  ep.ws_count = reinterpret_cast<int*>(ws);
+  ep.ws_part = ws ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + SPLITK_COUNTER_BYTES) : nullptr;
+  const int items = tiles * S;
+  const int grid = items < num_sms() ? items : num_sms();
+  gemm_tc_kernel<BN, STAGES><<<grid, TC_THREADS, Cfg::SMEM_BYTES, stream>>>(ma, mb, M, N, K, ep);
   WF_CHECK_LAUNCH();
   return WF_OK;
 }
@@ -300,8 +406,17 @@ int linear_bf16_tc(const void* A, long long lda, const void* W, long long ldw, i
                    const LinearEpilogue& e, int tile_hint, cudaStream_t stream) {
   WF_REQUIRE(M > 0 && N > 0 && K > 0, "linear: empty problem M=%d N=%d K=%d", M, N, K);
   int bn = tile_hint;
-  if (bn == 0) bn = (M <= 256) ? 32 : (N >= 256 ? 256 : 128);
+  if (bn == 0) {
+    if (M <= 256) bn = (N >= 16384) ? 128 : (N >= 4096 ? 64 : 32);  // decode: many narrow tiles stream the weights
+    else bn = N >= 256 ? 256 : 128;
+  }
   WF_REQUIRE(bn == 32 || bn == 64 || bn == 128 || bn == 256, "linear: unsupported tile hint %d", tile_hint);
+  if (e.hm_heads > 0) {
+    WF_REQUIRE(N % 64 == 0 && e.hm_heads * 64 == N && e.hm_T > 0 && e.hm_rpb > 0 && !e.residual,
+               "linear: bad head-major output spec (N=%d heads=%d T=%d rpb=%d)", N, e.hm_heads, e.hm_T, e.hm_rpb);
+  }
+  WF_REQUIRE(!e.ws || ((reinterpret_cast<uintptr_t>(e.ws) & 15) == 0 && e.ws_bytes >= SPLITK_COUNTER_BYTES),
+             "linear: split-K workspace must be 16-byte aligned and hold at least %d bytes", SPLITK_COUNTER_BYTES);
   CUtensorMap ma, mb;
   int rc = make_map_bf16(&ma, A, M, K, lda, BM);
   if (rc) return rc;
@@ -311,11 +426,13 @@ int linear_bf16_tc(const void* A, long long lda, const void* W, long long ldw, i
   ep.C = e.C; ep.ldc = e.ldc; ep.bias = e.bias; ep.residual = e.residual; ep.ldr = e.ldr;
   ep.res_row_mod = e.res_row_mod; ep.gate = e.gate; ep.act = e.act; ep.out_f32 = e.out_f32;
   ep.c_off_ptr = e.c_off_ptr; ep.c_off_mul = e.c_off_mul;
+  ep.hm_heads = e.hm_heads; ep.hm_T = e.hm_T; ep.hm_rpb = e.hm_rpb;
+  ep.splits = 1; ep.ws_part = nullptr; ep.ws_count = nullptr;
   switch (bn) {
-    case 32: return launch_tc<32, 8>(ma, mb, M, N, K, ep, stream);
-    case 64: return launch_tc<64, 8>(ma, mb, M, N, K, ep, stream);
-    case 128: return launch_tc<128, 6>(ma, mb, M, N, K, ep, stream);
-    default: return launch_tc<256, 4>(ma, mb, M, N, K, ep, stream);
+    case 32: return launch_tc<32, 8>(ma, mb, M, N, K, ep, e.ws, e.ws_bytes, stream);
+    case 64: return launch_tc<64, 8>(ma, mb, M, N, K, ep, e.ws, e.ws_bytes, stream);
+    case 128: return launch_tc<128, 6>(ma, mb, M, N, K, ep, e.ws, e.ws_bytes, stream);
+    default: return launch_tc<256, 4>(ma, mb, M, N, K, ep, e.ws, e.ws_bytes, stream);
   }
 }
 

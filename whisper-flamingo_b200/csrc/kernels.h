@@ -17,6 +17,12 @@ struct LinearEpilogue {
   int out_f32 = 0;              // bf16 GEMM only: write fp32
   const int* c_off_ptr = nullptr;  // device int p: C += p * c_off_mul elements (KV-cache append position)
   long long c_off_mul = 0;
+  // head-major output for K/V caches (hm_heads > 0): element (m, n) is stored at
+  //   (((m / hm_rpb) * hm_heads + n / 64) * hm_T + m % hm_rpb) * 64 + n % 64      (ldc is ignored)
+  int hm_heads = 0, hm_T = 0, hm_rpb = 0;
+  // optional split-K workspace (bf16 engine, M <= 256): first 4096 bytes = zero-initialised arrival counters
+  void* ws = nullptr;
+  long long ws_bytes = 0;
 };
 
 // gemm_tc.cu / gemm_f32.cu
@@ -49,8 +55,9 @@ int attention_full(int dtype, const void* q, long long ldq, const void* k, long 
 
 // decode.cu
 int attention_decode(int dtype, const void* q, long long ldq, const void* kc, const void* vc, long long ld_kv,
-                     long long kv_batch_stride, void* o, long long ldo, int R, int G, int H, const int* len_ptr,
-                     int len_add, int len_const, void* workspace, long long workspace_bytes, cudaStream_t stream);
+                     long long kv_batch_stride, long long kv_head_stride, void* o, long long ldo, int R, int G, int H,
+                     const int* len_ptr, int len_add, int len_const, void* workspace, long long workspace_bytes,
+                     cudaStream_t stream);
 long long attention_decode_workspace_bytes(int R, int H);
 
 struct SampleArgs {

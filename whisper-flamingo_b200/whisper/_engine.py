@@ -6,9 +6,11 @@ allocates device buffers, owns the streams and captures the decode step into a C
 Data layout in HBM
   activations        [rows, d] row-major, rows = batch * time; bf16 (tensor-core engine) or fp32
   packed weights     [N, K] row-major ("K-major" for both GEMM operands), biases / LN affine fp32
-  cross / x-attn KV  per layer one [B * T_src, 2d] buffer: K in columns [0,d), V in [d,2d); a head is a
-                     64-column slice, so one (audio, head) K or V row is one 128-byte line
-  self-attn KV       per layer [R, T_cap, 2d], appended in place by the K/V projection GEMM
+  cross / x-attn KV  decode sessions: per layer [B, 2H, T_src, 64] head-major (K heads 0..H-1, V heads H..2H-1):
+                     the keys (values) of one (audio, head) are T_src contiguous 128-byte lines, written in that
+                     layout directly by the K/V projection GEMM epilogue (DRAM-page friendly streaming)
+  self-attn KV       per layer [R, 2H, T_cap, 64], appended in place by the K/V projection GEMM at state[0]
+  (teacher-forced passes keep the simpler [B * T_src, 2d] row-interleaved buffers)
 """
 from __future__ import annotations
 
@@ -219,11 +221,12 @@ def _empty(rows: int, cols: int, dt, dev) -> Tensor:
     return torch.empty((rows, cols), dtype=dt, device=dev)
 
 
-def _mlp_inplace(x: Tensor, xn: Tensor, h: Tensor, ln: _LnPack, mlp: _MlpPack, gate: Optional[Tensor] = None):
+def _mlp_inplace(x: Tensor, xn: Tensor, h: Tensor, ln: _LnPack, mlp: _MlpPack, gate: Optional[Tensor] = None,
+                 ws: Optional[Tensor] = None):
     """x += tanh(gate) * W2 gelu(W1 LN(x) + b1) + b2   (reference model.py:149-152, 197, 214)."""
     nv.layernorm(x, ln.w, ln.b, xn)
-    nv.linear(xn, mlp.w1, h, bias=mlp.b1, act=nv.ACT_GELU)
-    nv.linear(h, mlp.w2, x, bias=mlp.b2, residual=x, gate=gate)
+    nv.linear(xn, mlp.w1, h, bias=mlp.b1, act=nv.ACT_GELU, ws=ws)
+    nv.linear(h, mlp.w2, x, bias=mlp.b2, residual=x, gate=gate, ws=ws)
 
 
 # ============================================================================ encoder
@@ -402,19 +405,21 @@ class DecodeSession:
         fprep = [prepare_features(p, f, dt) for f in feats]
         self.Tx = [f.shape[0] // B for f in fprep]
         for bp in p.blocks:
-            kv = _empty(B * Ta, 2 * d, dt, dev)
-            nv.linear(xa2, bp.cross.kv_w, kv, bias=bp.cross.kv_b)
+            kv = torch.empty((B, 2 * H, Ta, 64), dtype=dt, device=dev)
+            nv.linear(xa2, bp.cross.kv_w, kv.view(-1, 64), bias=bp.cross.kv_b, head_major=(2 * H, Ta, Ta))
             self.cross_kv.append(kv)
             per = []
             for i, f in enumerate(fprep):
-                kvx = _empty(f.shape[0], 2 * d, dt, dev)
-                nv.linear(f, bp.x_attn[i].kv_w, kvx, bias=bp.x_attn[i].kv_b)
+                kvx = torch.empty((B, 2 * H, self.Tx[i], 64), dtype=dt, device=dev)
+                nv.linear(f, bp.x_attn[i].kv_w, kvx.view(-1, 64), bias=bp.x_attn[i].kv_b,
+                          head_major=(2 * H, self.Tx[i], self.Tx[i]))
                 per.append(kvx)
             self.x_kv.append(per)
         del fprep
         # ---- step buffers
         L = len(p.blocks)
-        self.self_kv = [torch.zeros((R, t_cap, 2 * d), dtype=dt, device=dev) for _ in range(L)]
+        self.self_kv = [torch.zeros((R, 2 * H, t_cap, 64), dtype=dt, device=dev) for _ in range(L)]
+        self.gemm_ws = torch.zeros(4096 + 8 * 1024 * 1024, dtype=torch.uint8, device=dev)  # split-K counters + partials
         self.x = _empty(R, d, dt, dev)
         self.xn, self.q, self.att = _empty(R, d, dt, dev), _empty(R, d, dt, dev), _empty(R, d, dt, dev)
         self.acc = _empty(R, d, dt, dev) if len(feats) > 1 else None
@@ -436,6 +441,7 @@ class DecodeSession:
     def _forward_token(self):
         p, d, H, G = self.p, self.p.d, self.p.n_head, self.G
         st = self.state
+        gws = self.gemm_ws if self.dt == torch.bfloat16 else None
         nv.embed(self.tokens, self.tokens.shape[1], st, 0, p.tok_emb, p.pos_emb, self.x)
         x, xn, q, att, h = self.x, self.xn, self.q, self.att, self.h
         for l, bp in enumerate(p.blocks):
@@ -448,32 +454,33 @@ class DecodeSession:
                 for i, kvx in enumerate(self.x_kv[l]):
                     Tx = self.Tx[i]
                     nv.layernorm(x, bp.x_ln[i].w, bp.x_ln[i].b, xn)
-                    nv.linear(xn, bp.x_attn[i].q_w, q, bias=bp.x_attn[i].q_b)
-                    nv.attention_decode(q, kvx[:, :d], kvx[:, d:], 2 * d, Tx * 2 * d, att, G, H, None, 0, Tx, self.ws)
-                    nv.linear(att, bp.x_attn[i].o_w, acc, bias=bp.x_attn[i].o_b, residual=acc, gate=bp.x_gate[i])
+                    nv.linear(xn, bp.x_attn[i].q_w, q, bias=bp.x_attn[i].q_b, ws=gws)
+                    nv.attention_decode(q, kvx, kvx[:, H:], 64, 2 * H * Tx * 64, Tx * 64, att, G, H, None, 0, Tx,
+                                        self.ws)
+                    nv.linear(att, bp.x_attn[i].o_w, acc, bias=bp.x_attn[i].o_b, residual=acc, gate=bp.x_gate[i],
+                              ws=gws)
                 if multi:
                     x.copy_(acc)
-                _mlp_inplace(x, xn, h, bp.ff_ln, bp.ff, gate=bp.ff_gate)
+                _mlp_inplace(x, xn, h, bp.ff_ln, bp.ff, gate=bp.ff_gate, ws=gws)
             # causal self-attention over the cache; this token's K/V are appended by the GEMM epilogue
+            Tc = self.T_cap
             nv.layernorm(x, bp.attn_ln.w, bp.attn_ln.b, xn)
-            nv.linear(xn, bp.attn.q_w, q, bias=bp.attn.q_b)
-            kv = self.self_kv[l]
-            kv_rows = kv.view(self.R, self.T_cap * 2 * d)[:, : 2 * d]  # row r -> cache[r, 0, :], advanced by c_off
-            nv.linear(xn, bp.attn.kv_w, kv_rows, bias=bp.attn.kv_b, c_off_ptr=st, c_off_mul=2 * d)
-            kv2 = kv.view(self.R * self.T_cap, 2 * d)
-            nv.attention_decode(q, kv2[:, :d], kv2[:, d:], 2 * d, self.T_cap * 2 * d, att, 1, H, st, 1, self.T_cap,
-                                self.ws)
-            nv.linear(att, bp.attn.o_w, x, bias=bp.attn.o_b, residual=x)
+            nv.linear(xn, bp.attn.q_w, q, bias=bp.attn.q_b, ws=gws)
+            kv = self.self_kv[l]  # [R, 2H, T_cap, 64]; row r, position state[0]: offset state[0] * 64 inside each head
+            nv.linear(xn, bp.attn.kv_w, kv.view(-1, 64), bias=bp.attn.kv_b, head_major=(2 * H, Tc, 1),
+                      c_off_ptr=st, c_off_mul=64, ws=gws)
+            nv.attention_decode(q, kv, kv[:, H:], 64, 2 * H * Tc * 64, Tc * 64, att, 1, H, st, 1, Tc, self.ws)
+            nv.linear(att, bp.attn.o_w, x, bias=bp.attn.o_b, residual=x, ws=gws)
             # cross-attention to the encoder output (K/V cached per audio, shared by its G beams)
             nv.layernorm(x, bp.cross_ln.w, bp.cross_ln.b, xn)
-            nv.linear(xn, bp.cross.q_w, q, bias=bp.cross.q_b)
+            nv.linear(xn, bp.cross.q_w, q, bias=bp.cross.q_b, ws=gws)
             ckv = self.cross_kv[l]
-            nv.attention_decode(q, ckv[:, :d], ckv[:, d:], 2 * d, self.Ta * 2 * d, att, G, H, None, 0, self.Ta,
-                                self.ws)
-            nv.linear(att, bp.cross.o_w, x, bias=bp.cross.o_b, residual=x)
-            _mlp_inplace(x, xn, h, bp.mlp_ln, bp.mlp)
+            nv.attention_decode(q, ckv, ckv[:, H:], 64, 2 * H * self.Ta * 64, self.Ta * 64, att, G, H, None, 0,
+                                self.Ta, self.ws)
+            nv.linear(att, bp.cross.o_w, x, bias=bp.cross.o_b, residual=x, ws=gws)
+            _mlp_inplace(x, xn, h, bp.mlp_ln, bp.mlp, ws=gws)
         nv.layernorm(x, p.ln.w, p.ln.b, xn)
-        nv.linear(xn, p.tok_emb_t, self.logits, n=p.n_vocab)
+        nv.linear(xn, p.tok_emb_t, self.logits, n=p.n_vocab, ws=gws)
 
     # -- greedy ---------------------------------------------------------------------------------------
     def configure_greedy(self, initial_tokens: Sequence[int], sot_index: int, suppress: Tensor,
@@ -540,7 +547,7 @@ class DecodeSession:
         d = self.p.d
         elt = self.self_kv[0].element_size()
         row_bytes = self.T_cap * 2 * d * elt
-        used = used_positions * 2 * d * elt
+        used = row_bytes  # head-major rows: the used positions are a prefix of every head segment, copy the row
         new = []
         for kv in self.self_kv:
             dst = torch.empty_like(kv)

@@ -27,7 +27,9 @@ class WfError(RuntimeError):
 class _Epilogue(C.Structure):
     _fields_ = [("C", C.c_void_p), ("ldc", C.c_longlong), ("bias", C.c_void_p), ("residual", C.c_void_p),
                 ("ldr", C.c_longlong), ("res_row_mod", C.c_int), ("gate", C.c_void_p), ("act", C.c_int),
-                ("out_f32", C.c_int), ("c_off_ptr", C.c_void_p), ("c_off_mul", C.c_longlong)]
+                ("out_f32", C.c_int), ("c_off_ptr", C.c_void_p), ("c_off_mul", C.c_longlong),
+                ("hm_heads", C.c_int), ("hm_T", C.c_int), ("hm_rpb", C.c_int), ("ws", C.c_void_p),
+                ("ws_bytes", C.c_longlong)]
 
 
 class _Sample(C.Structure):
@@ -70,8 +72,8 @@ _SIGNATURES = {
                                C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "wf_attention_decode_workspace_bytes": (C.c_longlong, [C.c_int, C.c_int]),
     "wf_attention_decode": (C.c_int, [C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_longlong,
-                                      C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p,
-                                      C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p]),
+                                      C.c_longlong, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int,
+                                      C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p]),
     "wf_sample_greedy": (C.c_int, [C.POINTER(_Sample), C.c_void_p]),
     "wf_step_advance": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "wf_topk_logprobs": (C.c_int, [C.POINTER(_Topk), C.c_void_p]),
@@ -210,8 +212,13 @@ def logmel(pcm: torch.Tensor, n_mels: int, mode: int) -> torch.Tensor:
 def linear(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias: Optional[torch.Tensor] = None,
            residual: Optional[torch.Tensor] = None, res_row_mod: int = 0, gate: Optional[torch.Tensor] = None,
            act: int = ACT_NONE, c_off_ptr: Optional[torch.Tensor] = None, c_off_mul: int = 0,
-           tile_hint: int = 0, n: Optional[int] = None) -> torch.Tensor:
-    """out[M,N] = residual + tanh(gate) * act(a[M,K] @ w[N,K]^T + bias).  All 2-D row-major views."""
+           tile_hint: int = 0, n: Optional[int] = None, head_major: Optional[tuple] = None,
+           ws: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[M,N] = residual + tanh(gate) * act(a[M,K] @ w[N,K]^T + bias).  All 2-D row-major views.
+
+    head_major=(heads, T, rows_per_batch): ``out`` is a K/V cache ``[batch, heads, T, 64]`` (any view of its
+    storage) and element (m, n) lands at [m // rpb, n // 64, m % rpb (+ offset), n % 64].
+    ws: optional split-K workspace (uint8, first 4096 bytes zeroed once)."""
     m, k = a.shape
     n_w, k_w = w.shape
     n = n_w if n is None else n
@@ -226,9 +233,11 @@ def linear(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias: Optiona
         assert residual.dtype == out.dtype
     if gate is not None:
         assert gate.dtype == torch.float32
-    ep = _Epilogue(out.data_ptr(), _row_stride(out), _ptr(bias), _ptr(residual),
+    hm = head_major or (0, 0, 0)
+    ep = _Epilogue(out.data_ptr(), 0 if head_major else _row_stride(out), _ptr(bias), _ptr(residual),
                    _row_stride(residual) if residual is not None else 0, res_row_mod, _ptr(gate), act, out_f32,
-                   _ptr(c_off_ptr), c_off_mul)
+                   _ptr(c_off_ptr), c_off_mul, hm[0], hm[1], hm[2], _ptr(ws),
+                   0 if ws is None else ws.numel() * ws.element_size())
     fam = ("gemm_tc_bf16" if m > 256 else "gemm_tc_bf16_skinny") if dt == WF_BF16 else "gemm_f32"
     with _Prof(fam, flops=2 * m * n * k, bytes=(m * k + n * k) * a.element_size() + m * n * out.element_size()):
         _check(load().wf_linear(dt, a.data_ptr(), _row_stride(a), w.data_ptr(), _row_stride(w), m, n, k,
@@ -299,16 +308,16 @@ def attention_decode_workspace_bytes(r: int, h: int) -> int:
 
 
 def attention_decode(q: torch.Tensor, kc: torch.Tensor, vc: torch.Tensor, ld_kv: int, kv_batch_stride: int,
-                     out: torch.Tensor, g: int, h: int, len_ptr: Optional[torch.Tensor], len_add: int,
-                     len_const: int, ws: Optional[torch.Tensor]) -> torch.Tensor:
+                     kv_head_stride: int, out: torch.Tensor, g: int, h: int, len_ptr: Optional[torch.Tensor],
+                     len_add: int, len_const: int, ws: Optional[torch.Tensor]) -> torch.Tensor:
     r = q.shape[0]
     # algorithmic bytes: K and V rows of every (audio, head) once; dynamic lengths are reported at their bound
     dyn = len_ptr is not None  # growing self-attention cache: charged at half its bound (average over a decode)
     with _Prof("attention_decode_self" if dyn else "attention_decode",
                bytes=2 * (r // g) * h * 64 * (len_const // 2 if dyn else len_const) * q.element_size()):
         _check(load().wf_attention_decode(dtype_id(q.dtype), q.data_ptr(), _row_stride(q), kc.data_ptr(),
-                                          vc.data_ptr(), ld_kv, kv_batch_stride, out.data_ptr(), _row_stride(out), r,
-                                          g, h, _ptr(len_ptr), len_add, len_const, _ptr(ws),
+                                          vc.data_ptr(), ld_kv, kv_batch_stride, kv_head_stride, out.data_ptr(),
+                                          _row_stride(out), r, g, h, _ptr(len_ptr), len_add, len_const, _ptr(ws),
                                           0 if ws is None else ws.numel() * ws.element_size(), _stream()))
     return out
 
