@@ -17,7 +17,6 @@ import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
 import threading
 import time
@@ -59,45 +58,43 @@ def peaks():
 
 # ----------------------------------------------------------------------------- clocks sampling
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+    """SM clock + throttle reasons DURING the timed region, read in-process through NVML every 250 ms
+    (an external `nvidia-smi -lms 200` loop was measured to perturb the timed region by up to 30 %)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, index: int):
-        self.rows, self.proc = [], None
+    def __init__(self, index: int, period_s: float = 0.25):
+        self.sm, self.mask, self.max_mhz, self.ok = [], 0, None, False
+        self._stop = threading.Event()
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+            return
+        self.period = period_s
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                self.mask |= int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(self.period)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
-            except (ValueError, IndexError):
-                continue
-            for name, v in zip(self.NAMES, r[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"nvml unavailable: {getattr(self, 'err', '')}"]}
+        self._stop.set()
+        self.thread.join(timeout=2)
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(n for bit, n in self.REASONS.items() if self.mask & bit), "samples": len(self.sm)}
 
 
 # ----------------------------------------------------------------------------- product arm
@@ -201,6 +198,10 @@ def run_product(args):
     clocks = sampler.stop() if sampler else None
     e2e_step()
     ms_e2e, toks_e2e = timed(e2e_step, args.steps)
+    phases = None
+    if os.environ.get("WF_TIMING", "0") == "1":
+        from whisper._engine import PhaseTimer
+        phases = {k: round(v, 2) for k, v in PhaseTimer.last.items()}
     assert toks.shape == (B * world, SAMPLE_LEN), toks.shape
     assert torch.equal(toks.cpu(), toks_e2e), "device-resident and end-to-end runs decoded different tokens"
 
@@ -219,6 +220,8 @@ def run_product(args):
                 "d2h_bytes_per_step": B * world * SAMPLE_LEN * 4},
         "gpu_launches": launches, "clocks": clocks,
     }
+    if phases:
+        line["phases_ms"] = phases
     if rank == 0:
         if not args.no_profile:
             line.update(profile_kernels(model, pcm_dev, feat_dev, opt, B, ms / args.steps))

@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include <stdarg.h>
+#include <stdlib.h>
 
 namespace wf {
 
@@ -19,6 +20,19 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 static unsigned long long g_launches = 0;
 void count_launch() { __atomic_add_fetch(&g_launches, 1ull, __ATOMIC_RELAXED); }
+
+bool pdl_enabled(int kind) {
+  static int mask = -1;
+  if (mask < 0) {
+    const char* e = getenv("WF_PDL_MASK");
+    // default: GEMMs only.  Measured on B200 (large-v2 decode loop): GEMM-only PDL -5 %, attention-only -2 %,
+    // every kernel +40 % (early-launched CTAs of many future kernels crowd the SMs), so the chain is kept short.
+    mask = e ? atoi(e) : 0x1;
+    const char* n = getenv("WF_NO_PDL");
+    if (n && n[0] == '1') mask = 0;
+  }
+  return (mask >> kind) & 1;
+}
 
 int num_sms() {
   static int sms = 0;

@@ -42,6 +42,29 @@ void count_launch();
 
 int num_sms();
 
+// ---- programmatic dependent launch (PDL): a kernel launched with launch_pdl() may start while its predecessor in
+// the stream is still running; it must execute pdl_wait() before touching anything the predecessor produces, and
+// every such kernel executes pdl_wait() at least once so that completion stays transitive along the stream.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool pdl_enabled(int kind);  // kind: 0 gemm, 1 layernorm, 2 attention, 3 misc (WF_PDL_MASK bit)
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(int kind, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                       Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled(kind) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- dtype helpers
 template <typename T> struct DType;
 template <> struct DType<float> { static constexpr int id = WF_F32; };

@@ -41,6 +41,8 @@ attn_decode_kernel(const T* __restrict__ q, long long ldq, const T* __restrict__
   __shared__ float sred[NQ][DT / 32];
   __shared__ float sacc[DT / 32][NQ][HD];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_trigger();
+  pdl_wait();
   const int kvb = blockIdx.x / H, h = blockIdx.x % H;
   const int split = blockIdx.y;
   const int len = len_ptr ? (*len_ptr + len_add) : len_const;
@@ -189,6 +191,10 @@ attn_decode_hm_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const 
   __shared__ float sred[NQ][DT / 32];
   __shared__ float sacc[DT / 32][NQ][HD];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_trigger();
+  // A cache of static length (cross / x-attention) was written long before this step: its first tiles are requested
+  // before the dependency wait and stream in while the previous kernel drains.  A growing cache (len_ptr) is not.
+  if (len_ptr) pdl_wait();
   const int kvb = blockIdx.x / H, h = blockIdx.x % H;
   const int split = blockIdx.y;
   const int len = len_ptr ? (*len_ptr + len_add) : len_const;
@@ -200,17 +206,6 @@ attn_decode_hm_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const 
   const __nv_bfloat16* kbase = kc + kvb * kv_batch_stride + h * kv_head_stride;
   const __nv_bfloat16* vbase = vc + kvb * kv_batch_stride + h * kv_head_stride;
 
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < HM_STAGES; ++s) mbar_init(&full_bar[s], 1);
-    mbar_fence_init();
-  }
-  for (int i = tid; i < NQ * HD; i += DT) {
-    const int qi = i / HD, d = i % HD;
-    sq[qi][d] = __bfloat162float(q[(static_cast<long long>(kvb) * NQ + qi) * ldq + h * HD + d]) * 0.125f;
-  }
-  __syncthreads();
-
   auto issue = [&](int tile, int stage) {
     const int rows = min(HM_KEYS, len - tile * HM_KEYS);
     const uint32_t bytes = static_cast<uint32_t>(rows) * HD * 2;
@@ -220,9 +215,18 @@ attn_decode_hm_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const 
     bulk_load_1d(dst + HM_TILE_BYTES, vbase + static_cast<long long>(tile) * HM_KEYS * HD, bytes, &full_bar[stage]);
   };
   if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < HM_STAGES; ++s) mbar_init(&full_bar[s], 1);
+    mbar_fence_init();
     for (int s = 0; s < HM_STAGES; ++s)
       if (tile_begin + s < tile_end) issue(tile_begin + s, s);
   }
+  if (!len_ptr) pdl_wait();  // q (and everything written below) depends on the previous kernel
+  for (int i = tid; i < NQ * HD; i += DT) {
+    const int qi = i / HD, d = i % HD;
+    sq[qi][d] = __bfloat162float(q[(static_cast<long long>(kvb) * NQ + qi) * ldq + h * HD + d]) * 0.125f;
+  }
+  __syncthreads();
 
   const int dgrp = lane & 7, ksub = lane >> 3;
   float m_run[NQ], l_run[NQ], acc[NQ][8];
@@ -340,6 +344,8 @@ attn_decode_hm_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const 
 template <typename T>
 __global__ void __launch_bounds__(HD)
 attn_decode_combine_kernel(const float* __restrict__ partials, T* __restrict__ o, long long ldo, int H, int n_splits) {
+  pdl_trigger();
+  pdl_wait();
   const long long row = blockIdx.x / H;
   const int h = blockIdx.x % H, d = threadIdx.x;
   const float* pp = partials + (row * H + h) * n_splits * PART;
@@ -400,23 +406,25 @@ static int launch_decode_attn(const T* q, long long ldq, const T* kc, const T* v
         configured = true;
       }
       dim3 hgrid(blocks, hs);
-      attn_decode_hm_kernel<NQ><<<hgrid, DT, HM_SMEM_BYTES, stream>>>(q, ldq, kc, vc, kv_batch_stride, kv_head_stride,
-                                                                     o, ldo, H, len_ptr, len_add, len_max, hs, ws);
-      WF_CHECK_LAUNCH();
+      WF_CHECK_CUDA(launch_pdl(2, attn_decode_hm_kernel<NQ>, hgrid, dim3(DT), HM_SMEM_BYTES, stream, q, ldq, kc, vc,
+                               kv_batch_stride, kv_head_stride, o, ldo, H, len_ptr, len_add, len_max, hs, ws));
+      count_launch();
       if (hs > 1) {
-        attn_decode_combine_kernel<T><<<R * H, HD, 0, stream>>>(ws, o, ldo, H, hs);
-        WF_CHECK_LAUNCH();
+        WF_CHECK_CUDA(launch_pdl(2, attn_decode_combine_kernel<T>, dim3(R * H), dim3(HD), 0, stream, (const float*)ws, o,
+                                 ldo, H, hs));
+        count_launch();
       }
       return WF_OK;
     }
   }
   dim3 grid(blocks, n_splits);
-  attn_decode_kernel<T, NQ><<<grid, DT, 0, stream>>>(q, ldq, kc, vc, ld_kv, kv_batch_stride, kv_head_stride, o, ldo,
-                                                     H, len_ptr, len_add, len_max, n_splits, ws);
-  WF_CHECK_LAUNCH();
+  WF_CHECK_CUDA(launch_pdl(2, attn_decode_kernel<T, NQ>, grid, dim3(DT), 0, stream, q, ldq, kc, vc, ld_kv,
+                           kv_batch_stride, kv_head_stride, o, ldo, H, len_ptr, len_add, len_max, n_splits, ws));
+  count_launch();
   if (n_splits > 1) {
-    attn_decode_combine_kernel<T><<<R * H, HD, 0, stream>>>(ws, o, ldo, H, n_splits);
-    WF_CHECK_LAUNCH();
+    WF_CHECK_CUDA(launch_pdl(2, attn_decode_combine_kernel<T>, dim3(R * H), dim3(HD), 0, stream, (const float*)ws, o, ldo,
+                             H, n_splits));
+    count_launch();
   }
   return WF_OK;
 }
@@ -565,6 +573,8 @@ __device__ void apply_timestamp_mass_rule(RowMask& m, const float* lg, int V, co
 __global__ void __launch_bounds__(256) sample_greedy_kernel(SampleArgs a) {
   __shared__ ArgMax sh_am[8];
   __shared__ float sh_f[8];
+  pdl_trigger();
+  pdl_wait();
   const int r = blockIdx.x;
   const float* lg = a.logits + r * a.ld;
   const int t = a.state[0], n_init = a.state[1], sot_index = a.state[4];
@@ -608,20 +618,22 @@ __global__ void __launch_bounds__(256) sample_greedy_kernel(SampleArgs a) {
 
 int sample_greedy(const SampleArgs& a, cudaStream_t stream) {
   WF_REQUIRE(a.R > 0 && a.V > 0 && a.logits && a.tokens && a.state && a.suppress, "sample_greedy: bad arguments");
-  sample_greedy_kernel<<<a.R, 256, 0, stream>>>(a);
-  WF_CHECK_LAUNCH();
+  WF_CHECK_CUDA(launch_pdl(3, sample_greedy_kernel, dim3(a.R), dim3(256), 0, stream, a));
+  count_launch();
   return WF_OK;
 }
 
 __global__ void step_advance_kernel(int* state, int R) {
+  pdl_trigger();
+  pdl_wait();
   const int t = state[0], n_init = state[1];
   if (t + 1 >= n_init && state[3] == R) state[2] = 1;
   state[3] = 0;
   state[0] = t + 1;
 }
 int step_advance(int* state, int R, cudaStream_t stream) {
-  step_advance_kernel<<<1, 1, 0, stream>>>(state, R);
-  WF_CHECK_LAUNCH();
+  WF_CHECK_CUDA(launch_pdl(3, step_advance_kernel, dim3(1), dim3(1), 0, stream, state, R));
+  count_launch();
   return WF_OK;
 }
 

@@ -32,6 +32,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const T* __restrict__ x, long long ldx, const float* __restrict__ w, const float* __restrict__ b,
                  T* __restrict__ y, long long ldy, int rows, int d, float eps, int vec_ok) {
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -97,13 +99,14 @@ int layernorm(int dtype, const void* x, long long ldx, const float* w, const flo
   const auto al = [](const void* p, unsigned a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; };
   const int vec_ok = (d % 8 == 0) && (ldx % 8 == 0) && (ldy % 8 == 0) && al(x, 32) && al(y, 32) && al(w, 16) && al(b, 16);
   if (dtype == WF_F32)
-    layernorm_kernel<float><<<grid, warps * 32, 0, stream>>>((const float*)x, ldx, w, b, (float*)y, ldy, rows, d, eps, vec_ok);
+    WF_CHECK_CUDA(launch_pdl(1, layernorm_kernel<float>, dim3(grid), dim3(warps * 32), 0, stream, (const float*)x, ldx, w,
+                             b, (float*)y, ldy, rows, d, eps, vec_ok));
   else if (dtype == WF_BF16)
-    layernorm_kernel<__nv_bfloat16><<<grid, warps * 32, 0, stream>>>((const __nv_bfloat16*)x, ldx, w, b,
-                                                                    (__nv_bfloat16*)y, ldy, rows, d, eps, vec_ok);
+    WF_CHECK_CUDA(launch_pdl(1, layernorm_kernel<__nv_bfloat16>, dim3(grid), dim3(warps * 32), 0, stream,
+                             (const __nv_bfloat16*)x, ldx, w, b, (__nv_bfloat16*)y, ldy, rows, d, eps, vec_ok));
   else
     WF_REQUIRE(false, "layernorm: bad dtype %d", dtype);
-  WF_CHECK_LAUNCH();
+  count_launch();
   return WF_OK;
 }
 
@@ -166,6 +169,8 @@ __global__ void __launch_bounds__(128)
 embed_kernel(const int* __restrict__ tokens, long long tok_stride, const int* __restrict__ pos_ptr, int pos_const,
              const float* __restrict__ tok_emb, const float* __restrict__ pos_emb, T* __restrict__ out, long long ldo,
              int d, int n_pos) {
+  pdl_trigger();
+  pdl_wait();
   const int r = blockIdx.x, j = blockIdx.y;
   const int pos = (pos_ptr ? *pos_ptr : pos_const) + j;
   const int tok = tokens[r * tok_stride + pos];
@@ -181,12 +186,14 @@ int embed_tokens(int dtype, const int* tokens, long long tok_stride, const int* 
   WF_REQUIRE(R > 0 && d > 0 && n_pos > 0 && n_pos <= 65535, "embed: bad shape R=%d d=%d n_pos=%d", R, d, n_pos);
   dim3 grid(R, n_pos);
   if (dtype == WF_F32)
-    embed_kernel<float><<<grid, 128, 0, stream>>>(tokens, tok_stride, pos_ptr, pos_const, tok_emb, pos_emb, (float*)out, ldo, d, n_pos);
+    WF_CHECK_CUDA(launch_pdl(3, embed_kernel<float>, grid, dim3(128), 0, stream, tokens, tok_stride, pos_ptr, pos_const,
+                             tok_emb, pos_emb, (float*)out, ldo, d, n_pos));
   else if (dtype == WF_BF16)
-    embed_kernel<__nv_bfloat16><<<grid, 128, 0, stream>>>(tokens, tok_stride, pos_ptr, pos_const, tok_emb, pos_emb, (__nv_bfloat16*)out, ldo, d, n_pos);
+    WF_CHECK_CUDA(launch_pdl(3, embed_kernel<__nv_bfloat16>, grid, dim3(128), 0, stream, tokens, tok_stride, pos_ptr,
+                             pos_const, tok_emb, pos_emb, (__nv_bfloat16*)out, ldo, d, n_pos));
   else
     WF_REQUIRE(false, "embed: bad dtype %d", dtype);
-  WF_CHECK_LAUNCH();
+  count_launch();
   return WF_OK;
 }
 

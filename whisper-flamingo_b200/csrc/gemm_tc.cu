@@ -154,6 +154,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_trigger();  // the next kernel in the stream may start its own prologue now
 
   const int m_tiles = (M + BM - 1) / BM;
   const int n_tiles = (N + BN - 1) / BN;
@@ -186,13 +187,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------ TMA producer
+    // The weight (B) tiles of the first stages do not depend on the previous kernel: they are requested before the
+    // programmatic-dependency wait, so their DRAM latency overlaps the predecessor's tail; A tiles follow the wait.
     int stage = 0;
     uint32_t phase = 0;
+    bool first = true;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       const int tile = item / S, split = item - tile * S;
       const int n_blk = tile % n_tiles, m_blk = tile / n_tiles;
       const int kb0 = split * kb_per, kb1 = min(k_blocks, kb0 + kb_per);
-      for (int kb = kb0; kb < kb1; ++kb) {
+      int kb = kb0;
+      if (first) {
+        first = false;
+        const int npre = min(STAGES, kb1 - kb0);
+        for (int i = 0; i < npre; ++i) {
+          mbar_arrive_expect_tx(&full_bar[i], Cfg::STAGE_BYTES);
+          tma_load_2d(smem_b + i * Cfg::B_BYTES, &map_b, &full_bar[i], (kb0 + i) * BK, n_blk * BN);
+        }
+        pdl_wait();
+        for (int i = 0; i < npre; ++i)
+          tma_load_2d(smem_a + i * Cfg::A_BYTES, &map_a, &full_bar[i], (kb0 + i) * BK, m_blk * BM);
+        kb = kb0 + npre;
+        if (npre == STAGES) { stage = 0; phase = 1; } else { stage = npre; }
+      }
+      for (; kb < kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
         tma_load_2d(smem_a + stage * Cfg::A_BYTES, &map_a, &full_bar[stage], kb * BK, m_blk * BM);
@@ -235,6 +253,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int q = warp & 3;
     const int csel = (warp - 4) >> 2;
     const int rloc = q * 32 + lane;
+    pdl_wait();  // residual / gate / offset / workspace may be produced by the previous kernel
     long long c_off = 0;
     if (ep.c_off_ptr) c_off = static_cast<long long>(*ep.c_off_ptr) * ep.c_off_mul;
     const float gate = ep.gate ? tanhf(*ep.gate) : 1.0f;
@@ -397,8 +416,9 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, int M, int N,
   ep.ws_part = ws ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + SPLITK_COUNTER_BYTES) : nullptr;
   const int items = tiles * S;
   const int grid = items < num_sms() ? items : num_sms();
-  gemm_tc_kernel<BN, STAGES><<<grid, TC_THREADS, Cfg::SMEM_BYTES, stream>>>(ma, mb, M, N, K, ep);
-  WF_CHECK_LAUNCH();
+  WF_CHECK_CUDA(launch_pdl(0, gemm_tc_kernel<BN, STAGES>, dim3(grid), dim3(TC_THREADS), Cfg::SMEM_BYTES, stream, ma, mb, M,
+                           N, K, ep));
+  count_launch();
   return WF_OK;
 }
 

@@ -15,6 +15,7 @@ Data layout in HBM
 from __future__ import annotations
 
 import os
+import weakref
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence
 
@@ -42,6 +43,27 @@ def _to_dtype(t: Tensor, dt: torch.dtype) -> Tensor:
         src = t.contiguous()
         return nv.cast(src, torch.empty(src.shape, dtype=dt, device=src.device))
     return t.to(dt)  # fp16 boundary conversion only
+
+
+class PhaseTimer:
+    """Optional phase timing (WF_TIMING=1): CUDA events between the phases of one decode() call; the last call's
+    milliseconds are kept in ``PhaseTimer.last`` (read by bench.py / tools).  Disabled -> zero overhead."""
+    last: Dict[str, float] = {}
+
+    def __init__(self):
+        self.on = os.environ.get("WF_TIMING", "0") == "1"
+        self.marks = []
+
+    def mark(self, name: str):
+        if self.on:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.marks.append((name, ev))
+
+    def report(self):
+        if self.on and len(self.marks) > 1:
+            torch.cuda.synchronize()
+            PhaseTimer.last = {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(self.marks, self.marks[1:])}
 
 
 # ============================================================================ weight packing
@@ -390,34 +412,13 @@ class DecodeSession:
         self.T_cap = t_cap
         d, H = p.d, p.n_head
         self.gated = len(p.blocks) > 0 and len(p.blocks[0].x_attn) > 0
-        if self.gated and feats is None:
-            raise TypeError("object of type 'NoneType' has no len(): a gated x-attn model needs its feature input "
-                            "(pass x_v= to decode())")
-        feats = list(feats) if (self.gated and feats is not None) else []
-        if self.gated and len(feats) > len(p.blocks[0].x_attn):
-            raise ValueError(f"Got {len(feats)} translations but only support up to {len(p.blocks[0].x_attn)}")
-        xa2 = _to_dtype(xa, dt).contiguous().view(-1, d)
+        feats = self._check_feats(feats)
         self.Ta = Ta = xa.shape[1]
-        # ---- per-clip precompute: cross K/V and x-attn K/V for every layer
-        self.cross_kv: List[Tensor] = []
-        self.x_kv: List[List[Tensor]] = []
-        self.Tx: List[int] = []
-        fprep = [prepare_features(p, f, dt) for f in feats]
-        self.Tx = [f.shape[0] // B for f in fprep]
-        for bp in p.blocks:
-            kv = torch.empty((B, 2 * H, Ta, 64), dtype=dt, device=dev)
-            nv.linear(xa2, bp.cross.kv_w, kv.view(-1, 64), bias=bp.cross.kv_b, head_major=(2 * H, Ta, Ta))
-            self.cross_kv.append(kv)
-            per = []
-            for i, f in enumerate(fprep):
-                kvx = torch.empty((B, 2 * H, self.Tx[i], 64), dtype=dt, device=dev)
-                nv.linear(f, bp.x_attn[i].kv_w, kvx.view(-1, 64), bias=bp.x_attn[i].kv_b,
-                          head_major=(2 * H, self.Tx[i], self.Tx[i]))
-                per.append(kvx)
-            self.x_kv.append(per)
-        del fprep
-        # ---- step buffers
+        self.Tx = [f.shape[1] for f in feats]
         L = len(p.blocks)
+        # ---- per-clip K/V caches (head-major) and step buffers; contents are (re)filled by load()
+        self.cross_kv = [torch.empty((B, 2 * H, Ta, 64), dtype=dt, device=dev) for _ in range(L)]
+        self.x_kv = [[torch.empty((B, 2 * H, tx, 64), dtype=dt, device=dev) for tx in self.Tx] for _ in range(L)]
         self.self_kv = [torch.zeros((R, 2 * H, t_cap, 64), dtype=dt, device=dev) for _ in range(L)]
         self.gemm_ws = torch.zeros(4096 + 8 * 1024 * 1024, dtype=torch.uint8, device=dev)  # split-K counters + partials
         self.x = _empty(R, d, dt, dev)
@@ -432,10 +433,39 @@ class DecodeSession:
         self.tokens = torch.zeros((R, t_cap + 1), dtype=torch.int32, device=dev)
         self.sum_logprobs = torch.zeros(R, dtype=torch.float32, device=dev)
         self.no_speech_prob = torch.full((R,), float("nan"), dtype=torch.float32, device=dev)
+        self.suppress = torch.zeros(p.n_vocab, dtype=torch.uint8, device=dev)
+        self.suppress_first = torch.zeros(p.n_vocab, dtype=torch.uint8, device=dev)
         self.use_graph = use_graph and os.environ.get("WF_NO_GRAPH", "0") != "1"
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._graph_kernels = 0
+        self._graph_key = None
         self._sampler = None
+        self.load(xa, feats)
+
+    def _check_feats(self, feats) -> List[Tensor]:
+        if self.gated and feats is None:
+            raise TypeError("object of type 'NoneType' has no len(): a gated x-attn model needs its feature input "
+                            "(pass x_v= to decode())")
+        feats = list(feats) if (self.gated and feats is not None) else []
+        if self.gated and len(feats) > len(self.p.blocks[0].x_attn):
+            raise ValueError(f"Got {len(feats)} translations but only support up to {len(self.p.blocks[0].x_attn)}")
+        return feats
+
+    def shape_key(self):
+        return (self.dt, self.dev, self.B, self.G, self.T_cap, self.Ta, tuple(self.Tx), id(self.p))
+
+    def load(self, xa: Tensor, feats: Sequence[Tensor]):
+        """Per-clip precompute into the session's caches: cross-attention K/V of the encoder output and
+        x-attention K/V of the (projected, position-embedded) features, for every layer."""
+        p, dt, B, H = self.p, self.dt, self.B, self.p.n_head
+        xa2 = _to_dtype(xa, dt).contiguous().view(-1, p.d)
+        fprep = [prepare_features(p, f, dt) for f in feats]
+        for l, bp in enumerate(p.blocks):
+            nv.linear(xa2, bp.cross.kv_w, self.cross_kv[l].view(-1, 64), bias=bp.cross.kv_b,
+                      head_major=(2 * H, self.Ta, self.Ta))
+            for i, f in enumerate(fprep):
+                nv.linear(f, bp.x_attn[i].kv_w, self.x_kv[l][i].view(-1, 64), bias=bp.x_attn[i].kv_b,
+                          head_major=(2 * H, self.Tx[i], self.Tx[i]))
 
     # -- one decoder pass for the token at position state[0]; logits of that position land in self.logits
     def _forward_token(self):
@@ -492,7 +522,15 @@ class DecodeSession:
         self.state.copy_(torch.tensor([0, n_init, 0, 0, sot_index, 0, 0, 0], dtype=torch.int32))
         self.sum_logprobs.zero_()
         self.no_speech_prob.fill_(float("nan"))
-        self._sampler = (suppress, suppress_first, eot, no_speech, tuple(ts))
+        # the masks live in session-owned buffers so that a captured graph stays valid across decode() calls
+        self.suppress.copy_(suppress)
+        if suppress_first is not None:
+            self.suppress_first.copy_(suppress_first)
+        self._sampler = (self.suppress, self.suppress_first if suppress_first is not None else None, eot, no_speech,
+                         tuple(ts))
+        key = (suppress_first is not None, eot, no_speech, tuple(ts))
+        if key != self._graph_key:  # scalars baked into the captured launch changed: re-capture lazily
+            self._graph, self._graph_key = None, key
         self.n_init = n_init
 
     def _greedy_step(self):
@@ -548,12 +586,40 @@ class DecodeSession:
         elt = self.self_kv[0].element_size()
         row_bytes = self.T_cap * 2 * d * elt
         used = row_bytes  # head-major rows: the used positions are a prefix of every head segment, copy the row
-        new = []
+        # gather through a scratch layer and copy back: the cache buffers keep their addresses (captured graphs
+        # and cached sessions stay valid)
+        if getattr(self, "_kv_scratch", None) is None:
+            self._kv_scratch = torch.empty_like(self.self_kv[0])
         for kv in self.self_kv:
-            dst = torch.empty_like(kv)
-            nv.kv_gather_rows(kv, dst, src_index, self.R, row_bytes, used)
-            new.append(dst)
-        self.self_kv = new
+            nv.kv_gather_rows(kv, self._kv_scratch, src_index, self.R, row_bytes, used)
+            kv.copy_(self._kv_scratch)
+
+
+_SESSION_CACHE = weakref.WeakKeyDictionary()  # decoder module -> its last DecodeSession
+
+
+def get_session(dec, xa: Tensor, feats: Optional[Sequence[Tensor]], n_group: int, t_cap: int) -> DecodeSession:
+    """One cached session per decoder: a repeated decode() with the same shapes reuses the ~(B x 370 MB) K/V arena,
+    the step buffers and the captured CUDA graph instead of re-allocating and re-capturing them every call."""
+    dt = _engine_dtype(xa.dtype)
+    p = decoder_pack(dec, dt)
+    old = _SESSION_CACHE.get(dec)
+    n_feats = 0 if feats is None else len(feats)
+    if old is not None and os.environ.get("WF_NO_SESSION_CACHE", "0") != "1":
+        tx = tuple(f.shape[1] for f in feats) if (old.gated and feats is not None) else ()
+        key = (dt, xa.device, xa.shape[0], n_group, t_cap, xa.shape[1], tx, id(p))
+        if old.shape_key() == key and (not old.gated or n_feats == len(old.Tx)):
+            old.load(xa, old._check_feats(feats))
+            return old
+    _SESSION_CACHE.pop(dec, None)
+    del old
+    sess = DecodeSession(dec, xa, feats, n_group, t_cap)
+    _SESSION_CACHE[dec] = sess
+    return sess
+
+
+def clear_sessions() -> None:
+    _SESSION_CACHE.clear()
 
 
 # ============================================================================ stand-alone sub-module calls

@@ -288,8 +288,11 @@ class DecodingTask:
         tk = self.tokenizer
         n_audio = mel.shape[0]
         feats = _as_feature_list(x_v)
+        timing = _engine.PhaseTimer()
         with torch.cuda.device(mel.device):
+            timing.mark("start")
             audio_features = self._get_audio_features(mel)
+            timing.mark("encoder")
             init_rows = [list(self.initial_tokens) for _ in range(n_audio)]
             languages, language_probs = self._detect_language(audio_features, init_rows, feats)
             if self.options.task == "lang_id":
@@ -299,7 +302,8 @@ class DecodingTask:
             if n_sample <= 0:
                 raise ValueError("the prompt already fills the text context; nothing can be sampled")
             t_cap = self.sample_begin + n_sample
-            session = _engine.DecodeSession(self.model.decoder, audio_features, feats, self.n_group, t_cap)
+            session = _engine.get_session(self.model.decoder, audio_features, feats, self.n_group, t_cap)
+            timing.mark("kv_precompute")
             suppress, suppress_first = self._masks(mel.device)
             no_speech = tk.no_speech if tk.no_speech is not None else -1
             session.configure_greedy(self.initial_tokens, self.sot_index, suppress, suppress_first, tk.eot,
@@ -311,6 +315,8 @@ class DecodingTask:
                 cand, cand_lp, no_speech_probs = self._run_greedy(session, n_sample)
             else:
                 cand, cand_lp, no_speech_probs = self._run_beam(session, n_sample, init_rows)
+            timing.mark("decode_loop")
+            timing.report()
         # slice between the first sampled token and EOT, rank, build results (reference :757-798)
         cand = [[self._trim(seq) for seq in group] for group in cand]
         selected = self.sequence_ranker.rank(cand, cand_lp)
