@@ -240,13 +240,15 @@ def profile_kernels(model, pcm_dev, feat_dev, opt, B, step_ms):
     pk = peaks()
     rec = []
     nv.set_profiler(lambda fam, work, e0, e1: rec.append((fam, work, e0, e1)))
-    os.environ["WF_NO_GRAPH"] = "1"
+    os.environ["WF_NO_GRAPH"] = "1"          # every decode-step kernel becomes an individually timed launch
+    os.environ["WF_NO_SESSION_CACHE"] = "1"  # ... in a fresh session (the cached one replays its captured graph)
     try:
         hot_path_step(model, pcm_dev, feat_dev, opt)
         torch.cuda.synchronize()
     finally:
         nv.set_profiler(None)
         os.environ["WF_NO_GRAPH"] = "0"
+        os.environ["WF_NO_SESSION_CACHE"] = "0"
     fams = {}
     for fam, work, e0, e1 in rec:
         f = fams.setdefault(fam, {"ms": 0.0, "launches": 0, "flops": 0, "bytes": 0})

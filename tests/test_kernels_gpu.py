@@ -282,7 +282,8 @@ def _ref_attention(q, k, v, B, Tq, Tk, H, causal):
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 2e-2)])
 @pytest.mark.parametrize("B,Tq,Tk,H,causal", [(2, 1500, 1500, 6, False), (3, 37, 37, 6, True), (2, 8, 1500, 12, False),
-                                              (2, 70, 100, 6, False), (1, 130, 130, 20, True)])
+                                              (2, 70, 100, 6, False), (1, 130, 130, 20, True), (3, 300, 700, 2, False),
+                                              (1, 256, 256, 1, False), (2, 500, 1500, 20, False)])
 def test_attention_full_vs_torch(nv, dtype, tol, B, Tq, Tk, H, causal):
     d = H * 64
     qkv = _randn(B * Tq, 3 * d, dtype=dtype, seed=1)

@@ -8,6 +8,7 @@
 // head_dim is fixed at 64 (every Whisper size).
 #include "common.cuh"
 #include "kernels.h"
+#include <stdlib.h>
 
 namespace wf {
 
@@ -290,6 +291,9 @@ int attention_full(int dtype, const void* q, long long ldq, const void* k, long 
                "attention(bf16): q/k/v row strides must be multiples of 8 elements");
     const auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     WF_REQUIRE(al(q) && al(k) && al(v), "attention(bf16): q/k/v must be 16-byte aligned");
+    // long non-causal sequences (encoder self-attention, teacher-forced cross-attention): tcgen05 / TMEM kernel
+    if (!causal && Tq >= 256 && Tk >= 256 && ldo % 8 == 0 && al(o) && getenv("WF_NO_TC_ATTENTION") == nullptr)
+      return attention_full_tc(q, ldq, k, ldk, v, ldv, o, ldo, B, Tq, Tk, H, stream);
     dim3 grid((Tq + FA_BM - 1) / FA_BM, H, B);
     attn_bf16_kernel<<<grid, 128, 0, stream>>>((const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k, ldk,
                                                (const __nv_bfloat16*)v, ldv, (__nv_bfloat16*)o, ldo, Tq, Tk, H,

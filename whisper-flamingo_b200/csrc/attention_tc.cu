@@ -1,0 +1,278 @@
+// Flash attention on the 5th-gen tensor cores (bf16, head_dim 64, non-causal): the encoder's self-attention
+// (T = 1500) and every long cross-attention of the teacher-forced decoder pass.
+// Replaces reference whisper/model.py:93-108; scores live only in TMEM, never in HBM.
+//
+// One CTA per (batch, head, 256-query tile) = two 128-query warpgroups A and B sharing every K/V tile:
+//   warp 0 lane 0 : TMA producer  - Q_A, Q_B once, then K/V tiles of 128 keys through a 3-stage ring
+//   warp 1 lane 0 : MMA issuer    - S_w(j) = Q_w K(j)^T (128x128x64, fp32 in TMEM), O_w += P_w(j) V(j)
+//                                   (A = P_w from shared memory, B = V as an MN-major operand), interleaved so that
+//                                   the tensor pipe works for one warpgroup while the other does its exponentials
+//   warp 2        : TMEM allocator (S_A | S_B | O_A | O_B = 384 -> 512 columns)
+//   warps 4..11   : softmax warpgroups: one thread owns one query row = one TMEM lane, so row max / row sum need
+//                   no shuffles; exp2 with the 1/sqrt(64) scale folded in; P written as bf16 into a 128B-swizzled
+//                   K-major tile; O rescaled in TMEM (tcgen05.ld / tcgen05.st) only when the running max of some
+//                   row of the warp moved.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace wf {
+
+static constexpr int FT_M = 128;      // queries per softmax warpgroup
+static constexpr int FT_WG = 2;       // warpgroups (query tiles) per CTA: 256 queries share every K/V tile
+static constexpr int FT_N = 128;      // keys per tile
+static constexpr int FT_D = 64;       // head dim
+static constexpr int FT_STAGES = 3;
+static constexpr int FT_TILE = FT_N * FT_D * 2;             // 16 KB: one K (or V, or Q, or half-P) tile
+static constexpr int FT_OFF_KV = FT_WG * FT_TILE;           // after Q_A, Q_B
+static constexpr int FT_OFF_P = FT_OFF_KV + FT_STAGES * 2 * FT_TILE;
+static constexpr int FT_OFF_BAR = FT_OFF_P + FT_WG * 2 * FT_TILE;
+static constexpr int FT_SMEM = FT_OFF_BAR + 256 + 1024;
+static constexpr int FT_TMEM_COLS = 512;
+static constexpr int FT_COL_O = 256;                         // S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384)
+static constexpr int FT_THREADS = 128 + FT_WG * 128;
+
+__global__ void __launch_bounds__(FT_THREADS, 1)
+fa_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+             const __grid_constant__ CUtensorMap map_v, __nv_bfloat16* __restrict__ o, long long ldo, int Tq, int Tk) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FT_OFF_BAR);
+  uint64_t* q_full = bars;                           // [1]
+  uint64_t* kv_full = bars + 1;                      // [STAGES]
+  uint64_t* kv_empty = kv_full + FT_STAGES;          // [STAGES]
+  uint64_t* s_full = kv_empty + FT_STAGES;           // [WG]  S_w(j) landed in TMEM
+  uint64_t* s_free = s_full + FT_WG;                 // [WG]  S_w(j) has been read into registers
+  uint64_t* p_full = s_free + FT_WG;                 // [WG]  P_w(j) in smem, O_w rescaled
+  uint64_t* o_done = p_full + FT_WG;                 // [WG]  P_w(j) V(j) accumulated
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + FT_WG);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * (FT_WG * FT_M);
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int n_tiles = (Tk + FT_N - 1) / FT_N;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_q);
+    tma_prefetch_desc(&map_k);
+    tma_prefetch_desc(&map_v);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < FT_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < FT_WG; ++i) {
+      mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 128); mbar_init(&p_full[i], 128); mbar_init(&o_done[i], 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc<FT_TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    mbar_arrive_expect_tx(q_full, FT_WG * FT_TILE);
+    for (int w = 0; w < FT_WG; ++w) tma_load_2d(smem + w * FT_TILE, &map_q, q_full, h * FT_D, b * Tq + q0 + w * FT_M);
+    for (int j = 0; j < n_tiles; ++j) {
+      const int st = j % FT_STAGES;
+      mbar_wait(&kv_empty[st], ((j / FT_STAGES) & 1) ^ 1);
+      mbar_arrive_expect_tx(&kv_full[st], 2 * FT_TILE);
+      uint8_t* dst = smem + FT_OFF_KV + st * 2 * FT_TILE;
+      tma_load_2d(dst, &map_k, &kv_full[st], h * FT_D, b * Tk + j * FT_N);
+      tma_load_2d(dst + FT_TILE, &map_v, &kv_full[st], h * FT_D, b * Tk + j * FT_N);
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc_s = umma_idesc_bf16(FT_M, FT_N);        // S = Q K^T : both K-major
+    constexpr uint32_t idesc_o = umma_idesc_bf16(FT_M, FT_D, 1);     // O += P V  : B (= V) MN-major
+    auto issue_s = [&](int w, int j) {   // S_w(j) = Q_w K(j)^T  (kv_full(j) already observed by the caller)
+      const int st = j % FT_STAGES;
+      const uint64_t q_desc = umma_desc_kmajor_sw128(smem_u32(smem + w * FT_TILE));
+      const uint64_t k_desc = umma_desc_kmajor_sw128(smem_u32(smem + FT_OFF_KV + st * 2 * FT_TILE));
+#pragma unroll
+      for (int k = 0; k < FT_D / 16; ++k)
+        umma_f16(tmem_base + w * FT_N, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k > 0);
+      umma_commit(&s_full[w]);
+    };
+    auto issue_pv = [&](int w, int j) {  // O_w += P_w(j) V(j)
+      const int st = j % FT_STAGES;
+      const uint32_t v_addr = smem_u32(smem + FT_OFF_KV + st * 2 * FT_TILE + FT_TILE);
+      const uint32_t p_addr = smem_u32(smem + FT_OFF_P + w * 2 * FT_TILE);
+#pragma unroll
+      for (int kk = 0; kk < FT_N / 16; ++kk) {
+        // A: P half (kk / 4) of 64 keys, 16 keys (32 B) per step; B: V rows 16 kk .. 16 kk + 15 (two 1024-B groups)
+        const uint64_t a_desc = umma_desc_kmajor_sw128(p_addr + (kk >> 2) * FT_TILE) + 2 * (kk & 3);
+        const uint64_t b_desc = umma_desc_mnmajor_sw128(v_addr + kk * 2048);
+        umma_f16(tmem_base + FT_COL_O + w * FT_D, a_desc, b_desc, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+      }
+      umma_commit(&o_done[w]);
+    };
+    mbar_wait(q_full, 0);
+    mbar_wait(&kv_full[0], 0);
+    tc_fence_after();
+    issue_s(0, 0);
+    issue_s(1, 0);
+    for (int j = 0; j < n_tiles; ++j) {
+      const uint32_t ph = j & 1;
+      const bool more = j + 1 < n_tiles;
+      if (more) {
+        mbar_wait(&kv_full[(j + 1) % FT_STAGES], ((j + 1) / FT_STAGES) & 1);
+        mbar_wait(&s_free[0], ph);        // warpgroup A has pulled S_A(j) out of TMEM
+        tc_fence_after();
+        issue_s(0, j + 1);
+      }
+      mbar_wait(&p_full[0], ph);
+      tc_fence_after();
+      issue_pv(0, j);
+      if (more) {
+        mbar_wait(&s_free[1], ph);
+        tc_fence_after();
+        issue_s(1, j + 1);
+      }
+      mbar_wait(&p_full[1], ph);
+      tc_fence_after();
+      issue_pv(1, j);
+      umma_commit(&kv_empty[j % FT_STAGES]);  // both warpgroups are done with K(j), V(j)
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ softmax / correction / epilogue
+    const int w = (warp - 4) >> 2;                                   // warpgroup = query tile
+    const int qd = warp & 3;
+    const int r = qd * 32 + lane;                                   // query row in the tile == TMEM lane
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16);
+    const uint32_t s_addr = lane_addr + w * FT_N;
+    const uint32_t o_addr = lane_addr + FT_COL_O + w * FT_D;
+    uint8_t* p_buf = smem + FT_OFF_P + w * 2 * FT_TILE;
+    const float sl2 = 0.125f * 1.44269504088896340736f;              // 64^-0.5 * log2(e)
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < n_tiles; ++j) {
+      const uint32_t ph = j & 1;
+      const int kbase = j * FT_N;
+      const bool tail = kbase + FT_N > Tk;
+      mbar_wait(&s_full[w], ph);
+      tc_fence_after();
+      // one pass over TMEM: the whole 128-wide score row of this thread goes to registers
+      uint32_t sv[4][32];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld_32x32(s_addr + c * 32, sv[c]);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&s_free[w]);                                       // the tensor core may overwrite S_w now
+      if (tail) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (kbase + c * 32 + i >= Tk) sv[c][i] = 0xff800000u;  // -inf: masked key
+      }
+      float mx4[4] = {m_run, -INFINITY, -INFINITY, -INFINITY};      // four independent chains (one warp per SMSP:
+#pragma unroll                                                      //  dependency latency is not hidden by TLP)
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(sv[c][i]));
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      const float alpha = ex2_approx((m_run - mx) * sl2);            // 0 on the first tile (m_run = -inf)
+      const float msc = mx * sl2;
+      // p = exp2(s * sl2 - m * sl2), packed to bf16 pairs in place (overlaps the P V MMA of the previous tile)
+      float ps4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float e0 = ex2_approx(fmaf(__uint_as_float(sv[c][i]), sl2, -msc));
+          const float e1 = ex2_approx(fmaf(__uint_as_float(sv[c][i + 1]), sl2, -msc));
+          ps4[(i >> 1) & 3] += e0 + e1;
+          sv[c][i >> 1] = pack_bf16(e0, e1);                          // slot i/2 <= i: already consumed
+        }
+      const float psum = (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
+      // O *= alpha (only when some row of this warp moved its max); PV_w(j-1) must have completed first
+      if (j > 0) {
+        mbar_wait(&o_done[w], (j - 1) & 1);
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+          uint32_t ov[2][32];
+          tmem_ld_32x32(o_addr, ov[0]);
+          tmem_ld_32x32(o_addr + 32, ov[1]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) ov[c][i] = __float_as_uint(__uint_as_float(ov[c][i]) * alpha);
+          tmem_st_32x32(o_addr, ov[0]);
+          tmem_st_32x32(o_addr + 32, ov[1]);
+          tmem_st_wait();
+        }
+      }
+      l_run = l_run * alpha + psum;
+      m_run = mx;
+      // P -> 128B-swizzled K-major tile (two 64-key halves); its previous reader PV_w(j-1) has completed
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint8_t* row_base = p_buf + (c >> 1) * FT_TILE + r * 128;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int ch = (c & 1) * 4 + g;                             // 16-byte chunk within the 128-byte row
+          *reinterpret_cast<uint4*>(row_base + ((ch ^ (r & 7)) << 4)) =
+              make_uint4(sv[c][g * 4], sv[c][g * 4 + 1], sv[c][g * 4 + 2], sv[c][g * 4 + 3]);
+        }
+      }
+      fence_proxy_async_smem();   // P (generic-proxy stores) must be visible to the tensor core's async proxy
+      tc_fence_before();
+      mbar_arrive(&p_full[w]);
+    }
+    // ---- epilogue: O / l -> bf16 -> global (one 128-byte row segment per thread)
+    mbar_wait(&o_done[w], (n_tiles - 1) & 1);
+    tc_fence_after();
+    const float inv = 1.0f / l_run;
+    const int row = q0 + w * FT_M + r;
+    __nv_bfloat16* orow = o + (static_cast<long long>(b) * Tq + row) * ldo + h * FT_D;
+#pragma unroll 1
+    for (int c = 0; c < FT_D / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32(o_addr + c * 32, v);
+      tmem_ld_wait();
+      if (row < Tq) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 u;
+          u.x = pack_bf16(__uint_as_float(v[g * 8 + 0]) * inv, __uint_as_float(v[g * 8 + 1]) * inv);
+          u.y = pack_bf16(__uint_as_float(v[g * 8 + 2]) * inv, __uint_as_float(v[g * 8 + 3]) * inv);
+          u.z = pack_bf16(__uint_as_float(v[g * 8 + 4]) * inv, __uint_as_float(v[g * 8 + 5]) * inv);
+          u.w = pack_bf16(__uint_as_float(v[g * 8 + 6]) * inv, __uint_as_float(v[g * 8 + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = u;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<FT_TMEM_COLS>(tmem_base);
+  }
+}
+
+int attention_full_tc(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                      void* o, long long ldo, int B, int Tq, int Tk, int H, cudaStream_t stream) {
+  WF_REQUIRE(ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0, "attention(tc): output must be 16-byte aligned");
+  CUtensorMap mq, mk, mv;
+  int rc = make_map_bf16(&mq, q, static_cast<long long>(B) * Tq, static_cast<long long>(H) * FT_D, ldq, FT_M);
+  if (rc) return rc;
+  rc = make_map_bf16(&mk, k, static_cast<long long>(B) * Tk, static_cast<long long>(H) * FT_D, ldk, FT_N);
+  if (rc) return rc;
+  rc = make_map_bf16(&mv, v, static_cast<long long>(B) * Tk, static_cast<long long>(H) * FT_D, ldv, FT_N);
+  if (rc) return rc;
+  static bool configured = false;
+  if (!configured) {
+    WF_CHECK_CUDA(cudaFuncSetAttribute(fa_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
+    configured = true;
+  }
+  dim3 grid((Tq + FT_WG * FT_M - 1) / (FT_WG * FT_M), H, B);
+  fa_tc_kernel<<<grid, FT_THREADS, FT_SMEM, stream>>>(mq, mk, mv, reinterpret_cast<__nv_bfloat16*>(o), ldo, Tq, Tk);
+  WF_CHECK_LAUNCH();
+  return WF_OK;
+}
+
+}  // namespace wf

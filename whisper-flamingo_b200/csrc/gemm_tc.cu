@@ -362,8 +362,7 @@ static PFN_encodeTiled get_encode_fn() {
 }
 
 // 2-D row-major bf16 matrix [rows, cols] with row stride ld (elements); box = [box_rows, 64 cols], 128B swizzle.
-static int make_map_bf16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld,
-                         int box_rows) {
+int make_map_bf16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows) {
   PFN_encodeTiled fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled entry point not available");

@@ -53,6 +53,10 @@ int attention_full(int dtype, const void* q, long long ldq, const void* k, long 
                    long long ldv, void* o, long long ldo, int B, int Tq, int Tk, int H, int causal,
                    cudaStream_t stream);
 
+// attention_tc.cu (tcgen05 flash attention, bf16 non-causal)
+int attention_full_tc(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                      void* o, long long ldo, int B, int Tq, int Tk, int H, cudaStream_t stream);
+
 // decode.cu
 int attention_decode(int dtype, const void* q, long long ldq, const void* kc, const void* vc, long long ld_kv,
                      long long kv_batch_stride, long long kv_head_stride, void* o, long long ldo, int R, int G, int H,
