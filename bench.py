@@ -158,13 +158,11 @@ def run_product(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    from whisper.parallel import gather_token_matrix
+
     def gather_tokens(results):
         toks = torch.tensor([r.tokens for r in results], dtype=torch.int32, device=dev)
-        if dist is not None:  # the only collective of the job: final result gather over NVLink
-            out = [torch.empty_like(toks) for _ in range(world)]
-            dist.all_gather(out, toks)
-            toks = torch.cat(out)
-        return toks
+        return gather_token_matrix(toks, 50257)  # the only collective of the job: final result gather over NVLink
 
     def device_step():
         return gather_tokens(hot_path_step(model, pcm_dev, feat_dev, opt))
@@ -216,7 +214,7 @@ def run_product(args):
                    "global_batch": B * world, "parallelism": f"dp{world}", "l2": "inputs_larger_than_l2",
                    "random_init_weights": True},
         "e2e": {"value": audio_s / (ms_e2e / 1e3), "unit": "audio-s/s",
-                "h2d_bytes_per_step": pcm_host.numel() * 4 + feat_host.numel() * 4,
+                "h2d_bytes_per_step": (pcm_host.numel() * 4 + feat_host.numel() * 4) * world,
                 "d2h_bytes_per_step": B * world * SAMPLE_LEN * 4},
         "gpu_launches": launches, "clocks": clocks,
     }

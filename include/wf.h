@@ -139,6 +139,8 @@ typedef struct {
   int timestamp_begin; /* ApplyTimestampRules (decoding.py:445-509); < 0 disables them */
   int no_timestamps;   /* id or -1 */
   int max_initial_ts;  /* max_initial_timestamp_index or -1 */
+  float temperature;   /* 0 = greedy argmax; > 0 = sample softmax(logits / T) (decoding.py:286-287) */
+  unsigned long long seed; /* RNG stream for temperature > 0; XORed with the 64-bit value in state[5] | state[6] << 32 */
 } wf_sample_t;
 int wf_sample_greedy(const wf_sample_t* args, wf_stream_t stream);
 int wf_step_advance(int* state, int R, wf_stream_t stream);

@@ -233,6 +233,18 @@ def main():
     dec_gold["greedy_av"] = {"spec": spec_to_json(spec_av), "tokens": [a[0] for a in av_ref],
                              "avg_logprob": [a[1] for a in av_ref], "no_speech_prob": nsp_ref,
                              "feat_frames": 100, "feat_dim": 1024}
+    # 3e. long-form transcribe(): 75 s of synthetic audio, 3 windows, temperature 0, thresholds
+    # off (no random fallback), 16 sampled tokens per window, conditioning on the previous text
+    from ref_whisper.transcribe import transcribe as ref_transcribe
+    long_pcm = synth.synthetic_pcm(1, n_samples=75 * 16000, seed=99)[0].numpy()
+    tr = ref_transcribe(model_a, long_pcm, temperature=0.0, compression_ratio_threshold=None, logprob_threshold=None,
+                        no_speech_threshold=None, language="en", fp16=False, sample_len=16, verbose=None)
+    print(f"  reference transcribe(): {len(tr['segments'])} segments, seeks {[s['seek'] for s in tr['segments']]}")
+    dec_gold["transcribe_long"] = {
+        "seconds": 75, "seed": 99, "text": tr["text"], "language": tr["language"],
+        "segments": [{k: (s[k] if k != "tokens" else list(map(int, s[k]))) for k in
+                      ("id", "seek", "start", "end", "text", "tokens", "temperature", "avg_logprob", "no_speech_prob")}
+                     for s in tr["segments"]]}
     with open(os.path.join(GOLD, "decode_tiny.json"), "w") as fh:
         json.dump({"meta": meta, "dims": TINY, "cases": dec_gold}, fh, indent=1)
     print("golden fixtures written to", GOLD)

@@ -173,3 +173,56 @@ def test_bf16_greedy_decode_runs_and_agrees_mostly(av_model, mel2):
     assert all(r.tokens[0] == g[0] for r, g in zip(res, gold["tokens"])) and min(agree) >= 0.5, agree
     for r, lp in zip(res, gold["avg_logprob"]):
         assert abs(r.avg_logprob - lp) < 0.15
+
+
+def test_transcribe_long_form_matches_reference_golden(a_model):
+    """the 30-s sliding-window driver (reference whisper/transcribe.py:38-383) over 75 s of
+    synthetic audio - same seeks, segment boundaries, tokens and text as the unmodified reference."""
+    import whisper
+    from whisper._synthetic import synthetic_pcm
+    gold = load_decode_golden()["cases"]["transcribe_long"]
+    pcm = synthetic_pcm(1, n_samples=gold["seconds"] * 16000, seed=gold["seed"])[0]
+    out = whisper.transcribe(a_model, pcm.numpy(), temperature=0.0, compression_ratio_threshold=None,
+                             logprob_threshold=None, no_speech_threshold=None, language="en", fp16=False,
+                             sample_len=16, verbose=None)
+    assert out["language"] == gold["language"] and out["text"] == gold["text"]
+    assert len(out["segments"]) == len(gold["segments"])
+    for s, g in zip(out["segments"], gold["segments"]):
+        assert (s["id"], s["seek"], s["tokens"], s["text"]) == (g["id"], g["seek"], g["tokens"], g["text"])
+        assert abs(s["start"] - g["start"]) < 1e-6 and abs(s["end"] - g["end"]) < 1e-6
+        assert abs(s["avg_logprob"] - g["avg_logprob"]) < 1e-4 and abs(s["no_speech_prob"] - g["no_speech_prob"]) < 1e-6
+    # bound method, as the reference exposes it (model.py:428)
+    assert a_model.transcribe(pcm.cuda(), temperature=0.0, language="en", fp16=False, sample_len=16,
+                              no_speech_threshold=None, logprob_threshold=None,
+                              compression_ratio_threshold=None)["text"] == gold["text"]
+    with pytest.raises(NotImplementedError):
+        whisper.transcribe(a_model, pcm.numpy(), word_timestamps=True)
+
+
+def test_temperature_sampling_seeded_best_of_and_beam(a_model, mel2):
+    """temperature > 0 through the public API (reference decoding.py:286-287, 553-559, 753-757): reproducible
+    under torch.manual_seed, best_of keeps the most likely of n independent samples, beam search ignores T.
+    (The distribution itself is checked at kernel level in test_kernels_gpu.)"""
+    import whisper
+    T = 0.7
+    sopt = whisper.DecodingOptions(language="en", without_timestamps=True, sample_len=8, fp16=False, temperature=T)
+
+    def run(seed):
+        torch.manual_seed(seed)
+        whisper.decoding.DecodingTask._sample_calls = 0
+        return [r.tokens for r in whisper.decode(a_model, mel2, sopt)]
+
+    a, b, c = run(7), run(7), run(8)
+    assert a == b and a != c and all(len(t) == 8 for t in a)
+    greedy = whisper.decode(a_model, mel2, whisper.DecodingOptions(language="en", without_timestamps=True,
+                                                                   sample_len=8, fp16=False))
+    assert a != [r.tokens for r in greedy]
+    best = whisper.decode(a_model, mel2, whisper.DecodingOptions(language="en", without_timestamps=True, sample_len=8,
+                                                                 fp16=False, temperature=T, best_of=5))
+    assert len(best) == 2 and all(len(r.tokens) == 8 and r.temperature == T for r in best)
+    with pytest.raises(ValueError):
+        whisper.decode(a_model, mel2, whisper.DecodingOptions(language="en", fp16=False, best_of=5))
+    # beam search ignores the temperature (reference decoding.py:553-559): same tokens as at T = 0
+    bopt = dict(language="en", without_timestamps=True, sample_len=8, fp16=False, beam_size=2)
+    assert (whisper.decode(a_model, mel2[0], whisper.DecodingOptions(temperature=T, **bopt)).tokens
+            == whisper.decode(a_model, mel2[0], whisper.DecodingOptions(**bopt)).tokens)

@@ -385,6 +385,42 @@ def test_sample_greedy_and_topk_vs_torch(nv):
     assert idx.tolist() == ti.tolist() and (vals - tv).abs().max().item() <= 1e-4
 
 
+def test_sample_temperature_follows_softmax(nv):
+    """temperature > 0 (reference decoding.py:286-291: Categorical(logits / T).sample(), sum_logprobs from the
+    UN-tempered log_softmax): Gumbel-max with a counter RNG must reproduce softmax(filtered logits / T).  The random
+    stream is not torch's, so the check is statistical: 8192 rows sharing one logits row, 5-sigma binomial bounds."""
+    R, V, eot, nosp, T = 8192, 51865, 50257, 50362, 0.7
+    row = _randn(1, V + 7, seed=3, scale=2.0)
+    row[0, 1000:1006] += 9.0  # a handful of likely tokens so that the empirical frequencies are measurable
+    logits = row.expand(R, -1).contiguous()
+    sup = torch.zeros(V, dtype=torch.uint8, device="cuda")
+    sup[[1002, nosp]] = 1
+    n_init = 2
+    tokens = torch.zeros((R, 8), dtype=torch.int32, device="cuda")
+    tokens[:, :n_init] = torch.tensor([50258, 50363], dtype=torch.int32)
+    state = torch.tensor([n_init - 1, n_init, 0, 0, 0, 0, 0, 0], dtype=torch.int32, device="cuda")
+    slp = torch.zeros(R, device="cuda")
+    nsp = torch.zeros(R, device="cuda")
+    nv.sample_greedy(logits, V, sup, None, tokens, state, slp, nsp, eot, nosp, (-1, -1, -1), T, 1234)
+    got = tokens[:, n_init].long()
+    masked = row[0, :V].double().clone()
+    masked[sup.bool()] = -np.inf
+    p = torch.softmax(masked / T, -1)
+    assert not sup.bool()[got].any()
+    top = torch.topk(p, 6).indices
+    emp = torch.stack([(got == i).double().mean() for i in top])
+    sigma = torch.sqrt(p[top] * (1 - p[top]) / R)
+    assert ((emp - p[top]).abs() <= 5 * sigma + 5e-4).all(), (emp, p[top])
+    want_lp = torch.log_softmax(masked, -1)[got]
+    assert (slp.double() - want_lp).abs().max().item() <= 1e-3
+    # deterministic in (seed, row, position); a different seed gives a different draw
+    tok2 = tokens.clone(); tok2[:, n_init:] = 0
+    nv.sample_greedy(logits, V, sup, None, tok2, state, slp, nsp, eot, nosp, (-1, -1, -1), T, 1234)
+    assert torch.equal(tok2[:, n_init], tokens[:, n_init])
+    nv.sample_greedy(logits, V, sup, None, tok2, state, slp, nsp, eot, nosp, (-1, -1, -1), T, 99)
+    assert not torch.equal(tok2[:, n_init], tokens[:, n_init])
+
+
 def test_kv_gather_rows(nv):
     src = _randn(8, 10, 128, dtype=torch.bfloat16, seed=1)
     dst = torch.zeros_like(src)

@@ -145,6 +145,8 @@ int wf_sample_greedy(const wf_sample_t* a, wf_stream_t stream) {
   s.suppress_first = a->suppress_first; s.tokens = a->tokens; s.T_cap = a->T_cap; s.state = a->state;
   s.sum_logprobs = a->sum_logprobs; s.no_speech_prob = a->no_speech_prob; s.eot = a->eot; s.no_speech = a->no_speech;
   s.timestamp_begin = a->timestamp_begin; s.no_timestamps = a->no_timestamps; s.max_initial_ts = a->max_initial_ts;
+  s.temperature = a->temperature; s.seed = a->seed;
+  WF_REQUIRE(s.temperature >= 0.f, "wf_sample_greedy: negative temperature");
   WF_REQUIRE(s.sum_logprobs && s.no_speech_prob, "wf_sample_greedy: null output buffer");
   return sample_greedy(s, S(stream));
 }

@@ -569,7 +569,19 @@ __device__ void apply_timestamp_mass_rule(RowMask& m, const float* lg, int V, co
   if (ts.v + logf(se) > text.v) m.text_end = m.tb;
 }
 
+// counter-based uniform in (0,1): splitmix64 finaliser over (seed, row, position, token id)
+__device__ __forceinline__ float uniform01(unsigned long long seed, int row, int pos, int tok) {
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (static_cast<unsigned long long>(row) * 1000003ull + pos) +
+                         0xD1B54A32D192ED03ull * static_cast<unsigned long long>(tok + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (static_cast<float>(z >> 40) + 0.5f) * (1.0f / 16777216.0f);
+}
+
 // state: [0]=t (position of the token fed this step) [1]=n_init [2]=all_done [3]=#rows at EOT this step [4]=sot_index
+//        [5],[6]=low/high word of a per-call RNG seed (temperature > 0), XORed with SampleArgs.seed: the seed changes
+//        from call to call without re-capturing the CUDA graph the launch is part of
 __global__ void __launch_bounds__(256) sample_greedy_kernel(SampleArgs a) {
   __shared__ ArgMax sh_am[8];
   __shared__ float sh_f[8];
@@ -603,13 +615,31 @@ __global__ void __launch_bounds__(256) sample_greedy_kernel(SampleArgs a) {
   for (int i = threadIdx.x; i < a.V; i += blockDim.x)
     if (!is_masked(m, i, a.suppress, a.suppress_first)) se += expf(lg[i] - am.v);
   se = block_sum(se, sh_f);
+  int chosen = am.i;
+  float chosen_logit = am.v;
+  if (a.temperature > 0.f) {
+    // Gumbel-max: argmax_i (x_i / T + G_i), G_i = -log(-log u_i)  ~  Categorical(softmax(x / T))
+    const float inv_t = 1.0f / a.temperature;
+    const unsigned long long seed = a.seed ^ (static_cast<unsigned long long>(static_cast<unsigned>(a.state[5])) |
+                                              (static_cast<unsigned long long>(static_cast<unsigned>(a.state[6])) << 32));
+    ArgMax gm{-INFINITY, 0x7fffffff};
+    for (int i = threadIdx.x; i < a.V; i += blockDim.x)
+      if (!is_masked(m, i, a.suppress, a.suppress_first)) {
+        const float u = uniform01(seed, r, t, i);
+        gm = better(gm, ArgMax{lg[i] * inv_t - logf(-logf(u)), i});
+      }
+    gm = block_argmax(gm, sh_am);
+    chosen = gm.i;
+    chosen_logit = lg[chosen];
+  }
   if (threadIdx.x == 0) {
     const int prev = row[t];
-    int next = am.i;
+    int next = chosen;
     if (prev == a.eot) {
       next = a.eot;  // finished rows keep emitting EOT and stop accumulating (decoding.py:291-293)
     } else {
-      a.sum_logprobs[r] += -logf(se);  // log_softmax at the argmax = -(log sum exp(x - max))
+      // log_softmax(filtered logits)[next] = x_next - max - log sum exp(x - max)   (un-tempered, decoding.py:289-291)
+      a.sum_logprobs[r] += (chosen_logit - am.v) - logf(se);
     }
     row[t + 1] = next;
     if (next == a.eot) atomicAdd(&a.state[3], 1);

@@ -426,8 +426,13 @@ int linear_bf16_tc(const void* A, long long lda, const void* W, long long ldw, i
   WF_REQUIRE(M > 0 && N > 0 && K > 0, "linear: empty problem M=%d N=%d K=%d", M, N, K);
   int bn = tile_hint;
   if (bn == 0) {
-    if (M <= 256) bn = (N >= 16384) ? 128 : (N >= 4096 ? 64 : 32);  // decode: many narrow tiles stream the weights
-    else bn = N >= 256 ? 256 : 128;
+    if (M <= 256) {
+      // decode: many narrow tiles stream the weights (split-K with 64-wide tiles was measured slower: the last CTA
+      // of a tile reduces S x 32 KB of partials alone)
+      bn = (N >= 16384) ? 128 : (N >= 4096 ? 64 : 32);
+    } else {
+      bn = N >= 256 ? 256 : 128;
+    }
   }
   WF_REQUIRE(bn == 32 || bn == 64 || bn == 128 || bn == 256, "linear: unsupported tile hint %d", tile_hint);
   if (e.hm_heads > 0) {

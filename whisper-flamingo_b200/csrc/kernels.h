@@ -81,6 +81,10 @@ struct SampleArgs {
   int timestamp_begin;
   int no_timestamps;              // token id or -1
   int max_initial_ts;             // max_initial_timestamp_index or -1
+  // temperature > 0: sample from softmax(logits / T) (GreedyDecoder with Categorical, decoding.py:286-287) by the
+  // Gumbel-max trick with a counter-based RNG keyed on (seed, row, position, token)
+  float temperature;
+  unsigned long long seed;
 };
 int sample_greedy(const SampleArgs& a, cudaStream_t stream);
 int step_advance(int* state, int R, cudaStream_t stream);

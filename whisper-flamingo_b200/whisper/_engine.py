@@ -514,12 +514,16 @@ class DecodeSession:
 
     # -- greedy ---------------------------------------------------------------------------------------
     def configure_greedy(self, initial_tokens: Sequence[int], sot_index: int, suppress: Tensor,
-                         suppress_first: Optional[Tensor], eot: int, no_speech: int, ts: Sequence[int]):
+                         suppress_first: Optional[Tensor], eot: int, no_speech: int, ts: Sequence[int],
+                         temperature: float = 0.0, seed: int = 0):
         n_init = len(initial_tokens)
         init = torch.tensor(list(initial_tokens), dtype=torch.int32, device=self.dev)
         self.tokens.zero_()
         self.tokens[:, :n_init] = init
-        self.state.copy_(torch.tensor([0, n_init, 0, 0, sot_index, 0, 0, 0], dtype=torch.int32))
+        seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        lo, hi = seed & 0xFFFFFFFF, seed >> 32
+        lo, hi = (lo - (1 << 32) if lo >= (1 << 31) else lo), (hi - (1 << 32) if hi >= (1 << 31) else hi)
+        self.state.copy_(torch.tensor([0, n_init, 0, 0, sot_index, lo, hi, 0], dtype=torch.int32))
         self.sum_logprobs.zero_()
         self.no_speech_prob.fill_(float("nan"))
         # the masks live in session-owned buffers so that a captured graph stays valid across decode() calls
@@ -527,17 +531,18 @@ class DecodeSession:
         if suppress_first is not None:
             self.suppress_first.copy_(suppress_first)
         self._sampler = (self.suppress, self.suppress_first if suppress_first is not None else None, eot, no_speech,
-                         tuple(ts))
-        key = (suppress_first is not None, eot, no_speech, tuple(ts))
+                         tuple(ts), float(temperature), 0)
+        # the per-call seed lives in device memory (state[5:7]) so that a new seed does not re-capture the graph
+        key = (suppress_first is not None, eot, no_speech, tuple(ts), float(temperature))
         if key != self._graph_key:  # scalars baked into the captured launch changed: re-capture lazily
             self._graph, self._graph_key = None, key
         self.n_init = n_init
 
     def _greedy_step(self):
         self._forward_token()
-        suppress, suppress_first, eot, no_speech, ts = self._sampler
+        suppress, suppress_first, eot, no_speech, ts, temperature, seed = self._sampler
         nv.sample_greedy(self.logits, self.p.n_vocab, suppress, suppress_first, self.tokens, self.state,
-                         self.sum_logprobs, self.no_speech_prob, eot, no_speech, ts)
+                         self.sum_logprobs, self.no_speech_prob, eot, no_speech, ts, temperature, seed)
         nv.step_advance(self.state, self.R)
 
     def run_greedy(self, n_sample: int, check_every: int = 8) -> int:

@@ -37,7 +37,8 @@ class _Sample(C.Structure):
                 ("suppress", C.c_void_p), ("suppress_first", C.c_void_p), ("tokens", C.c_void_p),
                 ("T_cap", C.c_int), ("state", C.c_void_p), ("sum_logprobs", C.c_void_p),
                 ("no_speech_prob", C.c_void_p), ("eot", C.c_int), ("no_speech", C.c_int),
-                ("timestamp_begin", C.c_int), ("no_timestamps", C.c_int), ("max_initial_ts", C.c_int)]
+                ("timestamp_begin", C.c_int), ("no_timestamps", C.c_int), ("max_initial_ts", C.c_int),
+                ("temperature", C.c_float), ("seed", C.c_ulonglong)]
 
 
 class _Topk(C.Structure):
@@ -324,13 +325,15 @@ def attention_decode(q: torch.Tensor, kc: torch.Tensor, vc: torch.Tensor, ld_kv:
 
 def sample_greedy(logits: torch.Tensor, v: int, suppress: torch.Tensor, suppress_first: Optional[torch.Tensor],
                   tokens: torch.Tensor, state: torch.Tensor, sum_logprobs: torch.Tensor,
-                  no_speech_prob: torch.Tensor, eot: int, no_speech: int, ts=(-1, -1, -1)) -> None:
+                  no_speech_prob: torch.Tensor, eot: int, no_speech: int, ts=(-1, -1, -1),
+                  temperature: float = 0.0, seed: int = 0) -> None:
     """ts = (timestamp_begin | -1, no_timestamps | -1, max_initial_timestamp_index | -1)."""
     assert logits.dtype == torch.float32 and tokens.dtype == torch.int32 and state.dtype == torch.int32
     assert suppress.dtype == torch.uint8 and suppress.numel() >= v
     a = _Sample(logits.data_ptr(), _row_stride(logits), logits.shape[0], v, suppress.data_ptr(),
                 _ptr(suppress_first), tokens.data_ptr(), tokens.shape[1], state.data_ptr(),
-                sum_logprobs.data_ptr(), no_speech_prob.data_ptr(), eot, no_speech, ts[0], ts[1], ts[2])
+                sum_logprobs.data_ptr(), no_speech_prob.data_ptr(), eot, no_speech, ts[0], ts[1], ts[2],
+                float(temperature), int(seed) & 0xFFFFFFFFFFFFFFFF)
     with _Prof("sample_greedy", bytes=2 * logits.shape[0] * v * 4):
         _check(load().wf_sample_greedy(C.byref(a), _stream()))
 

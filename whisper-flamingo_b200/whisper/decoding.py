@@ -14,8 +14,9 @@ autoregressive loop moved onto the GPU:
   (SURVEY.md F5); beam search works for any batch size (reference: batch 1 only, F7).
 
 ``fp16=True`` (the default) selects the bf16 tensor-core engine, ``fp16=False`` the token-exact
-fp32 engine.  Temperature sampling (``temperature > 0`` / ``best_of``) is not on the hot path and
-raises ``NotImplementedError``.
+fp32 engine.  ``temperature > 0`` (optionally with ``best_of``) samples on the device with the
+Gumbel-max trick and a counter-based RNG seeded from ``torch.initial_seed()``: same distribution as
+the reference's ``Categorical(logits / T).sample()``, not the same random stream.
 """
 from __future__ import annotations
 
@@ -178,6 +179,8 @@ class _BeamBook:
 
 
 class DecodingTask:
+    _sample_calls = 0  # advances the sampling RNG stream from call to call (seeded by torch.manual_seed)
+
     def __init__(self, model: "Whisper", options: DecodingOptions):
         self.model = model
         language = options.language or "en"
@@ -282,9 +285,6 @@ class DecodingTask:
     @torch.no_grad()
     def run(self, mel: Tensor, x_v=None, test_a: bool = False, test_v: bool = False) -> List[DecodingResult]:
         nv.require_cuda(mel)
-        if self.options.temperature != 0:
-            raise NotImplementedError("temperature sampling / best_of is not implemented by the CUDA engine "
-                                      "(greedy and beam search are)")
         tk = self.tokenizer
         n_audio = mel.shape[0]
         feats = _as_feature_list(x_v)
@@ -306,8 +306,13 @@ class DecodingTask:
             timing.mark("kv_precompute")
             suppress, suppress_first = self._masks(mel.device)
             no_speech = tk.no_speech if tk.no_speech is not None else -1
+            DecodingTask._sample_calls += 1
             session.configure_greedy(self.initial_tokens, self.sot_index, suppress, suppress_first, tk.eot,
-                                     no_speech, self.ts_params)
+                                     no_speech, self.ts_params,
+                                     # beam search ignores the temperature (reference :553-559 picks the decoder
+                                     # from beam_size alone)
+                                     temperature=0.0 if self.options.beam_size else float(self.options.temperature),
+                                     seed=(torch.initial_seed() + 0x9E3779B9 * DecodingTask._sample_calls))
             if any(r != list(self.initial_tokens) for r in init_rows):  # detected language tokens differ per clip
                 rows = torch.tensor(init_rows, dtype=torch.int32, device=mel.device)
                 session.tokens[:, : self.sample_begin] = rows.repeat_interleave(self.n_group, dim=0)
@@ -344,8 +349,12 @@ class DecodingTask:
         toks = session.tokens[:, : self.sample_begin + n_sample].cpu().tolist()
         lps = session.sum_logprobs.cpu().tolist()
         nsp = session.no_speech_prob.cpu().tolist()
-        # GreedyDecoder.finalize pads one EOT so that every row has one (reference :299-302)
-        return [[row + [self.tokenizer.eot]] for row in toks], [[lp] for lp in lps], nsp
+        # GreedyDecoder.finalize pads one EOT so that every row has one (reference :299-302); with best_of the
+        # n_group rows of an audio are its independent samples (reference :753-757)
+        G, eot = self.n_group, self.tokenizer.eot
+        cand = [[toks[a * G + g] + [eot] for g in range(G)] for a in range(len(toks) // G)]
+        cand_lp = [[lps[a * G + g] for g in range(G)] for a in range(len(toks) // G)]
+        return cand, cand_lp, nsp[::G]
 
     def _run_beam(self, session: "_engine.DecodeSession", n_sample: int, init_rows: List[List[int]]):
         G, tk, n_init = self.n_group, self.tokenizer, self.sample_begin
@@ -353,7 +362,7 @@ class DecodingTask:
         book = _BeamBook(G, tk.eot, self.options.patience, session.B)
         rows = [list(init_rows[r // G]) for r in range(R)]
         sum_lp = np.zeros(R, dtype=np.float32)
-        suppress, suppress_first, eot, no_speech, ts = session._sampler
+        suppress, suppress_first, eot, no_speech, ts = session._sampler[:5]
         for _ in range(n_init - 1):  # feed the prompt; the sampler only records no_speech_prob here
             session._greedy_step()
         k = G + 1

@@ -23,6 +23,7 @@ from torch import Tensor, nn
 from . import _engine
 from .decoding import decode as decode_function
 from .decoding import detect_language as detect_language_function
+from .transcribe import transcribe as transcribe_function
 
 
 @dataclass
@@ -213,4 +214,5 @@ class Whisper(nn.Module):
                            "is owned by the CUDA engine's decode session (see whisper.decode)")
 
     detect_language = detect_language_function
+    transcribe = transcribe_function
     decode = decode_function
