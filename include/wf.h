@@ -76,6 +76,15 @@ typedef struct {
    * fp32 partial tiles; NULL disables split-K.  Must not be shared by concurrently running wf_linear calls. */
   void* ws;
   long long ws_bytes;
+  /* fused LayerNorm of the A rows (model.py:30-32 in front of a Linear; WF_BF16, M <= 128 only): when ln_colsum is
+   * non-NULL, A holds the RAW rows x, W holds W * diag(gamma), ln_colsum[n] = sum_k W'[n,k] (fp32) and `bias` holds
+   * bias + W beta; the kernel computes the per-row mean / rstd itself: y = rstd * (x W'^T - mean * ln_colsum) + bias. */
+  const float* ln_colsum;
+  float ln_eps;
+  /* two-destination output (fused q | k,v projection) when split_n > 0: columns [0, split_n) are stored row-major in C
+   * (ldc), columns [split_n, N) in C2 with the head-major / c_off addressing above (N - split_n == 64 * hm_heads). */
+  int split_n;
+  void* C2;
 } wf_epilogue_t;
 /* C = residual + tanh(gate) * act(A[M,K] . W[N,K]^T + bias).  tile_hint: 0 = auto, else N-tile 32/64/128/256. */
 int wf_linear(int dtype, const void* A, long long lda, const void* W, long long ldw, int M, int N, int K,

@@ -226,3 +226,26 @@ def test_temperature_sampling_seeded_best_of_and_beam(a_model, mel2):
     bopt = dict(language="en", without_timestamps=True, sample_len=8, fp16=False, beam_size=2)
     assert (whisper.decode(a_model, mel2[0], whisper.DecodingOptions(temperature=T, **bopt)).tokens
             == whisper.decode(a_model, mel2[0], whisper.DecodingOptions(**bopt)).tokens)
+
+
+def test_split_session_streams_give_identical_tokens(av_model, mel2, monkeypatch):
+    """Greedy decode as concurrent sub-batches on separate CUDA streams (SplitSession) must be bit-identical to
+    the single-session run: clips are independent."""
+    import whisper
+    from whisper import _engine
+    mel = torch.cat([mel2, mel2.flip(0), mel2[:1]])  # 5 clips: ragged split 2 | 3 and 1 | 2 | 2
+    feat = torch.cat([_feat(2), _feat(2).flip(0), _feat(1)]).cuda()
+    opt = whisper.DecodingOptions(language="en", without_timestamps=True, sample_len=12, fp16=False)
+    outs = {}
+    for split in (1, 2, 3):
+        monkeypatch.setenv("WF_DECODE_SPLIT", str(split))
+        _engine.clear_sessions()
+        res = whisper.decode(av_model, mel, opt, x_v=feat)
+        res2 = whisper.decode(av_model, mel, opt, x_v=feat)  # cached session + graph replay
+        assert [r.tokens for r in res] == [r.tokens for r in res2]
+        outs[split] = ([r.tokens for r in res], [r.avg_logprob for r in res], [r.no_speech_prob for r in res])
+    _engine.clear_sessions()
+    assert outs[1][0] == outs[2][0] == outs[3][0]
+    assert outs[1][1] == outs[2][1] == outs[3][1] and outs[1][2] == outs[2][2] == outs[3][2]
+    gold = load_decode_golden()["cases"]["greedy_av"]
+    assert outs[2][0][0] == gold["tokens"][0][:12]

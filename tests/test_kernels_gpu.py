@@ -183,6 +183,83 @@ def test_linear_bf16_split_k_vs_torch(nv, m, n, k):
     assert (out32 - ref).abs().max().item() <= 1e-3 * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("m,n,k,hint", [
+    (128, 1280, 1280, 0), (128, 1280, 1280, 32), (128, 1280, 1280, 64), (128, 1280, 1280, 128), (128, 1280, 1280, 256),
+    (128, 5120, 1280, 0), (128, 1280, 5120, 0), (128, 3840, 1280, 0), (64, 768, 768, 0), (16, 3072, 768, 0),
+    (1, 384, 384, 0), (100, 1536, 384, 0), (37, 1000, 200, 0), (128, 4096, 1024, 0), (128, 1024, 4096, 64),
+])
+def test_linear_bf16_skinny_cluster_split_k_vs_torch(nv, m, n, k, hint):
+    """Decode-step GEMMs (M <= 128): thread-block cluster split-K with the DSMEM reduction, every epilogue option,
+    odd sizes (K and N tails are TMA zero-fill / predicated stores)."""
+    a = _randn(m, k, dtype=torch.bfloat16, seed=1)
+    w = _randn(n, k, dtype=torch.bfloat16, seed=2, scale=0.05)
+    bias, res = _randn(n, seed=3), _randn(m, n, dtype=torch.bfloat16, seed=4)
+    gate = torch.tensor([0.5], device="cuda")
+    want = _ref_linear(a, w, bias=bias, act=1, gate=gate, residual=res)
+    out = torch.full((m, n), float("nan"), dtype=torch.bfloat16, device="cuda")
+    nv.linear(a, w, out, bias=bias, act=nv.ACT_GELU, gate=gate, residual=res, tile_hint=hint)
+    assert (out.float() - want).abs().max().item() <= 3e-2 * max(1.0, want.abs().max().item())
+    out32 = torch.full((m, n), float("nan"), dtype=torch.float32, device="cuda")
+    nv.linear(a, w, out32, tile_hint=hint)
+    ref = _ref_linear(a, w)
+    assert (out32 - ref).abs().max().item() <= 1e-3 * max(1.0, ref.abs().max().item())
+    # in-place residual, repeated launches (no state carried between launches)
+    x = res.clone()
+    for _ in range(2):
+        nv.linear(a, w, x, bias=bias, residual=x, tile_hint=hint)
+    want2 = _ref_linear(a, w, bias=bias, residual=_ref_linear(a, w, bias=bias, residual=res).bfloat16())
+    assert (x.float() - want2).abs().max().item() <= 5e-2 * max(1.0, want2.abs().max().item())
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 1280, 1280), (128, 5120, 1280), (16, 768, 768), (3, 384, 384), (128, 3840, 1280)])
+def test_linear_bf16_fused_layernorm_vs_torch(nv, m, n, k):
+    """LayerNorm (reference model.py:30-32, fp32 statistics) folded into the following Linear: the kernel sees the raw
+    rows, gamma is folded into W, beta into the bias, and mean / rstd come from the staged operand tiles."""
+    x = (_randn(m, k, seed=1) * 1.7 + 0.6).bfloat16()           # non-zero mean: the mean correction must matter
+    gamma, beta = 1.0 + 0.2 * _randn(k, seed=2), 0.3 * _randn(k, seed=3)
+    w32 = _randn(n, k, seed=4, scale=0.05)
+    bias = _randn(n, seed=5)
+    w_fold = (w32 * gamma[None, :]).bfloat16()
+    colsum = w_fold.float().sum(1).contiguous()
+    bias_fold = (bias + w32 @ beta).contiguous()
+    want = F.linear(F.layer_norm(x.float(), (k,), gamma, beta, 1e-5), w32, bias)
+    out = torch.full((m, n), float("nan"), dtype=torch.bfloat16, device="cuda")
+    nv.linear(x, w_fold, out, bias=bias_fold, ln_colsum=colsum, ln_eps=1e-5)
+    scale = max(1.0, want.abs().max().item())
+    assert (out.float() - want).abs().max().item() <= 3e-2 * scale
+    # against the unfused sequence of this library (LayerNorm kernel -> bf16 -> GEMM): same quantity, other rounding
+    xn = torch.empty_like(x)
+    nv.layernorm(x, gamma, beta, xn)
+    out_unfused = torch.empty_like(out)
+    nv.linear(xn, w32.bfloat16(), out_unfused, bias=bias)
+    assert (out.float() - out_unfused.float()).abs().max().item() <= 4e-2 * scale
+    # with GELU + fp32 output
+    out32 = torch.empty((m, n), dtype=torch.float32, device="cuda")
+    nv.linear(x, w_fold, out32, bias=bias_fold, act=nv.ACT_GELU, ln_colsum=colsum, ln_eps=1e-5)
+    assert (out32 - F.gelu(want)).abs().max().item() <= 2e-2 * scale
+
+
+def test_linear_bf16_fused_qkv_two_destinations(nv):
+    """q | k,v projection in one GEMM: q columns row-major, k/v columns appended to the head-major self-attention cache
+    at the device-side position (reference model.py:76-85 computes the three projections separately)."""
+    R, H, k, cap = 7, 6, 384, 20
+    d = H * 64
+    x = _randn(R, k, dtype=torch.bfloat16, seed=1)
+    w = _randn(3 * d, k, dtype=torch.bfloat16, seed=2, scale=0.05)
+    bias = _randn(3 * d, seed=3)
+    q = torch.full((R, d), float("nan"), dtype=torch.bfloat16, device="cuda")
+    cache = torch.zeros((R, 2 * H, cap, 64), dtype=torch.bfloat16, device="cuda")
+    pos = torch.tensor([11], dtype=torch.int32, device="cuda")
+    nv.linear(x, w, q, bias=bias, out2=cache.view(-1, 64), split_n=d, head_major=(2 * H, cap, 1), c_off_ptr=pos,
+              c_off_mul=64)
+    want = _ref_linear(x, w, bias=bias)
+    tol = 3e-2 * max(1.0, want.abs().max().item())
+    assert (q.float() - want[:, :d]).abs().max().item() <= tol
+    assert (cache[:, :, 11].float() - want[:, d:].view(R, 2 * H, 64)).abs().max().item() <= tol
+    cache[:, :, 11] = 0
+    assert cache.abs().max().item() == 0
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_linear_head_major_kv_output(nv, dtype):
     """K/V projection written straight into a head-major cache [B, 2H, T, 64] (+ device-side append offset)."""

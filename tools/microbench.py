@@ -74,6 +74,42 @@ def skinny():
         print(row, flush=True)
 
 
+def skinny2():
+    """Dissect the decode GEMM: time vs M (A traffic), K (main-loop length), weights from L2 (rot=1) vs HBM."""
+    print("decode GEMM dissection, in-graph us per launch: N=1280, bn32")
+    for m in ((128,) if os.environ.get('SK2_FAST') else (16, 64, 128)):
+        for k in (320, 640, 1280, 2560, 5120):
+            row = f"M={m:4d} K={k:5d}: "
+            for n_rot in (1, max(2, int(300e6 // (1280 * k * 2)) + 1)):
+                ws = [torch.randn(1280, k, device="cuda").bfloat16() * 0.02 for _ in range(n_rot)]
+                a = torch.randn(m, k, device="cuda").bfloat16()
+                out = torch.empty(m, 1280, device="cuda", dtype=torch.bfloat16)
+                for hint in (32, 64):
+                    us = graph_timeit(lambda i: nv.linear(a, ws[i], out, tile_hint=hint), n_rot)
+                    row += f" rot{n_rot:3d} bn{hint}: {us:6.2f}us |"
+                del ws
+            print(row, flush=True)
+
+
+def skinny3():
+    """(tile, cluster size) grid for the decode GEMM shapes; cluster size forced through WF_SKINNY_CS."""
+    cs = os.environ.get("WF_SKINNY_CS", "auto")
+    for (n, k) in ((1280, 1280), (5120, 1280), (1280, 5120), (3840, 1280)):
+        n_rot = max(2, int(300e6 // (n * k * 2)) + 1)
+        ws = [torch.randn(n, k, device="cuda").bfloat16() * 0.02 for _ in range(n_rot)]
+        a = torch.randn(128, k, device="cuda").bfloat16()
+        out = torch.empty(128, n, device="cuda", dtype=torch.bfloat16)
+        row = f"cs={cs} N={n:5d} K={k:5d}: "
+        for hint in (32, 64, 128, 256):
+            try:
+                us = graph_timeit(lambda i: nv.linear(a, ws[i], out, tile_hint=hint), n_rot)
+                row += f" bn{hint}: {us:6.2f}us |"
+            except Exception as e:  # noqa: BLE001
+                row += f" bn{hint}:   n/a    |"
+        print(row, flush=True)
+        del ws
+
+
 def gemm():
     print("skinny / decode GEMMs (bf16, M = batch rows): us, GB/s of weight bytes")
     for m in (16, 128):
@@ -156,5 +192,5 @@ def fa():
 
 
 if __name__ == "__main__":
-    for what in sys.argv[1:] or ["gemm", "attn", "ln", "mel", "fa"]:
-        {"gemm": gemm, "attn": attn, "ln": ln, "mel": mel, "fa": fa, "skinny": skinny}[what]()
+    for what in sys.argv[1:] or ["gemm", "attn", "ln", "mel", "fa"]:  # also: skinny, skinny2
+        {"gemm": gemm, "attn": attn, "ln": ln, "mel": mel, "fa": fa, "skinny": skinny, "skinny2": skinny2, "skinny3": skinny3}[what]()

@@ -34,6 +34,17 @@ bool pdl_enabled(int kind) {
   return (mask >> kind) & 1;
 }
 
+int launch_priority(int kind) {
+  static int mode = -1, least = 0, greatest = 0;
+  if (mode < 0) {
+    const char* e = getenv("WF_PRIO");
+    mode = e ? atoi(e) : 0;
+    cudaDeviceGetStreamPriorityRange(&least, &greatest);
+  }
+  if (mode == 0) return INT_MIN;
+  return kind == 2 ? least : greatest;
+}
+
 int num_sms() {
   static int sms = 0;
   if (!sms) {
@@ -51,6 +62,7 @@ static LinearEpilogue to_cpp(const wf_epilogue_t* e) {
   o.res_row_mod = e->res_row_mod; o.gate = e->gate; o.act = e->act; o.out_f32 = e->out_f32;
   o.c_off_ptr = e->c_off_ptr; o.c_off_mul = e->c_off_mul;
   o.hm_heads = e->hm_heads; o.hm_T = e->hm_T; o.hm_rpb = e->hm_rpb; o.ws = e->ws; o.ws_bytes = e->ws_bytes;
+  o.ln_colsum = e->ln_colsum; o.ln_eps = e->ln_eps; o.split_n = e->split_n; o.C2 = e->C2;
   return o;
 }
 
@@ -83,6 +95,8 @@ int wf_linear(int dtype, const void* A, long long lda, const void* W, long long 
   WF_REQUIRE(ep->act == WF_ACT_NONE || ep->act == WF_ACT_GELU, "wf_linear: unknown activation %d", ep->act);
   WF_REQUIRE(!ep->residual || ep->ldr > 0, "wf_linear: residual without a row stride");
   const LinearEpilogue e = to_cpp(ep);
+  WF_REQUIRE(dtype == WF_BF16 || (!e.ln_colsum && e.split_n == 0),
+             "wf_linear: fused LayerNorm / two-destination output exist for WF_BF16 only");
   if (dtype == WF_BF16) return linear_bf16_tc(A, lda, W, ldw, M, N, K, e, tile_hint, S(stream));
   if (dtype == WF_F32) {
     WF_REQUIRE(!ep->out_f32, "wf_linear: out_f32 is only meaningful for WF_BF16");

@@ -1,5 +1,6 @@
 // Shared helpers for libwf (sm_100a only).
 #pragma once
+#include <climits>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <cuda.h>
@@ -50,6 +51,10 @@ int make_map_bf16(CUtensorMap* map, const void* base, long long rows, long long 
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 bool pdl_enabled(int kind);  // kind: 0 gemm, 1 layernorm, 2 attention, 3 misc (WF_PDL_MASK bit)
+// Launch priority of a decode-step kernel (INT_MIN = leave the stream's priority).  With concurrent sub-batches
+// (SplitSession) the latency-bound kernels (GEMM, LayerNorm, sampling) outrank the K/V-streaming attention kernels,
+// so their few CTAs are placed as soon as an SM drains instead of queueing behind thousands of attention CTAs.
+int launch_priority(int kind);
 
 template <typename... KArgs, typename... Args>
 cudaError_t launch_pdl(int kind, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
@@ -59,11 +64,21 @@ cudaError_t launch_pdl(int kind, void (*kernel)(KArgs...), dim3 grid, dim3 block
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (pdl_enabled(kind)) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  const int prio = launch_priority(kind);
+  if (prio != INT_MIN) {
+    attr[n].id = cudaLaunchAttributePriority;
+    attr[n].val.priority = prio;
+    ++n;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled(kind) ? 1 : 0;
+  cfg.numAttrs = n;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

@@ -1,0 +1,130 @@
+// Shared epilogue of the tcgen05 GEMM kernels (gemm_tc.cu: persistent large-M kernel; gemm_skinny.cu: cluster
+// split-K kernel for the decode step): bias / exact-erf GELU / tanh(gate) / residual / K/V-cache addressing / store.
+#pragma once
+#include "common.cuh"
+
+namespace wf {
+
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+struct TcEpilogue {
+  void* C;
+  long long ldc;
+  const float* bias;
+  const void* residual;
+  long long ldr;
+  int res_row_mod;
+  const float* gate;
+  int act;
+  int out_f32;
+  const int* c_off_ptr;
+  long long c_off_mul;
+  // head-major output (K/V caches): element (m, n) -> ((m / hm_rpb) * hm_heads + n / 64) * hm_T + m % hm_rpb) * 64 + n % 64
+  int hm_heads, hm_T, hm_rpb;
+  // split-K: S k-slices per tile; fp32 partials + arrival counters in `ws`, the last-arriving CTA finishes the tile
+  int splits;
+  float* ws_part;
+  int* ws_count;
+  // fused LayerNorm of the A operand (gemm_skinny.cu only): the GEMM runs on the RAW rows x with W' = W * diag(gamma);
+  // the epilogue applies  y = rstd * (acc - mean * ln_colsum[n]) + bias'[n]  with per-row mean / rstd computed inside
+  // the kernel, ln_colsum[n] = sum_k W'[n, k] and bias' = bias + W beta folded into `bias` by the caller.
+  const float* ln_colsum;
+  float ln_eps;
+  // two-destination output (fused q | k,v projection): columns [0, split_n) go row-major to C (ldc, no offset),
+  // columns [split_n, N) to C2 with the head-major / offset addressing above (column index rebased to n - split_n)
+  int split_n;
+  void* C2;
+};
+
+// gemm_skinny.cu
+bool skinny_plan(int M, int N, int K, int tile_hint, int* bn_out, int* cs_out);
+int linear_bf16_skinny(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K,
+                       const TcEpilogue& ep, int bn, int cs, cudaStream_t stream);
+
+// bias / GELU / gate / residual / convert / store for W (8, 16 or 32) consecutive columns of one output row
+template <int W>
+__device__ __forceinline__ void finish_chunk(float (&v)[W], const TcEpilogue& ep, int m, long long res_row, int n0,
+                                             int N, float gate, long long c_off, float ln_mean = 0.f,
+                                             float ln_rstd = 1.f) {
+  const bool full = (n0 + W <= N);
+  if (ep.ln_colsum) {
+#pragma unroll
+    for (int j = 0; j < W; ++j)
+      v[j] = ln_rstd * (v[j] - ln_mean * ((full || n0 + j < N) ? __ldg(ep.ln_colsum + n0 + j) : 0.f));
+  }
+  if (ep.bias) {
+#pragma unroll
+    for (int j = 0; j < W; ++j) v[j] += (full || n0 + j < N) ? __ldg(ep.bias + n0 + j) : 0.f;
+  }
+  if (ep.act == 1) {
+#pragma unroll
+    for (int j = 0; j < W; ++j) v[j] = gelu_erf(v[j]);
+  }
+  if (ep.gate) {
+#pragma unroll
+    for (int j = 0; j < W; ++j) v[j] *= gate;
+  }
+  long long off;
+  void* cbase = ep.C;
+  const bool second = ep.split_n > 0 && n0 >= ep.split_n;
+  if (ep.hm_heads > 0 && (ep.split_n == 0 || second)) {
+    const int nn = n0 - ep.split_n;
+    const int b = m / ep.hm_rpb, t = m - b * ep.hm_rpb;
+    off = (static_cast<long long>(b * ep.hm_heads + (nn >> 6)) * ep.hm_T + t) * 64 + (nn & 63);
+    if (second) cbase = ep.C2;
+  } else {
+    off = static_cast<long long>(m) * ep.ldc + n0;
+    if (ep.split_n > 0) c_off = 0;
+  }
+  if (ep.out_f32) {
+    float* crow = reinterpret_cast<float*>(cbase) + c_off + off;
+    if (ep.residual) {
+      const float* rrow = reinterpret_cast<const float*>(ep.residual) + res_row * ep.ldr + n0;
+#pragma unroll
+      for (int j = 0; j < W; ++j) if (full || n0 + j < N) v[j] += rrow[j];
+    }
+    if (full && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
+#pragma unroll
+      for (int j = 0; j < W; j += 4)
+        *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < W; ++j) if (n0 + j < N) crow[j] = v[j];
+    }
+  } else {
+    __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(cbase) + c_off + off;
+    if (ep.residual) {
+      const __nv_bfloat16* rrow = reinterpret_cast<const __nv_bfloat16*>(ep.residual) + res_row * ep.ldr + n0;
+      if (full && ((reinterpret_cast<uintptr_t>(rrow) & 15) == 0)) {
+#pragma unroll
+        for (int j = 0; j < W; j += 8) {
+          const uint4 u = *reinterpret_cast<const uint4*>(rrow + j);
+          v[j + 0] += bf16lo(u.x); v[j + 1] += bf16hi(u.x);
+          v[j + 2] += bf16lo(u.y); v[j + 3] += bf16hi(u.y);
+          v[j + 4] += bf16lo(u.z); v[j + 5] += bf16hi(u.z);
+          v[j + 6] += bf16lo(u.w); v[j + 7] += bf16hi(u.w);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < W; ++j) if (n0 + j < N) v[j] += __bfloat162float(rrow[j]);
+      }
+    }
+    if (full && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
+#pragma unroll
+      for (int j = 0; j < W; j += 8) {
+        uint4 u;
+        u.x = pack_bf16(v[j + 0], v[j + 1]);
+        u.y = pack_bf16(v[j + 2], v[j + 3]);
+        u.z = pack_bf16(v[j + 4], v[j + 5]);
+        u.w = pack_bf16(v[j + 6], v[j + 7]);
+        *reinterpret_cast<uint4*>(crow + j) = u;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < W; ++j) if (n0 + j < N) crow[j] = __float2bfloat16_rn(v[j]);
+    }
+  }
+}
+
+
+}  // namespace wf

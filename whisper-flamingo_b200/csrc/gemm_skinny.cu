@@ -1,0 +1,424 @@
+// Decode-step linear layers (M <= 128 rows = one batch of hypotheses):  C[M,N] = epilogue(LN?(A)[M,K] . W[N,K]^T)
+//
+// Replaces reference whisper/model.py:35-41 (Linear.forward) and, when asked, the LayerNorm in front of it
+// (model.py:30-32) for the one-token decoder pass (decoding.py:155-164).  These GEMMs move 3-13 MB of weights and
+// should take a microsecond; the persistent large-tile kernel (gemm_tc.cu) needed 8-26 us for them because ONE
+// CTA walked the whole K extent of its N tile serially.  Measured on B200 (tools/microbench.py skinny2):
+//     t = 1.9 us + 0.30 us per 64-wide k-block, whatever M, the N tile or where the weights come from,
+// of which 0.155 us is the L2->SM operand stream (20 KB per k-block at ~64 B/clk) and the rest the single MMA-issuing
+// thread (~350 cycles per barrier round + ~62 cycles per 128 x 32 x 16 MMA, operand-read bound).
+//
+// So this kernel splits K as well as N: a thread-block CLUSTER of CS CTAs owns one 128 x BN output tile, each CTA
+// accumulates a K slice in TMEM with two swizzle atoms (K = 128) per pipeline round, and the partial tiles are reduced
+// through distributed shared memory: every CTA dumps its accumulator to its own smem, cluster barrier, then CTA r
+// sums column slice r of all CS partials (ld.shared::cluster) and runs the fused epilogue for it.  No global
+// workspace, no atomics, no second kernel.
+//
+// Optional fused LayerNorm: the epilogue warps, idle during the main loop, accumulate sum / sum-of-squares of the raw
+// A rows straight from the TMA-staged smem tiles (a 128-byte swizzle permutes 16-byte chunks inside a row, which a
+// row sum does not care about); the row statistics travel with the partial tiles through DSMEM and the epilogue
+// applies  y = rstd * (acc - mean * colsum(W')) + bias'.
+#include "common.cuh"
+#include "kernels.h"
+#include "gemm_epilogue.cuh"
+
+namespace wf {
+
+static constexpr int SK_BM = 128;
+static constexpr int SK_BK = 64;       // one 128-byte swizzle atom of bf16
+static constexpr int SK_KA = 2;        // atoms per pipeline round
+static constexpr int SK_THREADS = 384; // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4..11 epilogue / LN stats
+static constexpr int SK_UMMA_K = 16;
+
+template <int BN, int STAGES>
+struct SkCfg {
+  static constexpr int A_ATOM = SK_BM * SK_BK * 2;  // 16 KB
+  static constexpr int B_ATOM = BN * SK_BK * 2;
+  static constexpr int STAGE_BYTES = SK_KA * (A_ATOM + B_ATOM);
+  static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
+  static constexpr int DUMP_LD = BN + 4;  // +16 B per row: 16-byte accesses of a quarter-warp hit distinct banks
+  static constexpr int DUMP_BYTES = SK_BM * DUMP_LD * 4;
+  static constexpr int STAT_BYTES = 2 * SK_BM * 2 * 4;  // [atom group][row]{sum, sumsq}
+  static constexpr int BAR_BYTES = (2 * STAGES + 1) * 8 + 16;
+  static constexpr int SMEM_BYTES = PIPE_BYTES + STAT_BYTES + BAR_BYTES + 1024;
+  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  static_assert(PIPE_BYTES >= DUMP_BYTES, "the accumulator dump aliases the pipeline stages");
+  static_assert(B_ATOM % 1024 == 0, "operand atoms must keep 1024-byte alignment");
+  static_assert(SMEM_BYTES <= 227 * 1024, "over the shared-memory budget");
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t dsmem_addr(uint32_t local_smem_addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(addr)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ float2 ld_dsmem_f2(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
+  return v;
+}
+
+// columns [col0 + c * CW, +CW) of this thread's row: sum over the CS partial tiles of the cluster, then the epilogue
+template <int CW>
+__device__ __forceinline__ void reduce_finish(uint32_t dump_local, int dump_ld, int cs, int rloc, int col_in_tile,
+                                              const TcEpilogue& ep, int m, long long res_row, int n0, int N, float gate,
+                                              long long c_off, float mean, float rstd) {
+  float v[CW];
+#pragma unroll
+  for (int j = 0; j < CW; ++j) v[j] = 0.f;
+  const uint32_t off = static_cast<uint32_t>((rloc * dump_ld + col_in_tile) * 4);
+  for (int s = 0; s < cs; ++s) {
+    const uint32_t base = dsmem_addr(dump_local + off, static_cast<uint32_t>(s));
+#pragma unroll
+    for (int j = 0; j < CW; j += 4) {
+      const float4 t = ld_dsmem_f4(base + j * 4);
+      v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+    }
+  }
+  finish_chunk<CW>(v, ep, m, res_row, n0, N, gate, c_off, mean, rstd);
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(SK_THREADS, 1)
+gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                   int M, int N, int K, TcEpilogue ep, int CS) {
+  using Cfg = SkCfg<BN, STAGES>;
+  extern __shared__ uint8_t sk_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sk_smem_raw) + 1023) & ~uintptr_t(1023));
+  float* dump = reinterpret_cast<float*>(smem);                                   // aliases the pipeline stages
+  float* stat = reinterpret_cast<float*>(smem + Cfg::PIPE_BYTES);                 // [2][128][2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::PIPE_BYTES + Cfg::STAT_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tfull_bar = bars + 2 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  pdl_trigger();
+
+  const int rank = static_cast<int>(cluster_ctarank());
+  const int n_blk = blockIdx.x / CS;
+  const int rounds_total = (K + SK_KA * SK_BK - 1) / (SK_KA * SK_BK);
+  const int per = (rounds_total + CS - 1) / CS;
+  const int r0 = min(rounds_total, rank * per), r1 = min(rounds_total, r0 + per);
+  const int nr = r1 - r0;  // pipeline rounds of this CTA (0 is legal: it contributes a zero partial)
+  const bool ln = ep.ln_colsum != nullptr;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], ln ? 9 : 1);  // MMA commit (+ one arrival per LN-statistics warp)
+    }
+    mbar_init(tfull_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto a_atom = [&](int stage, int a) { return smem + stage * Cfg::STAGE_BYTES + a * Cfg::A_ATOM; };
+  auto b_atom = [&](int stage, int a) { return smem + stage * Cfg::STAGE_BYTES + SK_KA * Cfg::A_ATOM + a * Cfg::B_ATOM; };
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------ TMA producer: weights first (they do not depend on
+    // the previous kernel), activations after the programmatic-dependency wait
+    const int npre = min(STAGES, nr);
+    for (int i = 0; i < npre; ++i) {
+      mbar_arrive_expect_tx(&full_bar[i], Cfg::STAGE_BYTES);
+#pragma unroll
+      for (int a = 0; a < SK_KA; ++a)
+        tma_load_2d(b_atom(i, a), &map_b, &full_bar[i], ((r0 + i) * SK_KA + a) * SK_BK, n_blk * BN);
+    }
+    pdl_wait();
+    for (int i = 0; i < npre; ++i) {
+#pragma unroll
+      for (int a = 0; a < SK_KA; ++a)
+        tma_load_2d(a_atom(i, a), &map_a, &full_bar[i], ((r0 + i) * SK_KA + a) * SK_BK, 0);
+    }
+    int stage = npre == STAGES ? 0 : npre;
+    uint32_t phase = npre == STAGES ? 1 : 0;
+    for (int r = npre; r < nr; ++r) {
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+#pragma unroll
+      for (int a = 0; a < SK_KA; ++a) {
+        tma_load_2d(a_atom(stage, a), &map_a, &full_bar[stage], ((r0 + r) * SK_KA + a) * SK_BK, 0);
+        tma_load_2d(b_atom(stage, a), &map_b, &full_bar[stage], ((r0 + r) * SK_KA + a) * SK_BK, n_blk * BN);
+      }
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = umma_idesc_bf16(SK_BM, BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int r = 0; r < nr; ++r) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+#pragma unroll
+      for (int a = 0; a < SK_KA; ++a) {
+        const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(a_atom(stage, a)));
+        const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(b_atom(stage, a)));
+#pragma unroll
+        for (int k = 0; k < SK_BK / SK_UMMA_K; ++k)
+          umma_f16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (r > 0 || a > 0 || k > 0) ? 1u : 0u);
+      }
+      umma_commit(&empty_bar[stage]);
+      if (r == nr - 1) umma_commit(tfull_bar);
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue warps, phase A
+    const int q = warp & 3;            // TMEM lane quarter
+    const int grp = (warp - 4) >> 2;   // 0 / 1: column half in the epilogue, swizzle atom in the LN statistics
+    const int rloc = q * 32 + lane;
+    if (ln) {
+      // row sums of the raw A operand from the staged tiles (row = 128 B = 8 chunks of 16 B, order irrelevant)
+      float s1 = 0.f, s2 = 0.f;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int r = 0; r < nr; ++r) {
+        mbar_wait(&full_bar[stage], phase);
+        const uint8_t* row = a_atom(stage, grp) + rloc * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint4 u = *reinterpret_cast<const uint4*>(row + ((j + rloc) & 7) * 16);
+          const float f[8] = {bf16lo(u.x), bf16hi(u.x), bf16lo(u.y), bf16hi(u.y),
+                              bf16lo(u.z), bf16hi(u.z), bf16lo(u.w), bf16hi(u.w)};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            s1 += f[e];
+            s2 = fmaf(f[e], f[e], s2);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      *reinterpret_cast<float2*>(stat + (grp * SK_BM + rloc) * 2) = make_float2(s1, s2);
+    }
+    if (nr > 0) {
+      mbar_wait(tfull_bar, 0);
+      tc_fence_after();
+    }
+    if (CS > 1) {
+      // all TMA loads of this CTA have been consumed and all its MMAs have retired: the stages are free to hold the dump
+      const uint32_t tsrc = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+      for (int c = grp; c < BN / 32; c += 2) {
+        uint32_t r[32];
+        if (nr > 0) {
+          tmem_ld_32x32(tsrc + c * 32, r);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = 0u;
+        }
+        float* drow = dump + rloc * Cfg::DUMP_LD + c * 32;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<uint4*>(drow + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+      }
+    }
+  }
+
+  // ---------------------------------------------------------------- partial tiles (and row statistics) are published
+  __syncwarp();
+  if (CS > 1) cluster_sync_all();
+  else if (ln) __syncthreads();
+
+  if (warp >= 4) {
+    const int q = warp & 3;
+    const int grp = (warp - 4) >> 2;
+    const int rloc = q * 32 + lane;
+    const int m = rloc;
+    const bool row_ok = m < M;
+    pdl_wait();  // residual / gate / offset may be produced by the previous kernel
+    long long c_off = 0;
+    if (ep.c_off_ptr) c_off = static_cast<long long>(*ep.c_off_ptr) * ep.c_off_mul;
+    const float gate = ep.gate ? tanhf(*ep.gate) : 1.0f;
+    const long long res_row = ep.res_row_mod > 0 ? (m % ep.res_row_mod) : m;
+    float mean = 0.f, rstd = 1.f;
+    if (ln) {
+      float s1 = 0.f, s2 = 0.f;
+      const uint32_t st_local = smem_u32(stat);
+      for (int s = 0; s < CS; ++s) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          const float2 t = ld_dsmem_f2(dsmem_addr(st_local + static_cast<uint32_t>((g * SK_BM + rloc) * 8), s));
+          s1 += t.x;
+          s2 += t.y;
+        }
+      }
+      mean = s1 / static_cast<float>(K);
+      const float var = fmaxf(s2 / static_cast<float>(K) - mean * mean, 0.f);
+      rstd = rsqrtf(var + ep.ln_eps);
+    }
+    if (CS == 1) {
+      const uint32_t tsrc = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+      for (int c = grp; c < BN / 32; c += 2) {
+        uint32_t r[32];
+        tmem_ld_32x32(tsrc + c * 32, r);
+        tmem_ld_wait();
+        const int n0 = n_blk * BN + c * 32;
+        if (row_ok && n0 < N) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          finish_chunk<32>(v, ep, m, res_row, n0, N, gate, c_off, mean, rstd);
+        }
+      }
+    } else {
+      const int wc = BN / CS;  // columns of the tile finished by this CTA
+      const int cw = wc < 32 ? wc : 32;
+      const uint32_t dump_local = smem_u32(dump);
+      if (row_ok) {
+        for (int c = grp; c * cw < wc; c += 2) {
+          const int col = rank * wc + c * cw;
+          const int n0 = n_blk * BN + col;
+          if (n0 >= N) continue;
+          if (cw == 32)
+            reduce_finish<32>(dump_local, Cfg::DUMP_LD, CS, rloc, col, ep, m, res_row, n0, N, gate, c_off, mean, rstd);
+          else if (cw == 16)
+            reduce_finish<16>(dump_local, Cfg::DUMP_LD, CS, rloc, col, ep, m, res_row, n0, N, gate, c_off, mean, rstd);
+          else
+            reduce_finish<8>(dump_local, Cfg::DUMP_LD, CS, rloc, col, ep, m, res_row, n0, N, gate, c_off, mean, rstd);
+        }
+      }
+    }
+  }
+
+  // nobody may leave (and release its shared memory) while a peer can still read it
+  __syncwarp();
+  if (CS > 1) cluster_sync_all();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+template <int BN, int STAGES>
+static int launch_skinny(const CUtensorMap& ma, const CUtensorMap& mb, int M, int N, int K, const TcEpilogue& ep, int cs,
+                         cudaStream_t stream) {
+  using Cfg = SkCfg<BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    WF_CHECK_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  const int tiles = (N + BN - 1) / BN;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(tiles * cs);
+  cfg.blockDim = dim3(SK_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[3];
+  int n = 0;
+  attr[n].id = cudaLaunchAttributeClusterDimension;
+  attr[n].val.clusterDim.x = cs;
+  attr[n].val.clusterDim.y = 1;
+  attr[n].val.clusterDim.z = 1;
+  ++n;
+  if (pdl_enabled(0)) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  const int prio = launch_priority(0);
+  if (prio != INT_MIN) {
+    attr[n].id = cudaLaunchAttributePriority;
+    attr[n].val.priority = prio;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  WF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_skinny_kernel<BN, STAGES>, ma, mb, M, N, K, ep, cs));
+  count_launch();
+  return WF_OK;
+}
+
+// Tile width and cluster size for an [M <= 128] x N x K problem.  Measured on B200 inside a CUDA graph with PDL
+// (tools/microbench.py skinny3, M = 128): t ~= 2.3 us + 0.22 us per 64-wide k-atom walked by one CTA, + ~2.5 us for a
+// 2-CTA cluster and ~5.5 us for a 4-CTA one (cluster scheduling + two cluster barriers + the DSMEM reduction).  So K
+// is split only when a CTA would otherwise walk >= 64 atoms (K >= 4096: 20.0 -> 12.6 us at K = 5120), and the N tile
+// is the narrowest that still fits the grid on the machine in one wave.
+bool skinny_plan(int M, int N, int K, int tile_hint, int* bn_out, int* cs_out) {
+  if (M > SK_BM) return false;
+  static int mode = -1, force_cs = -1;
+  if (mode < 0) {
+    const char* e = getenv("WF_SKINNY");  // 0: use the persistent kernel of gemm_tc.cu instead (A/B measurements)
+    mode = e ? atoi(e) : 1;
+    const char* c = getenv("WF_SKINNY_CS");
+    force_cs = c ? atoi(c) : 0;
+  }
+  if (mode == 0) return false;
+  const int sms = num_sms();
+  const int rounds = (K + SK_KA * SK_BK - 1) / (SK_KA * SK_BK);
+  int cs = 1;
+  if (rounds >= 32) cs = 4;
+  if (force_cs) cs = force_cs;
+  while (cs > 1 && cs > rounds) cs >>= 1;
+  for (;; cs >>= 1) {
+    const int bns[4] = {32, 64, 128, 256};
+    for (int i = 0; i < 4; ++i) {
+      const int bn = bns[i];
+      if (tile_hint && bn != tile_hint) continue;
+      if (bn / cs < 8) continue;
+      if (cs > 1 && bn < 64 && !tile_hint) continue;  // 4 x 8-column slices finish slower than 4 x 16
+      const int tiles = (N + bn - 1) / bn;
+      if (tiles * cs > sms) continue;
+      *bn_out = bn;
+      *cs_out = cs;
+      return true;
+    }
+    if (cs == 1) return false;
+  }
+}
+
+int linear_bf16_skinny(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K,
+                       const TcEpilogue& ep, int bn, int cs, cudaStream_t stream) {
+  CUtensorMap ma, mb;
+  int rc = make_map_bf16(&ma, A, M, K, lda, SK_BM);
+  if (rc) return rc;
+  rc = make_map_bf16(&mb, W, N, K, ldw, bn);
+  if (rc) return rc;
+  switch (bn) {
+    case 32: return launch_skinny<32, 4>(ma, mb, M, N, K, ep, cs, stream);
+    case 64: return launch_skinny<64, 4>(ma, mb, M, N, K, ep, cs, stream);
+    case 128: return launch_skinny<128, 3>(ma, mb, M, N, K, ep, cs, stream);
+    case 256: return launch_skinny<256, 2>(ma, mb, M, N, K, ep, cs, stream);
+    default:
+      set_error("linear (skinny): unsupported tile %d", bn);
+      return WF_ERR_UNSUPPORTED;
+  }
+}
+
+}  // namespace wf

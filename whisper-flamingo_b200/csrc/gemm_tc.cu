@@ -15,6 +15,7 @@
 // weight matrix (<= 13 MB) stays L2-resident: A is streamed from HBM once per GEMM.
 #include "common.cuh"
 #include "kernels.h"
+#include "gemm_epilogue.cuh"
 
 namespace wf {
 
@@ -39,101 +40,6 @@ struct TcCfg {
 static constexpr int TC_THREADS = 384;      // 4 control warps + 8 epilogue warps
 static constexpr int EPI_THREADS = 256;
 static constexpr int SPLITK_COUNTER_BYTES = 4096;  // 1024 per-tile arrival counters at the head of the workspace
-
-struct TcEpilogue {
-  void* C;
-  long long ldc;
-  const float* bias;
-  const void* residual;
-  long long ldr;
-  int res_row_mod;
-  const float* gate;
-  int act;
-  int out_f32;
-  const int* c_off_ptr;
-  long long c_off_mul;
-  // head-major output (K/V caches): element (m, n) -> ((m / hm_rpb) * hm_heads + n / 64) * hm_T + m % hm_rpb) * 64 + n % 64
-  int hm_heads, hm_T, hm_rpb;
-  // split-K: S k-slices per tile; fp32 partials + arrival counters in `ws`, the last-arriving CTA finishes the tile
-  int splits;
-  float* ws_part;
-  int* ws_count;
-};
-
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-
-// bias / GELU / gate / residual / convert / store for 32 consecutive columns of one output row
-__device__ __forceinline__ void finish_chunk(float (&v)[32], const TcEpilogue& ep, int m, long long res_row, int n0,
-                                             int N, float gate, long long c_off) {
-  const bool full = (n0 + 32 <= N);
-  if (ep.bias) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] += (full || n0 + j < N) ? __ldg(ep.bias + n0 + j) : 0.f;
-  }
-  if (ep.act == 1) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-  }
-  if (ep.gate) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] *= gate;
-  }
-  long long off;
-  if (ep.hm_heads > 0) {
-    const int b = m / ep.hm_rpb, t = m - b * ep.hm_rpb;
-    off = (static_cast<long long>(b * ep.hm_heads + (n0 >> 6)) * ep.hm_T + t) * 64 + (n0 & 63);
-  } else {
-    off = static_cast<long long>(m) * ep.ldc + n0;
-  }
-  if (ep.out_f32) {
-    float* crow = reinterpret_cast<float*>(ep.C) + c_off + off;
-    if (ep.residual) {
-      const float* rrow = reinterpret_cast<const float*>(ep.residual) + res_row * ep.ldr + n0;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) if (full || n0 + j < N) v[j] += rrow[j];
-    }
-    if (full && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) if (n0 + j < N) crow[j] = v[j];
-    }
-  } else {
-    __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(ep.C) + c_off + off;
-    if (ep.residual) {
-      const __nv_bfloat16* rrow = reinterpret_cast<const __nv_bfloat16*>(ep.residual) + res_row * ep.ldr + n0;
-      if (full && ((reinterpret_cast<uintptr_t>(rrow) & 15) == 0)) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          const uint4 u = *reinterpret_cast<const uint4*>(rrow + j);
-          v[j + 0] += bf16lo(u.x); v[j + 1] += bf16hi(u.x);
-          v[j + 2] += bf16lo(u.y); v[j + 3] += bf16hi(u.y);
-          v[j + 4] += bf16lo(u.z); v[j + 5] += bf16hi(u.z);
-          v[j + 6] += bf16lo(u.w); v[j + 7] += bf16hi(u.w);
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) if (n0 + j < N) v[j] += __bfloat162float(rrow[j]);
-      }
-    }
-    if (full && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        uint4 u;
-        u.x = pack_bf16(v[j + 0], v[j + 1]);
-        u.y = pack_bf16(v[j + 2], v[j + 3]);
-        u.z = pack_bf16(v[j + 4], v[j + 5]);
-        u.w = pack_bf16(v[j + 6], v[j + 7]);
-        *reinterpret_cast<uint4*>(crow + j) = u;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) if (n0 + j < N) crow[j] = __float2bfloat16_rn(v[j]);
-    }
-  }
-}
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -280,7 +186,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-            finish_chunk(v, ep, m, res_row, n0, N, gate, c_off);
+            finish_chunk<32>(v, ep, m, res_row, n0, N, gate, c_off);
           }
         }
         tc_fence_before();
@@ -326,7 +232,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                   v[j] += t4.x; v[j + 1] += t4.y; v[j + 2] += t4.z; v[j + 3] += t4.w;
                 }
               }
-              finish_chunk(v, ep, m, res_row, n0, N, gate, c_off);
+              finish_chunk<32>(v, ep, m, res_row, n0, N, gate, c_off);
             }
           }
           if (threadIdx.x == 4 * 32) ep.ws_count[tile] = 0;  // self-resetting: ready for the next launch
@@ -435,23 +341,32 @@ int linear_bf16_tc(const void* A, long long lda, const void* W, long long ldw, i
     }
   }
   WF_REQUIRE(bn == 32 || bn == 64 || bn == 128 || bn == 256, "linear: unsupported tile hint %d", tile_hint);
+  WF_REQUIRE(e.split_n >= 0 && e.split_n % 64 == 0 && e.split_n < N && (e.split_n == 0 || (e.C2 && e.hm_heads > 0)),
+             "linear: bad two-destination spec (split_n=%d N=%d)", e.split_n, N);
   if (e.hm_heads > 0) {
-    WF_REQUIRE(N % 64 == 0 && e.hm_heads * 64 == N && e.hm_T > 0 && e.hm_rpb > 0 && !e.residual,
-               "linear: bad head-major output spec (N=%d heads=%d T=%d rpb=%d)", N, e.hm_heads, e.hm_T, e.hm_rpb);
+    const int n_hm = N - e.split_n;
+    WF_REQUIRE(n_hm % 64 == 0 && e.hm_heads * 64 == n_hm && e.hm_T > 0 && e.hm_rpb > 0 && !e.residual,
+               "linear: bad head-major output spec (N=%d heads=%d T=%d rpb=%d)", n_hm, e.hm_heads, e.hm_T, e.hm_rpb);
   }
   WF_REQUIRE(!e.ws || ((reinterpret_cast<uintptr_t>(e.ws) & 15) == 0 && e.ws_bytes >= SPLITK_COUNTER_BYTES),
              "linear: split-K workspace must be 16-byte aligned and hold at least %d bytes", SPLITK_COUNTER_BYTES);
-  CUtensorMap ma, mb;
-  int rc = make_map_bf16(&ma, A, M, K, lda, BM);
-  if (rc) return rc;
-  rc = make_map_bf16(&mb, W, N, K, ldw, bn);
-  if (rc) return rc;
   TcEpilogue ep;
   ep.C = e.C; ep.ldc = e.ldc; ep.bias = e.bias; ep.residual = e.residual; ep.ldr = e.ldr;
   ep.res_row_mod = e.res_row_mod; ep.gate = e.gate; ep.act = e.act; ep.out_f32 = e.out_f32;
   ep.c_off_ptr = e.c_off_ptr; ep.c_off_mul = e.c_off_mul;
   ep.hm_heads = e.hm_heads; ep.hm_T = e.hm_T; ep.hm_rpb = e.hm_rpb;
   ep.splits = 1; ep.ws_part = nullptr; ep.ws_count = nullptr;
+  ep.ln_colsum = e.ln_colsum; ep.ln_eps = e.ln_eps; ep.split_n = e.split_n; ep.C2 = e.C2;
+  {
+    int sbn = 0, scs = 1;  // decode step (one M tile): cluster split-K kernel
+    if (skinny_plan(M, N, K, tile_hint, &sbn, &scs)) return linear_bf16_skinny(A, lda, W, ldw, M, N, K, ep, sbn, scs, stream);
+  }
+  WF_REQUIRE(!e.ln_colsum, "linear: the fused LayerNorm needs M <= 128 and N small enough for one wave (M=%d N=%d)", M, N);
+  CUtensorMap ma, mb;
+  int rc = make_map_bf16(&ma, A, M, K, lda, BM);
+  if (rc) return rc;
+  rc = make_map_bf16(&mb, W, N, K, ldw, bn);
+  if (rc) return rc;
   switch (bn) {
     case 32: return launch_tc<32, 8>(ma, mb, M, N, K, ep, e.ws, e.ws_bytes, stream);
     case 64: return launch_tc<64, 8>(ma, mb, M, N, K, ep, e.ws, e.ws_bytes, stream);

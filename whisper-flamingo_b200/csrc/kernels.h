@@ -23,6 +23,12 @@ struct LinearEpilogue {
   // optional split-K workspace (bf16 engine, M <= 256): first 4096 bytes = zero-initialised arrival counters
   void* ws = nullptr;
   long long ws_bytes = 0;
+  // fused LayerNorm of A (bf16 engine, M <= 128): see TcEpilogue in gemm_epilogue.cuh
+  const float* ln_colsum = nullptr;
+  float ln_eps = 0.f;
+  // two-destination output: columns [0, split_n) -> C row-major, [split_n, N) -> C2 (head-major / offset addressing)
+  int split_n = 0;
+  void* C2 = nullptr;
 };
 
 // gemm_tc.cu / gemm_f32.cu

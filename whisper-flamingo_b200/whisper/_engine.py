@@ -230,6 +230,56 @@ def _build_decoder_pack(dec, dt) -> _DecoderPack:
                         tok.shape[0])
 
 
+@dataclass
+class _LnLinear:
+    """LayerNorm folded into the Linear that consumes it (decode step, bf16, <= 128 rows): the GEMM kernel reads the raw
+    rows and computes mean / rstd itself; y = rstd * (x W'^T - mean * colsum) + bias'  with  W' = W diag(gamma)."""
+    w: Tensor        # [N, K] bf16 = bf16(W * gamma)
+    colsum: Tensor   # [N] fp32 = sum_k w[n, k] (of the ROUNDED weights the kernel multiplies)
+    bias: Tensor     # [N] fp32 = b + W beta
+    eps: float = 1e-5
+
+
+def _fold_ln(ln: _LnPack, w_master: Tensor, b: Optional[Tensor], dt) -> _LnLinear:
+    w32 = w_master.detach().float()
+    wf = _to_dtype((w32 * ln.w[None, :]).contiguous(), dt).contiguous()
+    bias = w32 @ ln.b
+    if b is not None:
+        bias = bias + b
+    return _LnLinear(wf, wf.float().sum(dim=1).contiguous(), bias.contiguous())
+
+
+@dataclass
+class _BlockFold:
+    x_q: List[_LnLinear]
+    ff1: Optional[_LnLinear]
+    self_qkv: _LnLinear
+    cross_q: Optional[_LnLinear]
+    mlp1: _LnLinear
+
+
+def _fold_block(blk, bp: _BlockPack, dt) -> _BlockFold:
+    d = bp.attn.d
+    qkv_master = torch.cat([blk.attn.query.weight.detach(), blk.attn.key.weight.detach(),
+                            blk.attn.value.weight.detach()], dim=0)
+    x_q = [_fold_ln(bp.x_ln[i], sub.attn.query.weight, bp.x_attn[i].qkv_b[:d], dt)
+           for i, sub in enumerate(blk.gated_x_attn_layers)] if blk.add_gated_x_attn != 0 else []
+    ff1 = _fold_ln(bp.ff_ln, blk.ff[0].weight, bp.ff.b1, dt) if bp.ff is not None else None
+    cross_q = (_fold_ln(bp.cross_ln, blk.cross_attn.query.weight, bp.cross.qkv_b[:d], dt)
+               if bp.cross is not None else None)
+    return _BlockFold(x_q, ff1, _fold_ln(bp.attn_ln, qkv_master, bp.attn.qkv_b, dt), cross_q,
+                      _fold_ln(bp.mlp_ln, blk.mlp[0].weight, bp.mlp.b1, dt))
+
+
+def decoder_fold(dec, p: _DecoderPack, dt) -> List[_BlockFold]:
+    """Folded LayerNorm + Linear weights of every decoder block, cached on the pack (rebuilt with it)."""
+    fold = p.__dict__.get("_fold")
+    if fold is None:
+        fold = [_fold_block(blk, bp, dt) for blk, bp in zip(dec.blocks, p.blocks)]
+        p.__dict__["_fold"] = fold
+    return fold
+
+
 def encoder_pack(enc, dt) -> _EncoderPack:
     return _cached_pack(enc, dt, _build_encoder_pack)
 
@@ -412,6 +462,9 @@ class DecodeSession:
         self.T_cap = t_cap
         d, H = p.d, p.n_head
         self.gated = len(p.blocks) > 0 and len(p.blocks[0].x_attn) > 0
+        # bf16 and one 128-row tile: LayerNorms run inside the GEMMs and q | k,v is a single projection
+        self.fold = (decoder_fold(dec, p, dt) if (dt == torch.bfloat16 and R <= 128 and
+                                                  os.environ.get("WF_NO_LN_FUSION", "0") != "1") else None)
         feats = self._check_feats(feats)
         self.Ta = Ta = xa.shape[1]
         self.Tx = [f.shape[1] for f in feats]
@@ -469,6 +522,8 @@ class DecodeSession:
 
     # -- one decoder pass for the token at position state[0]; logits of that position land in self.logits
     def _forward_token(self):
+        if self.fold is not None:
+            return self._forward_token_fused()
         p, d, H, G = self.p, self.p.d, self.p.n_head, self.G
         st = self.state
         gws = self.gemm_ws if self.dt == torch.bfloat16 else None
@@ -512,6 +567,50 @@ class DecodeSession:
         nv.layernorm(x, p.ln.w, p.ln.b, xn)
         nv.linear(xn, p.tok_emb_t, self.logits, n=p.n_vocab, ws=gws)
 
+    def _forward_token_fused(self):
+        """Same pass with every block LayerNorm folded into the GEMM behind it and q | k,v as one projection:
+        11 launches per block instead of 19 (reference model.py:171-215 per block)."""
+        p, H, G = self.p, self.p.n_head, self.G
+        st = self.state
+        nv.embed(self.tokens, self.tokens.shape[1], st, 0, p.tok_emb, p.pos_emb, self.x)
+        x, q, att, h = self.x, self.q, self.att, self.h
+
+        def lnlin(f: _LnLinear, out, **kw):
+            nv.linear(x, f.w, out, bias=f.bias, ln_colsum=f.colsum, ln_eps=f.eps, **kw)
+
+        for l, (bp, bf) in enumerate(zip(p.blocks, self.fold)):
+            if self.gated:
+                multi = len(self.x_kv[l]) > 1
+                acc = x
+                if multi:
+                    self.acc.copy_(x)
+                    acc = self.acc
+                for i, kvx in enumerate(self.x_kv[l]):
+                    Tx = self.Tx[i]
+                    lnlin(bf.x_q[i], q)
+                    nv.attention_decode(q, kvx, kvx[:, H:], 64, 2 * H * Tx * 64, Tx * 64, att, G, H, None, 0, Tx,
+                                        self.ws)
+                    nv.linear(att, bp.x_attn[i].o_w, acc, bias=bp.x_attn[i].o_b, residual=acc, gate=bp.x_gate[i])
+                if multi:
+                    x.copy_(acc)
+                lnlin(bf.ff1, h, act=nv.ACT_GELU)
+                nv.linear(h, bp.ff.w2, x, bias=bp.ff.b2, residual=x, gate=bp.ff_gate)
+            Tc = self.T_cap
+            kv = self.self_kv[l]
+            lnlin(bf.self_qkv, q, out2=kv.view(-1, 64), split_n=p.d, head_major=(2 * H, Tc, 1), c_off_ptr=st,
+                  c_off_mul=64)
+            nv.attention_decode(q, kv, kv[:, H:], 64, 2 * H * Tc * 64, Tc * 64, att, 1, H, st, 1, Tc, self.ws)
+            nv.linear(att, bp.attn.o_w, x, bias=bp.attn.o_b, residual=x)
+            lnlin(bf.cross_q, q)
+            ckv = self.cross_kv[l]
+            nv.attention_decode(q, ckv, ckv[:, H:], 64, 2 * H * self.Ta * 64, self.Ta * 64, att, G, H, None, 0,
+                                self.Ta, self.ws)
+            nv.linear(att, bp.cross.o_w, x, bias=bp.cross.o_b, residual=x)
+            lnlin(bf.mlp1, h, act=nv.ACT_GELU)
+            nv.linear(h, bp.mlp.w2, x, bias=bp.mlp.b2, residual=x)
+        nv.layernorm(x, p.ln.w, p.ln.b, self.xn)
+        nv.linear(self.xn, p.tok_emb_t, self.logits, n=p.n_vocab, ws=self.gemm_ws)
+
     # -- greedy ---------------------------------------------------------------------------------------
     def configure_greedy(self, initial_tokens: Sequence[int], sot_index: int, suppress: Tensor,
                          suppress_first: Optional[Tensor], eot: int, no_speech: int, ts: Sequence[int],
@@ -545,38 +644,58 @@ class DecodeSession:
                          self.sum_logprobs, self.no_speech_prob, eot, no_speech, ts, temperature, seed)
         nv.step_advance(self.state, self.R)
 
+    def set_initial_rows(self, rows: Tensor):
+        """Per-clip prompts (detected language tokens differ per clip): rows int32 [B, n_init]."""
+        self.tokens[:, : rows.shape[1]] = rows.repeat_interleave(self.G, dim=0)
+
+    def results(self, n_tokens: int):
+        """(tokens [R, n_tokens] list, sum_logprobs [R] list, no_speech_prob [R] list) on the host."""
+        return (self.tokens[:, :n_tokens].cpu().tolist(), self.sum_logprobs.cpu().tolist(),
+                self.no_speech_prob.cpu().tolist())
+
+    def _ensure_graph(self):
+        if not self.use_graph or self._graph is not None:
+            return
+        # warm-up outside capture (lazy module init, cudaFuncSetAttribute), then restore the state
+        snap = (self.state.clone(), self.tokens.clone(), self.sum_logprobs.clone(), self.no_speech_prob.clone())
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):
+            self._greedy_step()
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        for dst, src in zip((self.state, self.tokens, self.sum_logprobs, self.no_speech_prob), snap):
+            dst.copy_(src)
+        g = torch.cuda.CUDAGraph()
+        before = nv.kernel_launch_count()
+        with torch.cuda.graph(g):
+            self._greedy_step()
+        # capture records but does not execute: state is still at t=0
+        self._graph_kernels = nv.kernel_launch_count() - before
+        self._graph = g
+
+    def step(self):
+        """One token for every row: graph replay (or the eager kernel sequence) on the CURRENT stream."""
+        if self._graph is not None:
+            self._graph.replay()
+            nv.note_graph_replay(self._graph_kernels)
+        else:
+            self._greedy_step()
+
+    def all_done(self) -> bool:
+        return int(self.state[2].item()) != 0  # every row has emitted EOT (decoding.py:296, 713)
+
     def run_greedy(self, n_sample: int, check_every: int = 8) -> int:
         """Feeds the initial tokens and samples up to ``n_sample`` new ones; returns #graph launches."""
         total = self.n_init - 1 + n_sample
         assert self.n_init + n_sample <= self.tokens.shape[1]
         launches = 0
-        if self.use_graph and self._graph is None:
-            # warm-up outside capture (lazy module init, cudaFuncSetAttribute), then restore the state
-            snap = (self.state.clone(), self.tokens.clone(), self.sum_logprobs.clone(), self.no_speech_prob.clone())
-            side = torch.cuda.Stream(device=self.dev)
-            side.wait_stream(torch.cuda.current_stream(self.dev))
-            with torch.cuda.stream(side):
-                self._greedy_step()
-            torch.cuda.current_stream(self.dev).wait_stream(side)
-            for dst, src in zip((self.state, self.tokens, self.sum_logprobs, self.no_speech_prob), snap):
-                dst.copy_(src)
-            g = torch.cuda.CUDAGraph()
-            before = nv.kernel_launch_count()
-            with torch.cuda.graph(g):
-                self._greedy_step()
-            # capture records but does not execute: state is still at t=0
-            self._graph_kernels = nv.kernel_launch_count() - before
-            self._graph = g
+        self._ensure_graph()
         for i in range(total):
-            if self._graph is not None:
-                self._graph.replay()
-                nv.note_graph_replay(self._graph_kernels)
-            else:
-                self._greedy_step()
+            self.step()
             launches += 1
             sampled = i - (self.n_init - 1) + 1
             if sampled > 0 and sampled % check_every == 0 and i + 1 < total:
-                if int(self.state[2].item()) != 0:  # every row has emitted EOT (decoding.py:296, 713)
+                if self.all_done():
                     break
         return launches
 
@@ -600,25 +719,124 @@ class DecodeSession:
             kv.copy_(self._kv_scratch)
 
 
-_SESSION_CACHE = weakref.WeakKeyDictionary()  # decoder module -> its last DecodeSession
+class SplitSession:
+    """Greedy decode of one batch as `n_split` independent sub-batches on `n_split` CUDA streams.
+
+    A decode step is a serial chain of ~600 kernels: the K/V-streaming attention kernels are HBM-bound, the M<=128
+    GEMMs and LayerNorms between them are latency-bound (a few microseconds each, the SMs mostly idle).  Clips are
+    independent, so two (or more) sub-batches stepping concurrently let one sub-batch's latency-bound chain run under
+    the other's K/V streaming.  Each sub-batch is a full DecodeSession (own step buffers, K/V arena slice and CUDA
+    graph); the packed weights are shared.  Beam search stays on a single session (host-driven reordering).
+    """
+
+    def __init__(self, dec, xa: Tensor, feats: Optional[Sequence[Tensor]], n_group: int, t_cap: int, n_split: int):
+        B = xa.shape[0]
+        n_split = max(1, min(n_split, B))
+        bounds = [(B * i // n_split, B * (i + 1) // n_split) for i in range(n_split)]
+        self.bounds = bounds
+        self.B, self.G, self.R, self.T_cap, self.dev = B, n_group, B * n_group, t_cap, xa.device
+        self.subs = [DecodeSession(dec, xa[lo:hi], None if feats is None else [f[lo:hi] for f in feats], n_group, t_cap)
+                     for lo, hi in bounds]
+        self.streams = [torch.cuda.Stream(device=xa.device) for _ in bounds]
+        first = self.subs[0]
+        self.gated, self.Tx, self.dt, self.p, self.Ta = first.gated, first.Tx, first.dt, first.p, first.Ta
+        self.n_split = n_split
+
+    def _check_feats(self, feats):
+        return self.subs[0]._check_feats(feats)
+
+    def shape_key(self):
+        return (self.dt, self.dev, self.B, self.G, self.T_cap, self.Ta, tuple(self.Tx), id(self.p), self.n_split)
+
+    def load(self, xa: Tensor, feats: Sequence[Tensor]):
+        for sub, (lo, hi) in zip(self.subs, self.bounds):
+            sub.load(xa[lo:hi], [f[lo:hi] for f in feats])
+
+    def configure_greedy(self, *args, **kw):
+        seed = int(kw.pop("seed", 0))
+        for i, sub in enumerate(self.subs):  # the sampling RNG is keyed on (seed, row): decorrelate the sub-batches
+            sub.configure_greedy(*args, seed=seed + 0xA0761D6478BD642F * i, **kw)
+        self.n_init = self.subs[0].n_init
+
+    def set_initial_rows(self, rows: Tensor):
+        for sub, (lo, hi) in zip(self.subs, self.bounds):
+            sub.set_initial_rows(rows[lo:hi])
+
+    def run_greedy(self, n_sample: int, check_every: int = 8) -> int:
+        total = self.n_init - 1 + n_sample
+        main = torch.cuda.current_stream(self.dev)
+        for sub in self.subs:
+            sub._ensure_graph()
+        for st in self.streams:
+            st.wait_stream(main)
+        launches = 0
+        for i in range(total):
+            for sub, st in zip(self.subs, self.streams):
+                with torch.cuda.stream(st):
+                    sub.step()
+            launches += 1
+            sampled = i - (self.n_init - 1) + 1
+            if sampled > 0 and sampled % check_every == 0 and i + 1 < total:
+                done = True
+                for sub, st in zip(self.subs, self.streams):
+                    with torch.cuda.stream(st):
+                        done = sub.all_done() and done
+                if done:
+                    break
+        for st in self.streams:
+            main.wait_stream(st)
+        return launches
+
+    def results(self, n_tokens: int):
+        toks, lps, nsp = [], [], []
+        for sub in self.subs:
+            t, l, n = sub.results(n_tokens)
+            toks += t
+            lps += l
+            nsp += n
+        return toks, lps, nsp
 
 
-def get_session(dec, xa: Tensor, feats: Optional[Sequence[Tensor]], n_group: int, t_cap: int) -> DecodeSession:
+_SESSION_CACHE = weakref.WeakKeyDictionary()  # decoder module -> its last DecodeSession / SplitSession
+
+
+def default_split(n_rows: int, greedy: bool) -> int:
+    """Sub-batches stepping concurrently (SplitSession).  WF_DECODE_SPLIT overrides; beam search is never split."""
+    if not greedy:
+        return 1
+    env = os.environ.get("WF_DECODE_SPLIT")
+    if env:
+        return max(1, int(env))
+    # Measured on B200 (large-v2 AV, B=128, tools/split_probe.py): 1 -> 964 ms, 2 -> 1063 ms, 4 -> 1195 ms per decode
+    # loop; with launch priorities 1018 / 1293 ms.  The attention CTAs fill every SM, so the other sub-batch's GEMM
+    # CTAs (160-190 KB of shared memory each) only get in when an SM drains completely: no useful overlap yet.
+    return 1
+
+
+def get_session(dec, xa: Tensor, feats: Optional[Sequence[Tensor]], n_group: int, t_cap: int, n_split: int = 1):
     """One cached session per decoder: a repeated decode() with the same shapes reuses the ~(B x 370 MB) K/V arena,
     the step buffers and the captured CUDA graph instead of re-allocating and re-capturing them every call."""
     dt = _engine_dtype(xa.dtype)
     p = decoder_pack(dec, dt)
+    n_split = max(1, min(n_split, xa.shape[0]))
+    if os.environ.get("WF_NO_GRAPH", "0") == "1":
+        n_split = 1  # per-kernel profiling mode: one eager stream
     old = _SESSION_CACHE.get(dec)
     n_feats = 0 if feats is None else len(feats)
     if old is not None and os.environ.get("WF_NO_SESSION_CACHE", "0") != "1":
         tx = tuple(f.shape[1] for f in feats) if (old.gated and feats is not None) else ()
         key = (dt, xa.device, xa.shape[0], n_group, t_cap, xa.shape[1], tx, id(p))
+        if n_split > 1:
+            key = key + (n_split,)
         if old.shape_key() == key and (not old.gated or n_feats == len(old.Tx)):
             old.load(xa, old._check_feats(feats))
             return old
     _SESSION_CACHE.pop(dec, None)
     del old
-    sess = DecodeSession(dec, xa, feats, n_group, t_cap)
+    if n_split > 1:
+        sess = SplitSession(dec, xa, feats, n_group, t_cap, n_split)
+    else:
+        sess = DecodeSession(dec, xa, feats, n_group, t_cap)
     _SESSION_CACHE[dec] = sess
     return sess
 

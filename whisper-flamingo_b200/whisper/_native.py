@@ -29,7 +29,8 @@ class _Epilogue(C.Structure):
                 ("ldr", C.c_longlong), ("res_row_mod", C.c_int), ("gate", C.c_void_p), ("act", C.c_int),
                 ("out_f32", C.c_int), ("c_off_ptr", C.c_void_p), ("c_off_mul", C.c_longlong),
                 ("hm_heads", C.c_int), ("hm_T", C.c_int), ("hm_rpb", C.c_int), ("ws", C.c_void_p),
-                ("ws_bytes", C.c_longlong)]
+                ("ws_bytes", C.c_longlong), ("ln_colsum", C.c_void_p), ("ln_eps", C.c_float), ("split_n", C.c_int),
+                ("C2", C.c_void_p)]
 
 
 class _Sample(C.Structure):
@@ -214,8 +215,13 @@ def linear(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias: Optiona
            residual: Optional[torch.Tensor] = None, res_row_mod: int = 0, gate: Optional[torch.Tensor] = None,
            act: int = ACT_NONE, c_off_ptr: Optional[torch.Tensor] = None, c_off_mul: int = 0,
            tile_hint: int = 0, n: Optional[int] = None, head_major: Optional[tuple] = None,
-           ws: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """out[M,N] = residual + tanh(gate) * act(a[M,K] @ w[N,K]^T + bias).  All 2-D row-major views.
+           ws: Optional[torch.Tensor] = None, ln_colsum: Optional[torch.Tensor] = None, ln_eps: float = 1e-5,
+           out2: Optional[torch.Tensor] = None, split_n: int = 0) -> torch.Tensor:
+    """out[M,N] = residual + tanh(gate) * act(LN?(a)[M,K] @ w[N,K]^T + bias).  All 2-D row-major views.
+
+    ln_colsum (bf16, M <= 128): fused LayerNorm of the rows of ``a`` - ``w`` must be W * diag(gamma), ``bias`` must be
+    bias + W beta and ``ln_colsum[n] = sum_k w[n, k]``.
+    out2 / split_n: columns [0, split_n) go to ``out`` (row-major), the rest to the head-major cache ``out2``.
 
     head_major=(heads, T, rows_per_batch): ``out`` is a K/V cache ``[batch, heads, T, 64]`` (any view of its
     storage) and element (m, n) lands at [m // rpb, n // 64, m % rpb (+ offset), n % 64].
@@ -235,10 +241,11 @@ def linear(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias: Optiona
     if gate is not None:
         assert gate.dtype == torch.float32
     hm = head_major or (0, 0, 0)
-    ep = _Epilogue(out.data_ptr(), 0 if head_major else _row_stride(out), _ptr(bias), _ptr(residual),
+    ep = _Epilogue(out.data_ptr(), 0 if (head_major and not split_n) else _row_stride(out), _ptr(bias), _ptr(residual),
                    _row_stride(residual) if residual is not None else 0, res_row_mod, _ptr(gate), act, out_f32,
                    _ptr(c_off_ptr), c_off_mul, hm[0], hm[1], hm[2], _ptr(ws),
-                   0 if ws is None else ws.numel() * ws.element_size())
+                   0 if ws is None else ws.numel() * ws.element_size(), _ptr(ln_colsum), float(ln_eps), int(split_n),
+                   _ptr(out2))
     fam = ("gemm_tc_bf16" if m > 256 else "gemm_tc_bf16_skinny") if dt == WF_BF16 else "gemm_f32"
     with _Prof(fam, flops=2 * m * n * k, bytes=(m * k + n * k) * a.element_size() + m * n * out.element_size()):
         _check(load().wf_linear(dt, a.data_ptr(), _row_stride(a), w.data_ptr(), _row_stride(w), m, n, k,

@@ -302,7 +302,9 @@ class DecodingTask:
             if n_sample <= 0:
                 raise ValueError("the prompt already fills the text context; nothing can be sampled")
             t_cap = self.sample_begin + n_sample
-            session = _engine.get_session(self.model.decoder, audio_features, feats, self.n_group, t_cap)
+            greedy = self.options.beam_size is None
+            session = _engine.get_session(self.model.decoder, audio_features, feats, self.n_group, t_cap,
+                                          _engine.default_split(n_audio * self.n_group, greedy))
             timing.mark("kv_precompute")
             suppress, suppress_first = self._masks(mel.device)
             no_speech = tk.no_speech if tk.no_speech is not None else -1
@@ -315,7 +317,7 @@ class DecodingTask:
                                      seed=(torch.initial_seed() + 0x9E3779B9 * DecodingTask._sample_calls))
             if any(r != list(self.initial_tokens) for r in init_rows):  # detected language tokens differ per clip
                 rows = torch.tensor(init_rows, dtype=torch.int32, device=mel.device)
-                session.tokens[:, : self.sample_begin] = rows.repeat_interleave(self.n_group, dim=0)
+                session.set_initial_rows(rows)
             if self.options.beam_size is None:
                 cand, cand_lp, no_speech_probs = self._run_greedy(session, n_sample)
             else:
@@ -346,9 +348,7 @@ class DecodingTask:
 
     def _run_greedy(self, session: "_engine.DecodeSession", n_sample: int):
         session.run_greedy(n_sample)
-        toks = session.tokens[:, : self.sample_begin + n_sample].cpu().tolist()
-        lps = session.sum_logprobs.cpu().tolist()
-        nsp = session.no_speech_prob.cpu().tolist()
+        toks, lps, nsp = session.results(self.sample_begin + n_sample)
         # GreedyDecoder.finalize pads one EOT so that every row has one (reference :299-302); with best_of the
         # n_group rows of an audio are its independent samples (reference :753-757)
         G, eot = self.n_group, self.tokenizer.eot
