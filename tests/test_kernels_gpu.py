@@ -375,7 +375,10 @@ def test_attention_full_vs_torch(nv, dtype, tol, B, Tq, Tk, H, causal):
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 2e-2)])
 @pytest.mark.parametrize("B,G,H,Tk,dyn", [(2, 1, 6, 1500, False), (16, 1, 12, 750, False), (3, 5, 16, 1500, False),
-                                          (4, 1, 6, 37, True), (1, 1, 6, 300, True), (2, 3, 6, 100, False)])
+                                          (4, 1, 6, 37, True), (1, 1, 6, 300, True), (2, 3, 6, 100, False),
+                                          # >= 2 items per SM: the persistent kernel (head-major bf16 only)
+                                          (32, 1, 12, 750, False), (20, 5, 16, 1500, False), (64, 1, 6, 300, False),
+                                          (50, 2, 6, 257, False)])
 @pytest.mark.parametrize("head_major", [False, True])
 def test_attention_decode_vs_torch(nv, dtype, tol, B, G, H, Tk, dyn, head_major):
     d, R, cap = H * 64, B * G, 448

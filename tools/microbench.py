@@ -163,6 +163,22 @@ def attn():
         print(row, flush=True)
 
 
+def attn2():
+    """Head-major decode attention, persistent kernel vs the per-item kernel (WF_DECODE_PERSIST), in-graph."""
+    persist = os.environ.get("WF_DECODE_PERSIST", "1")
+    for (B, H, Tk, G) in ((128, 20, 1500, 1), (128, 20, 750, 1), (64, 20, 1500, 1), (64, 20, 750, 1), (64, 16, 1500, 5)):
+        d = H * 64
+        n_rot = max(2, int(600e6 // (B * Tk * 2 * d * 2)) + 1)
+        kvs = [torch.randn(B, 2 * H, Tk, 64, device="cuda").bfloat16() for _ in range(n_rot)]
+        q = torch.randn(B * G, d, device="cuda").bfloat16()
+        out = torch.empty_like(q)
+        ws = torch.empty(nv.attention_decode_workspace_bytes(B * G, H), dtype=torch.uint8, device="cuda")
+        us = graph_timeit(lambda i: nv.attention_decode(q, kvs[i], kvs[i][:, H:], 64, 2 * H * Tk * 64, Tk * 64, out, G, H,
+                                                        None, 0, Tk, ws), n_rot, reps=16)
+        print(f"persist={persist} B={B} H={H} Tk={Tk} G={G}: {us:7.1f}us {B * Tk * 2 * d * 2 / us / 1e3:6.0f}GB/s", flush=True)
+        del kvs
+
+
 def ln():
     for rows, d in ((128, 1280), (192000, 1280), (24000, 768)):
         x = torch.randn(rows, d, device="cuda").bfloat16()
@@ -193,4 +209,4 @@ def fa():
 
 if __name__ == "__main__":
     for what in sys.argv[1:] or ["gemm", "attn", "ln", "mel", "fa"]:  # also: skinny, skinny2
-        {"gemm": gemm, "attn": attn, "ln": ln, "mel": mel, "fa": fa, "skinny": skinny, "skinny2": skinny2, "skinny3": skinny3}[what]()
+        {"gemm": gemm, "attn": attn, "ln": ln, "mel": mel, "fa": fa, "skinny": skinny, "skinny2": skinny2, "skinny3": skinny3, "attn2": attn2}[what]()

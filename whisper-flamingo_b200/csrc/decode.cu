@@ -173,11 +173,10 @@ attn_decode_kernel(const T* __restrict__ q, long long ldq, const T* __restrict__
 // mbarrier completion) three stages ahead of the math: the memory system always has 2 CTAs x 3 x 32 KB = 192 KB in
 // flight per SM, independent of register pressure and of the softmax barriers.
 static constexpr int HM_KEYS = 128;
-static constexpr int HM_STAGES = 3;
 static constexpr int HM_TILE_BYTES = HM_KEYS * HD * 2;           // 16 KB of K (or V)
-static constexpr int HM_SMEM_BYTES = HM_STAGES * 2 * HM_TILE_BYTES + 128;
+static constexpr int HM_SMEM_BYTES = 3 * 2 * HM_TILE_BYTES + 128;
 
-template <int NQ>
+template <int NQ, int HM_STAGES = 3>
 __global__ void __launch_bounds__(DT, 2)
 attn_decode_hm_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const __nv_bfloat16* __restrict__ kc,
                       const __nv_bfloat16* __restrict__ vc, long long kv_batch_stride, long long kv_head_stride,
@@ -361,6 +360,203 @@ attn_decode_combine_kernel(const float* __restrict__ partials, T* __restrict__ o
   o[row * ldo + h * HD + d] = from_f32<T>(num / den);
 }
 
+// ---- persistent variant for static-length caches (cross- and gated x-attention): ONE CTA per SM walks a strided list
+// of (audio, head) items; a producer warp keeps PS_STAGES tiles of K/V (32 KB each, plus the item's query rows) in
+// flight ACROSS item boundaries, four consumer warps run an independent online softmax each over their 32 keys of a
+// tile (no block-wide barrier per tile) and merge once per item.  The CTA needs ~100 KB of shared memory, so a
+// decode-step GEMM CTA of another sub-batch still fits on the SM next to it (SplitSession overlap).
+static constexpr int PS_STAGES = 3;
+static constexpr int PS_CONSUMERS = 128;
+static constexpr int PS_THREADS = PS_CONSUMERS + 32;
+template <int NQ>
+struct PsSmem {
+  static constexpr int Q_BYTES = NQ * HD * 2;                                   // bf16 query rows of an item
+  static constexpr int STAGE_BYTES = 2 * HM_TILE_BYTES + ((Q_BYTES + 127) / 128) * 128;
+  static constexpr int DYN_BYTES = PS_STAGES * STAGE_BYTES + 128;
+};
+__device__ __forceinline__ void ps_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+template <int NQ>
+__global__ void __launch_bounds__(PS_THREADS, 1)
+attn_decode_ps_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const __nv_bfloat16* __restrict__ kc,
+                      const __nv_bfloat16* __restrict__ vc, long long kv_batch_stride, long long kv_head_stride,
+                      __nv_bfloat16* __restrict__ o, long long ldo, int H, int len, int n_items) {
+  using L = PsSmem<NQ>;
+  extern __shared__ uint8_t ps_raw[];
+  uint8_t* stage_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ps_raw) + 127) & ~uintptr_t(127));
+  __shared__ __align__(8) uint64_t full_bar[PS_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[PS_STAGES];
+  __shared__ __align__(16) float sq[NQ][HD];
+  __shared__ float comb_acc[2][4][NQ][HD];
+  __shared__ float comb_ml[2][4][NQ][2];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_trigger();
+  const int n_tiles = (len + HM_KEYS - 1) / HM_KEYS;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < PS_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 4);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == 4) {
+    // ------------------------------------------------------------ producer (one lane)
+    if (lane == 0) {
+      const uint64_t pol = l2_policy_evict_first();
+      int stage = 0;
+      uint32_t phase = 0;
+      bool waited = false;
+      long long issued = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int kvb = item / H, h = item - kvb * H;
+        const __nv_bfloat16* kbase = kc + kvb * kv_batch_stride + h * kv_head_stride;
+        const __nv_bfloat16* vbase = vc + kvb * kv_batch_stride + h * kv_head_stride;
+        for (int t = 0; t < n_tiles; ++t, ++issued) {
+          if (issued >= PS_STAGES) mbar_wait(&empty_bar[stage], phase ^ 1);
+          const int rows = min(HM_KEYS, len - t * HM_KEYS);
+          const uint32_t bytes = static_cast<uint32_t>(rows) * HD * 2;
+          uint8_t* dst = stage_base + stage * L::STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], 2 * bytes + (t == 0 ? L::Q_BYTES : 0));
+          bulk_load_1d_hint(dst, kbase + static_cast<long long>(t) * HM_KEYS * HD, bytes, &full_bar[stage], pol);
+          bulk_load_1d_hint(dst + HM_TILE_BYTES, vbase + static_cast<long long>(t) * HM_KEYS * HD, bytes,
+                            &full_bar[stage], pol);
+          if (t == 0) {
+            // the queries are written by the previous kernel: everything before this point streams a static cache
+            if (!waited) { pdl_wait(); waited = true; }
+#pragma unroll
+            for (int i = 0; i < NQ; ++i)
+              bulk_load_1d(dst + 2 * HM_TILE_BYTES + i * HD * 2,
+                           q + (static_cast<long long>(kvb) * NQ + i) * ldq + h * HD, HD * 2, &full_bar[stage]);
+          }
+          if (++stage == PS_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+      if (!waited) pdl_wait();
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------- consumers: thread = key of the tile
+  pdl_wait();  // o / anything written below must not race the previous kernel's readers
+  const int dgrp = lane & 7, ksub = lane >> 3;
+  constexpr float QSCALE = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e): softmax in base 2
+  int stage = 0;
+  uint32_t phase = 0;
+  int parity = 0;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x, parity ^= 1) {
+    const int kvb = item / H, h = item - kvb * H;
+    float m_run[NQ], l_run[NQ], acc[NQ][8];
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) {
+      m_run[i] = -INFINITY;
+      l_run[i] = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    }
+    for (int t = 0; t < n_tiles; ++t) {
+      mbar_wait(&full_bar[stage], phase);
+      const uint8_t* ks = stage_base + stage * L::STAGE_BYTES;
+      const uint8_t* vs = ks + HM_TILE_BYTES;
+      if (t == 0) {
+        const __nv_bfloat16* qs = reinterpret_cast<const __nv_bfloat16*>(ks + 2 * HM_TILE_BYTES);
+        for (int i = tid; i < NQ * HD; i += PS_CONSUMERS) sq[i / HD][i % HD] = __bfloat162float(qs[i]) * QSCALE;
+        ps_bar();
+      }
+      const int key = t * HM_KEYS + tid;
+      float s[NQ];
+#pragma unroll
+      for (int i = 0; i < NQ; ++i) s[i] = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int cc = (j + tid) & 7;
+        const uint4 u = *reinterpret_cast<const uint4*>(ks + tid * 128 + cc * 16);
+        const float kf[8] = {bf16lo(u.x), bf16hi(u.x), bf16lo(u.y), bf16hi(u.y), bf16lo(u.z), bf16hi(u.z), bf16lo(u.w), bf16hi(u.w)};
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) {
+          const float4 qa = *reinterpret_cast<const float4*>(&sq[i][cc * 8]);
+          const float4 qb = *reinterpret_cast<const float4*>(&sq[i][cc * 8 + 4]);
+          s[i] = fmaf(qa.x, kf[0], s[i]); s[i] = fmaf(qa.y, kf[1], s[i]); s[i] = fmaf(qa.z, kf[2], s[i]);
+          s[i] = fmaf(qa.w, kf[3], s[i]); s[i] = fmaf(qb.x, kf[4], s[i]); s[i] = fmaf(qb.y, kf[5], s[i]);
+          s[i] = fmaf(qb.z, kf[6], s[i]); s[i] = fmaf(qb.w, kf[7], s[i]);
+        }
+      }
+      float pr[NQ];
+#pragma unroll
+      for (int i = 0; i < NQ; ++i) {
+        if (key >= len) s[i] = -INFINITY;  // stale rows of a partial tile
+        const float mn = fmaxf(m_run[i], warp_max(s[i]));
+        const bool dead = (mn == -INFINITY);
+        const float corr = dead ? 1.f : ex2_approx(m_run[i] - mn);
+        pr[i] = dead ? 0.f : ex2_approx(s[i] - mn);
+        m_run[i] = mn;
+        l_run[i] = l_run[i] * corr + pr[i];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] *= corr;
+      }
+      // acc += P V over this warp's 32 keys: 4 keys x 8 dim-groups per instruction, p by shuffle
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+        const int kl = kk * 4 + ksub;
+        const int kt = warp * 32 + kl;
+        float pk[NQ];
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) pk[i] = __shfl_sync(0xffffffffu, pr[i], kl);
+        if (t * HM_KEYS + kt < len) {
+          const uint4 u = *reinterpret_cast<const uint4*>(vs + kt * 128 + dgrp * 16);
+          const float vf[8] = {bf16lo(u.x), bf16hi(u.x), bf16lo(u.y), bf16hi(u.y), bf16lo(u.z), bf16hi(u.z), bf16lo(u.w), bf16hi(u.w)};
+#pragma unroll
+          for (int i = 0; i < NQ; ++i) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(pk[i], vf[j], acc[i][j]);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[stage]);
+      if (++stage == PS_STAGES) { stage = 0; phase ^= 1; }
+    }
+    // ---- merge the four warps' (m, l, acc) and write the item's output rows
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) {
+      const float wl = warp_sum(l_run[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float a = acc[i][j];
+        a += __shfl_xor_sync(0xffffffffu, a, 8);
+        a += __shfl_xor_sync(0xffffffffu, a, 16);
+        acc[i][j] = a;
+      }
+      if (ksub == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) comb_acc[parity][warp][i][dgrp * 8 + j] = acc[i][j];
+      }
+      if (lane == 0) {
+        comb_ml[parity][warp][i][0] = m_run[i];
+        comb_ml[parity][warp][i][1] = wl;
+      }
+    }
+    ps_bar();
+    for (int idx = tid; idx < NQ * HD; idx += PS_CONSUMERS) {
+      const int i = idx / HD, d = idx % HD;
+      float M = -INFINITY;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) M = fmaxf(M, comb_ml[parity][w][i][0]);
+      float num = 0.f, den = 0.f;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const float mw = comb_ml[parity][w][i][0];
+        const float sc = (mw == -INFINITY) ? 0.f : ex2_approx(mw - M);
+        num = fmaf(sc, comb_acc[parity][w][i][d], num);
+        den = fmaf(sc, comb_ml[parity][w][i][1], den);
+      }
+      o[(static_cast<long long>(kvb) * NQ + i) * ldo + h * HD + d] = __float2bfloat16_rn(num / den);
+    }
+  }
+}
+
 long long attention_decode_workspace_bytes(int R, int H) {
   return static_cast<long long>(R) * H * 32 /* max splits */ * PART * sizeof(float);
 }
@@ -393,21 +589,62 @@ static int launch_decode_attn(const T* q, long long ldq, const T* kc, const T* v
   if constexpr (sizeof(T) == 2) {
     // head-major cache + long key range: bulk-copy pipelined kernel, one CTA streams a whole (audio, head) item
     // (measured: 5.8 TB/s unsplit vs 4.0 TB/s when the item is cut into 12 one-tile CTAs - the pipeline needs depth)
+    static int persist = -1;
+    if (persist < 0) {
+      const char* e = getenv("WF_DECODE_PERSIST");
+      persist = e ? atoi(e) : 0;  // measured slower than the per-item kernel (4.1 vs 6.0 TB/s): opt-in
+    }
+    if (persist && ld_kv == HD && !len_ptr && len_max >= 256 && blocks >= 2 * num_sms()) {
+      using L = PsSmem<NQ>;
+      static bool ps_configured = false;
+      if (!ps_configured) {
+        WF_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_ps_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           L::DYN_BYTES));
+        ps_configured = true;
+      }
+      WF_CHECK_CUDA(launch_pdl(2, attn_decode_ps_kernel<NQ>, dim3(num_sms()), dim3(PS_THREADS), L::DYN_BYTES, stream, q,
+                               ldq, kc, vc, kv_batch_stride, kv_head_stride, o, ldo, H, len_max, blocks));
+      count_launch();
+      return WF_OK;
+    }
     if (ld_kv == HD && len_max >= 512 && getenv("WF_DECODE_NO_BULK") == nullptr) {
       int hs = 1;
       if (const char* e = getenv("WF_DECODE_SPLITS")) { const int v = atoi(e); if (v > 0) hs = v < max_tiles ? v : max_tiles; }
       if (hs > 1)
         WF_REQUIRE(ws && ws_bytes >= static_cast<long long>(R) * H * hs * PART * (long long)sizeof(float),
                    "attention_decode: workspace too small");
+      static int pad = -1;  // WF_ATTN_SMEM_PAD: extra dynamic shared memory (bytes) to cap the CTAs per SM (experiments)
+      if (pad < 0) {
+        const char* e = getenv("WF_ATTN_SMEM_PAD");
+        pad = e ? atoi(e) : 0;
+      }
       static bool configured = false;
       if (!configured) {
         WF_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_hm_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           HM_SMEM_BYTES));
+                                           HM_SMEM_BYTES + pad));
         configured = true;
       }
       dim3 hgrid(blocks, hs);
-      WF_CHECK_CUDA(launch_pdl(2, attn_decode_hm_kernel<NQ>, hgrid, dim3(DT), HM_SMEM_BYTES, stream, q, ldq, kc, vc,
-                               kv_batch_stride, kv_head_stride, o, ldo, H, len_ptr, len_add, len_max, hs, ws));
+      // Two stages (64 KB per CTA) let THREE CTAs share an SM instead of two: the softmax barriers and the prologue /
+      // epilogue of one CTA hide behind the other two.  Measured on B200, large-v2 decode loop: 852 -> 792 ms.
+      static int two = -1;
+      if (two < 0) {
+        const char* e = getenv("WF_ATTN_STAGES");
+        two = (e && atoi(e) == 3) ? 0 : 1;
+      }
+      if (two) {
+        constexpr int SM2 = 2 * 2 * HM_TILE_BYTES + 128;
+        static bool c2 = false;
+        if (!c2) {
+          WF_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_hm_kernel<NQ, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM2));
+          c2 = true;
+        }
+        WF_CHECK_CUDA(launch_pdl(2, attn_decode_hm_kernel<NQ, 2>, hgrid, dim3(DT), SM2, stream, q, ldq, kc, vc,
+                                 kv_batch_stride, kv_head_stride, o, ldo, H, len_ptr, len_add, len_max, hs, ws));
+      } else {
+        WF_CHECK_CUDA(launch_pdl(2, attn_decode_hm_kernel<NQ>, hgrid, dim3(DT), HM_SMEM_BYTES + pad, stream, q, ldq, kc, vc,
+                                 kv_batch_stride, kv_head_stride, o, ldo, H, len_ptr, len_add, len_max, hs, ws));
+      }
       count_launch();
       if (hs > 1) {
         WF_CHECK_CUDA(launch_pdl(2, attn_decode_combine_kernel<T>, dim3(R * H), dim3(HD), 0, stream, (const float*)ws, o,

@@ -410,6 +410,13 @@ int linear_bf16_skinny(const void* A, long long lda, const void* W, long long ld
   if (rc) return rc;
   rc = make_map_bf16(&mb, W, N, K, ldw, bn);
   if (rc) return rc;
+  static int small = -1;  // WF_SKINNY_SMALL=1: <= 100 KB of shared memory per CTA, so that a GEMM CTA fits on an SM next to
+  if (small < 0) {        // one K/V-streaming attention CTA of another sub-batch (SplitSession)
+    const char* e = getenv("WF_SKINNY_SMALL");
+    small = e ? atoi(e) : 0;
+  }
+  if (small && bn == 32) return launch_skinny<32, 2>(ma, mb, M, N, K, ep, cs, stream);
+  if (small && bn == 64) return launch_skinny<64, 2>(ma, mb, M, N, K, ep, cs, stream);
   switch (bn) {
     case 32: return launch_skinny<32, 4>(ma, mb, M, N, K, ep, cs, stream);
     case 64: return launch_skinny<64, 4>(ma, mb, M, N, K, ep, cs, stream);
