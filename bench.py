@@ -144,6 +144,7 @@ def run_product(args):
     pcm_dev, feat_dev = pcm_host.to(dev), feat_host.to(dev)
 
     if args.single_step:
+        hot_path_step(model, pcm_dev, feat_dev, opt)  # not profiled: one-time weight packing, graph capture
         torch.cuda.synchronize()
         torch.cuda.profiler.start()  # ncu --profile-from-start off: only the hot path is captured, not the weight init
         res = hot_path_step(model, pcm_dev, feat_dev, opt)

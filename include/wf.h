@@ -85,6 +85,13 @@ typedef struct {
    * (ldc), columns [split_n, N) in C2 with the head-major / c_off addressing above (N - split_n == 64 * hm_heads). */
   int split_n;
   void* C2;
+  /* LayerNorm statistics across GEMMs (WF_BF16, M > 128; smaller problems compute them inside the consuming kernel):
+   * stat_out [M, 2 * ceil(N / tile), 2] fp32 receives per-row partial (sum, sum of squares) of the stored values;
+   * a later wf_linear with ln_colsum set reads them back through stat_in / stat_in_slots (= 2 * ceil(N_producer / tile),
+   * tile = the producer's tile_hint). */
+  float* stat_out;
+  const float* stat_in;
+  int stat_in_slots;
 } wf_epilogue_t;
 /* C = residual + tanh(gate) * act(A[M,K] . W[N,K]^T + bias).  tile_hint: 0 = auto, else N-tile 32/64/128/256. */
 int wf_linear(int dtype, const void* A, long long lda, const void* W, long long ldw, int M, int N, int K,

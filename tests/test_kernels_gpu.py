@@ -239,6 +239,32 @@ def test_linear_bf16_fused_layernorm_vs_torch(nv, m, n, k):
     assert (out32 - F.gelu(want)).abs().max().item() <= 2e-2 * scale
 
 
+@pytest.mark.parametrize("m,d,n", [(300, 384, 1152), (1500, 1280, 5120), (129, 768, 768)])
+def test_linear_bf16_layernorm_statistics_across_gemms(nv, m, d, n):
+    """Encoder-sized problems (M > 128): the GEMM that writes the residual stream emits per-row (sum, sum of squares)
+    partials, the next GEMM applies the folded LayerNorm from them (reference model.py:30-32 + :35-41)."""
+    a = _randn(m, d, dtype=torch.bfloat16, seed=1)
+    w0 = _randn(d, d, dtype=torch.bfloat16, seed=2, scale=0.05)
+    res = (_randn(m, d, seed=3) + 0.5).bfloat16()
+    slots = 2 * ((d + 255) // 256)
+    stats = torch.full((m, slots, 2), float("nan"), dtype=torch.float32, device="cuda")
+    x = res.clone()
+    nv.linear(a, w0, x, residual=x, tile_hint=256, stat_out=stats)       # x = res + a w0^T, statistics of the stored x
+    xf = x.float()
+    assert (stats[:, :, 0].sum(1) - xf.sum(1)).abs().max().item() <= 2e-2
+    assert (stats[:, :, 1].sum(1) - (xf * xf).sum(1)).abs().max().item() <= 1e-3 * (xf * xf).sum(1).max().item()
+    gamma, beta = 1.0 + 0.2 * _randn(d, seed=4), 0.3 * _randn(d, seed=5)
+    w32, bias = _randn(n, d, seed=6, scale=0.05), _randn(n, seed=7)
+    w_fold = (w32 * gamma[None, :]).bfloat16()
+    out = torch.full((m, n), float("nan"), dtype=torch.bfloat16, device="cuda")
+    nv.linear(x, w_fold, out, bias=(bias + (w32 * beta[None, :]).sum(1)).contiguous(), act=nv.ACT_GELU,
+              ln_colsum=w_fold.float().sum(1).contiguous(), ln_eps=1e-5, stat_in=stats)
+    want = F.gelu(F.linear(F.layer_norm(xf, (d,), gamma, beta, 1e-5), w32, bias))
+    assert (out.float() - want).abs().max().item() <= 3e-2 * max(1.0, want.abs().max().item())
+    with pytest.raises(nv.WfError):  # more than 128 rows and no statistics: refused, not silently wrong
+        nv.linear(x, w_fold, out, ln_colsum=w_fold.float().sum(1).contiguous())
+
+
 def test_linear_bf16_fused_qkv_two_destinations(nv):
     """q | k,v projection in one GEMM: q columns row-major, k/v columns appended to the head-major self-attention cache
     at the device-side position (reference model.py:76-85 computes the three projections separately)."""

@@ -63,6 +63,7 @@ static LinearEpilogue to_cpp(const wf_epilogue_t* e) {
   o.c_off_ptr = e->c_off_ptr; o.c_off_mul = e->c_off_mul;
   o.hm_heads = e->hm_heads; o.hm_T = e->hm_T; o.hm_rpb = e->hm_rpb; o.ws = e->ws; o.ws_bytes = e->ws_bytes;
   o.ln_colsum = e->ln_colsum; o.ln_eps = e->ln_eps; o.split_n = e->split_n; o.C2 = e->C2;
+  o.stat_out = e->stat_out; o.stat_in = e->stat_in; o.stat_in_slots = e->stat_in_slots;
   return o;
 }
 
@@ -95,7 +96,7 @@ int wf_linear(int dtype, const void* A, long long lda, const void* W, long long 
   WF_REQUIRE(ep->act == WF_ACT_NONE || ep->act == WF_ACT_GELU, "wf_linear: unknown activation %d", ep->act);
   WF_REQUIRE(!ep->residual || ep->ldr > 0, "wf_linear: residual without a row stride");
   const LinearEpilogue e = to_cpp(ep);
-  WF_REQUIRE(dtype == WF_BF16 || (!e.ln_colsum && e.split_n == 0),
+  WF_REQUIRE(dtype == WF_BF16 || (!e.ln_colsum && e.split_n == 0 && !e.stat_out),
              "wf_linear: fused LayerNorm / two-destination output exist for WF_BF16 only");
   if (dtype == WF_BF16) return linear_bf16_tc(A, lda, W, ldw, M, N, K, e, tile_hint, S(stream));
   if (dtype == WF_F32) {

@@ -34,6 +34,13 @@ struct TcEpilogue {
   // columns [split_n, N) to C2 with the head-major / offset addressing above (column index rebased to n - split_n)
   int split_n;
   void* C2;
+  // LayerNorm statistics across kernels (gemm_tc.cu, M > 128): a GEMM that PRODUCES a residual stream also emits, per
+  // output row and per (n-tile, column half), the sum and sum of squares of the values it stored:
+  // stat_out[(m * 2 * n_tiles + 2 * n_blk + half) * 2 + {0, 1}]; the GEMM that CONSUMES the stream (ln_colsum set) adds the
+  // stat_in_slots partials of its rows up instead of reading the activations a second time.
+  float* stat_out;
+  const float* stat_in;
+  int stat_in_slots;
 };
 
 // gemm_skinny.cu
@@ -45,20 +52,25 @@ int linear_bf16_skinny(const void* A, long long lda, const void* W, long long ld
 template <int W>
 __device__ __forceinline__ void finish_chunk(float (&v)[W], const TcEpilogue& ep, int m, long long res_row, int n0,
                                              int N, float gate, long long c_off, float ln_mean = 0.f,
-                                             float ln_rstd = 1.f) {
+                                             float ln_rstd = 1.f, float2* st = nullptr) {
   const bool full = (n0 + W <= N);
   if (ep.ln_colsum) {
+    // y = rstd * (acc - mean * colsum[n]) + bias[n]  as two FMAs per element
+    const float nm = -ln_rstd * ln_mean;
 #pragma unroll
-    for (int j = 0; j < W; ++j)
-      v[j] = ln_rstd * (v[j] - ln_mean * ((full || n0 + j < N) ? __ldg(ep.ln_colsum + n0 + j) : 0.f));
-  }
-  if (ep.bias) {
+    for (int j = 0; j < W; ++j) {
+      const bool ok = full || n0 + j < N;
+      const float b = (ep.bias && ok) ? __ldg(ep.bias + n0 + j) : 0.f;
+      const float cs = ok ? __ldg(ep.ln_colsum + n0 + j) : 0.f;
+      v[j] = fmaf(ln_rstd, v[j], fmaf(nm, cs, b));
+    }
+  } else if (ep.bias) {
 #pragma unroll
     for (int j = 0; j < W; ++j) v[j] += (full || n0 + j < N) ? __ldg(ep.bias + n0 + j) : 0.f;
   }
   if (ep.act == 1) {
 #pragma unroll
-    for (int j = 0; j < W; ++j) v[j] = gelu_erf(v[j]);
+    for (int j = 0; j < W; ++j) v[j] = gelu_fast(v[j]);
   }
   if (ep.gate) {
 #pragma unroll
@@ -82,6 +94,11 @@ __device__ __forceinline__ void finish_chunk(float (&v)[W], const TcEpilogue& ep
       const float* rrow = reinterpret_cast<const float*>(ep.residual) + res_row * ep.ldr + n0;
 #pragma unroll
       for (int j = 0; j < W; ++j) if (full || n0 + j < N) v[j] += rrow[j];
+    }
+    if (st) {
+#pragma unroll
+      for (int j = 0; j < W; ++j)
+        if (full || n0 + j < N) { st->x += v[j]; st->y = fmaf(v[j], v[j], st->y); }
     }
     if (full && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
 #pragma unroll
@@ -108,6 +125,15 @@ __device__ __forceinline__ void finish_chunk(float (&v)[W], const TcEpilogue& ep
 #pragma unroll
         for (int j = 0; j < W; ++j) if (n0 + j < N) v[j] += __bfloat162float(rrow[j]);
       }
+    }
+    if (st) {  // statistics of the ROUNDED values: that is what the consumer's LayerNorm will see
+#pragma unroll
+      for (int j = 0; j < W; ++j)
+        if (full || n0 + j < N) {
+          const float r = __bfloat162float(__float2bfloat16_rn(v[j]));
+          st->x += r;
+          st->y = fmaf(r, r, st->y);
+        }
     }
     if (full && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
 #pragma unroll

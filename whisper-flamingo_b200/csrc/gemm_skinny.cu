@@ -29,6 +29,7 @@ static constexpr int SK_BK = 64;       // one 128-byte swizzle atom of bf16
 static constexpr int SK_KA = 2;        // atoms per pipeline round
 static constexpr int SK_THREADS = 384; // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4..11 epilogue / LN stats
 static constexpr int SK_UMMA_K = 16;
+static constexpr int EPI_THREADS_SK = 256;
 
 template <int BN, int STAGES>
 struct SkCfg {
@@ -72,26 +73,6 @@ __device__ __forceinline__ float2 ld_dsmem_f2(uint32_t addr) {
   float2 v;
   asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
   return v;
-}
-
-// columns [col0 + c * CW, +CW) of this thread's row: sum over the CS partial tiles of the cluster, then the epilogue
-template <int CW>
-__device__ __forceinline__ void reduce_finish(uint32_t dump_local, int dump_ld, int cs, int rloc, int col_in_tile,
-                                              const TcEpilogue& ep, int m, long long res_row, int n0, int N, float gate,
-                                              long long c_off, float mean, float rstd) {
-  float v[CW];
-#pragma unroll
-  for (int j = 0; j < CW; ++j) v[j] = 0.f;
-  const uint32_t off = static_cast<uint32_t>((rloc * dump_ld + col_in_tile) * 4);
-  for (int s = 0; s < cs; ++s) {
-    const uint32_t base = dsmem_addr(dump_local + off, static_cast<uint32_t>(s));
-#pragma unroll
-    for (int j = 0; j < CW; j += 4) {
-      const float4 t = ld_dsmem_f4(base + j * 4);
-      v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
-    }
-  }
-  finish_chunk<CW>(v, ep, m, res_row, n0, N, gate, c_off, mean, rstd);
 }
 
 template <int BN, int STAGES>
@@ -251,33 +232,40 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   else if (ln) __syncthreads();
 
   if (warp >= 4) {
-    const int q = warp & 3;
-    const int grp = (warp - 4) >> 2;
-    const int rloc = q * 32 + lane;
-    const int m = rloc;
-    const bool row_ok = m < M;
     pdl_wait();  // residual / gate / offset may be produced by the previous kernel
     long long c_off = 0;
     if (ep.c_off_ptr) c_off = static_cast<long long>(*ep.c_off_ptr) * ep.c_off_mul;
     const float gate = ep.gate ? tanhf(*ep.gate) : 1.0f;
-    const long long res_row = ep.res_row_mod > 0 ? (m % ep.res_row_mod) : m;
-    float mean = 0.f, rstd = 1.f;
-    if (ln) {
-      float s1 = 0.f, s2 = 0.f;
-      const uint32_t st_local = smem_u32(stat);
-      for (int s = 0; s < CS; ++s) {
+    const uint32_t st_local = smem_u32(stat);
+    // per-row LayerNorm statistics: partial sums of every CTA of the cluster and of both atom groups
+    auto row_stats = [&](int row, float& mean, float& rstd) {
+      float2 t[8][2];
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          const float2 t = ld_dsmem_f2(dsmem_addr(st_local + static_cast<uint32_t>((g * SK_BM + rloc) * 8), s));
-          s1 += t.x;
-          s2 += t.y;
+      for (int s = 0; s < 8; ++s) {
+        if (s < CS) {
+#pragma unroll
+          for (int g = 0; g < 2; ++g)
+            t[s][g] = ld_dsmem_f2(dsmem_addr(st_local + static_cast<uint32_t>((g * SK_BM + row) * 8), s));
+        }
+      }
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int s = 0; s < 8; ++s) {
+        if (s < CS) {
+          s1 += t[s][0].x + t[s][1].x;
+          s2 += t[s][0].y + t[s][1].y;
         }
       }
       mean = s1 / static_cast<float>(K);
-      const float var = fmaxf(s2 / static_cast<float>(K) - mean * mean, 0.f);
-      rstd = rsqrtf(var + ep.ln_eps);
-    }
+      rstd = rsqrtf(fmaxf(s2 / static_cast<float>(K) - mean * mean, 0.f) + ep.ln_eps);
+    };
     if (CS == 1) {
+      const int q = warp & 3;
+      const int grp = (warp - 4) >> 2;
+      const int m = q * 32 + lane;
+      const long long res_row = ep.res_row_mod > 0 ? (m % ep.res_row_mod) : m;
+      float mean = 0.f, rstd = 1.f;
+      if (ln) row_stats(m, mean, rstd);
       const uint32_t tsrc = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
       for (int c = grp; c < BN / 32; c += 2) {
@@ -285,7 +273,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         tmem_ld_32x32(tsrc + c * 32, r);
         tmem_ld_wait();
         const int n0 = n_blk * BN + c * 32;
-        if (row_ok && n0 < N) {
+        if (m < M && n0 < N) {
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -293,21 +281,42 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         }
       }
     } else {
-      const int wc = BN / CS;  // columns of the tile finished by this CTA
-      const int cw = wc < 32 ? wc : 32;
+      // CTA `rank` finishes rows [rank * 128 / CS, +128 / CS) of the tile.  A thread takes 8 consecutive columns, so a
+      // warp reads 1 KB of CONTIGUOUS remote shared memory per partial tile (a row-per-thread mapping measured 8 GB/s
+      // over DSMEM: 32 different 128-byte lines per request) and stores coalesced 16-byte pieces of output rows.
+      const int et = (warp - 4) * 32 + lane;
+      const int rows_per = SK_BM / CS;
+      constexpr int GPR = BN / 8;
       const uint32_t dump_local = smem_u32(dump);
-      if (row_ok) {
-        for (int c = grp; c * cw < wc; c += 2) {
-          const int col = rank * wc + c * cw;
-          const int n0 = n_blk * BN + col;
-          if (n0 >= N) continue;
-          if (cw == 32)
-            reduce_finish<32>(dump_local, Cfg::DUMP_LD, CS, rloc, col, ep, m, res_row, n0, N, gate, c_off, mean, rstd);
-          else if (cw == 16)
-            reduce_finish<16>(dump_local, Cfg::DUMP_LD, CS, rloc, col, ep, m, res_row, n0, N, gate, c_off, mean, rstd);
-          else
-            reduce_finish<8>(dump_local, Cfg::DUMP_LD, CS, rloc, col, ep, m, res_row, n0, N, gate, c_off, mean, rstd);
+      for (int it = et; it < rows_per * GPR; it += EPI_THREADS_SK) {
+        const int row = rank * rows_per + it / GPR;
+        const int col = (it % GPR) * 8;
+        const int n0 = n_blk * BN + col;
+        if (row >= M || n0 >= N) continue;
+        const uint32_t off = static_cast<uint32_t>((row * Cfg::DUMP_LD + col) * 4);
+        float4 t[8][2];
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+          if (s < CS) {
+            const uint32_t base = dsmem_addr(dump_local + off, static_cast<uint32_t>(s));
+            t[s][0] = ld_dsmem_f4(base);
+            t[s][1] = ld_dsmem_f4(base + 16);
+          }
         }
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = 0.f;
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+          if (s < CS) {
+            v[0] += t[s][0].x; v[1] += t[s][0].y; v[2] += t[s][0].z; v[3] += t[s][0].w;
+            v[4] += t[s][1].x; v[5] += t[s][1].y; v[6] += t[s][1].z; v[7] += t[s][1].w;
+          }
+        }
+        float mean = 0.f, rstd = 1.f;
+        if (ln) row_stats(row, mean, rstd);
+        const long long res_row = ep.res_row_mod > 0 ? (row % ep.res_row_mod) : row;
+        finish_chunk<8>(v, ep, row, res_row, n0, N, gate, c_off, mean, rstd);
       }
     }
   }
@@ -366,10 +375,13 @@ static int launch_skinny(const CUtensorMap& ma, const CUtensorMap& mb, int M, in
 }
 
 // Tile width and cluster size for an [M <= 128] x N x K problem.  Measured on B200 inside a CUDA graph with PDL
-// (tools/microbench.py skinny3, M = 128): t ~= 2.3 us + 0.22 us per 64-wide k-atom walked by one CTA, + ~2.5 us for a
-// 2-CTA cluster and ~5.5 us for a 4-CTA one (cluster scheduling + two cluster barriers + the DSMEM reduction).  So K
-// is split only when a CTA would otherwise walk >= 64 atoms (K >= 4096: 20.0 -> 12.6 us at K = 5120), and the N tile
-// is the narrowest that still fits the grid on the machine in one wave.
+// (tools/microbench.py skinny3, M = 128):
+//   * one CTA walks a 64-wide k-atom in ~0.22 us (32-wide tile) .. 0.28 us (128-wide): the SM's shared-memory
+//     bandwidth carries the TMA fill AND the operand reads of four MMAs (the 128-row activation slab is re-read by
+//     every MMA), ~40 .. 64 KB per atom; fixed cost ~2.3 us;
+//   * a cluster costs ~1.1 us for its two barriers plus the DSMEM reduction at ~20 B/clk per SM (1.6 us for 32 KB of
+//     partials), so K is split 2-way only for the narrowest tile and 4-way only when a CTA would otherwise walk
+//     >= 64 atoms:  N=K=1280 6.95 -> 6.39 us (32, cs 2);  N=1280, K=5120 20.2 -> 10.5 us (64, cs 4).
 bool skinny_plan(int M, int N, int K, int tile_hint, int* bn_out, int* cs_out) {
   if (M > SK_BM) return false;
   static int mode = -1, force_cs = -1;
@@ -382,17 +394,15 @@ bool skinny_plan(int M, int N, int K, int tile_hint, int* bn_out, int* cs_out) {
   if (mode == 0) return false;
   const int sms = num_sms();
   const int rounds = (K + SK_KA * SK_BK - 1) / (SK_KA * SK_BK);
-  int cs = 1;
-  if (rounds >= 32) cs = 4;
+  const int bns[4] = {32, 64, 128, 256};
+  int cs = rounds >= 32 ? 4 : 1;
+  if (cs == 1 && rounds >= 8 && !tile_hint && ((N + 31) / 32) * 2 <= sms) cs = 2;  // -> (32, 2)
   if (force_cs) cs = force_cs;
   while (cs > 1 && cs > rounds) cs >>= 1;
   for (;; cs >>= 1) {
-    const int bns[4] = {32, 64, 128, 256};
     for (int i = 0; i < 4; ++i) {
       const int bn = bns[i];
       if (tile_hint && bn != tile_hint) continue;
-      if (bn / cs < 8) continue;
-      if (cs > 1 && bn < 64 && !tile_hint) continue;  // 4 x 8-column slices finish slower than 4 x 16
       const int tiles = (N + bn - 1) / bn;
       if (tiles * cs > sms) continue;
       *bn_out = bn;

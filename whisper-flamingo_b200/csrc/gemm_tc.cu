@@ -176,6 +176,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const long long res_row = ep.res_row_mod > 0 ? (m % ep.res_row_mod) : m;
       const uint32_t tsrc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
       if (S == 1) {
+        float mean = 0.f, rstd = 1.f;
+        if (ep.ln_colsum && row_ok) {  // LayerNorm statistics of this row, emitted by the kernel that produced it
+          // all partials of the row are requested before the first add (a counted loop would serialise the round trips)
+          float s1 = 0.f, s2 = 0.f;
+          const float4* sp = reinterpret_cast<const float4*>(ep.stat_in + static_cast<long long>(m) * ep.stat_in_slots * 2);
+          const int n4 = ep.stat_in_slots >> 1;  // slots are written in pairs (two column halves per n-tile)
+          float4 t[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) t[i] = (i < n4) ? __ldg(sp + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            s1 += t[i].x + t[i].z;
+            s2 += t[i].y + t[i].w;
+          }
+          for (int i = 8; i < n4; ++i) {
+            const float4 u = __ldg(sp + i);
+            s1 += u.x + u.z;
+            s2 += u.y + u.w;
+          }
+          mean = s1 / static_cast<float>(K);
+          rstd = rsqrtf(fmaxf(s2 / static_cast<float>(K) - mean * mean, 0.f) + ep.ln_eps);
+        }
+        float2 st = make_float2(0.f, 0.f);
 #pragma unroll 1
         for (int c = csel; c < BN / 32; c += 2) {
           uint32_t r[32];
@@ -186,9 +209,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-            finish_chunk<32>(v, ep, m, res_row, n0, N, gate, c_off);
+            finish_chunk<32>(v, ep, m, res_row, n0, N, gate, c_off, mean, rstd, ep.stat_out ? &st : nullptr);
           }
         }
+        if (ep.stat_out && row_ok)
+          reinterpret_cast<float2*>(ep.stat_out)[(static_cast<long long>(m) * n_tiles + n_blk) * 2 + csel] = st;
         tc_fence_before();
         mbar_arrive(&tempty_bar[acc]);
       } else {
@@ -357,11 +382,14 @@ int linear_bf16_tc(const void* A, long long lda, const void* W, long long ldw, i
   ep.hm_heads = e.hm_heads; ep.hm_T = e.hm_T; ep.hm_rpb = e.hm_rpb;
   ep.splits = 1; ep.ws_part = nullptr; ep.ws_count = nullptr;
   ep.ln_colsum = e.ln_colsum; ep.ln_eps = e.ln_eps; ep.split_n = e.split_n; ep.C2 = e.C2;
+  ep.stat_out = e.stat_out; ep.stat_in = e.stat_in; ep.stat_in_slots = e.stat_in_slots;
   {
     int sbn = 0, scs = 1;  // decode step (one M tile): cluster split-K kernel
     if (skinny_plan(M, N, K, tile_hint, &sbn, &scs)) return linear_bf16_skinny(A, lda, W, ldw, M, N, K, ep, sbn, scs, stream);
   }
-  WF_REQUIRE(!e.ln_colsum, "linear: the fused LayerNorm needs M <= 128 and N small enough for one wave (M=%d N=%d)", M, N);
+  WF_REQUIRE(!e.ln_colsum || (e.stat_in && e.stat_in_slots > 0),
+             "linear: a fused LayerNorm over more than 128 rows needs the row statistics of the producing GEMM (M=%d)", M);
+  WF_REQUIRE(!(e.stat_out && e.ws), "linear: row statistics cannot be combined with the split-K workspace");
   CUtensorMap ma, mb;
   int rc = make_map_bf16(&ma, A, M, K, lda, BM);
   if (rc) return rc;

@@ -29,6 +29,10 @@ struct LinearEpilogue {
   // two-destination output: columns [0, split_n) -> C row-major, [split_n, N) -> C2 (head-major / offset addressing)
   int split_n = 0;
   void* C2 = nullptr;
+  // LayerNorm statistics handed from the producing GEMM to the consuming one (M > 128): see TcEpilogue
+  float* stat_out = nullptr;
+  const float* stat_in = nullptr;
+  int stat_in_slots = 0;
 };
 
 // gemm_tc.cu / gemm_f32.cu

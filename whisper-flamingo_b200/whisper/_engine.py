@@ -243,7 +243,7 @@ class _LnLinear:
 def _fold_ln(ln: _LnPack, w_master: Tensor, b: Optional[Tensor], dt) -> _LnLinear:
     w32 = w_master.detach().float()
     wf = _to_dtype((w32 * ln.w[None, :]).contiguous(), dt).contiguous()
-    bias = w32 @ ln.b
+    bias = (w32 * ln.b[None, :]).sum(dim=1)  # W beta (elementwise: weight packing is plumbing, not a library GEMM)
     if b is not None:
         bias = bias + b
     return _LnLinear(wf, wf.float().sum(dim=1).contiguous(), bias.contiguous())
@@ -278,6 +278,29 @@ def decoder_fold(dec, p: _DecoderPack, dt) -> List[_BlockFold]:
         fold = [_fold_block(blk, bp, dt) for blk, bp in zip(dec.blocks, p.blocks)]
         p.__dict__["_fold"] = fold
     return fold
+
+
+@dataclass
+class _EncBlockFold:
+    qkv: _LnLinear
+    mlp1: _LnLinear
+
+
+def encoder_fold(enc, p: _EncoderPack, dt) -> List[_EncBlockFold]:
+    """attn_ln folded into the q|k|v projection and mlp_ln into the first MLP projection of every encoder block."""
+    fold = p.__dict__.get("_fold")
+    if fold is None:
+        fold = []
+        for blk, bp in zip(enc.blocks, p.blocks):
+            qkv_master = torch.cat([blk.attn.query.weight.detach(), blk.attn.key.weight.detach(),
+                                    blk.attn.value.weight.detach()], dim=0)
+            fold.append(_EncBlockFold(_fold_ln(bp.attn_ln, qkv_master, bp.attn.qkv_b, dt),
+                                      _fold_ln(bp.mlp_ln, blk.mlp[0].weight, bp.mlp.b1, dt)))
+        p.__dict__["_fold"] = fold
+    return fold
+
+
+STAT_TILE = 256  # N tile of the GEMMs that emit LayerNorm statistics (fixes the number of partials per row)
 
 
 def encoder_pack(enc, dt) -> _EncoderPack:
@@ -329,6 +352,15 @@ def encoder_forward(enc, mel: Tensor, track_norm: bool = False):
         x = _empty(B * T2, d, dt, dev)
         x_norm = None
         n_ctx = p.pos.shape[0]
+        # bf16: the block LayerNorms run inside the GEMMs.  Every GEMM that writes the residual stream x also emits
+        # per-row (sum, sum of squares) partials; the q|k|v and MLP-up GEMMs read the raw x with gamma / beta folded
+        # into their weights and normalise in the epilogue.  x is never re-read by a LayerNorm kernel.
+        fused = (dt == torch.bfloat16 and not track_norm and T2 <= n_ctx
+                 and os.environ.get("WF_NO_LN_FUSION", "0") != "1")
+        fold = encoder_fold(enc, p, dt) if fused else None
+        stats = (torch.empty((B * T2, 2 * ((d + STAT_TILE - 1) // STAT_TILE), 2), dtype=torch.float32, device=dev)
+                 if fused else None)
+        skw = dict(tile_hint=STAT_TILE, stat_out=stats) if fused and B * T2 > 128 else {}
         if track_norm or T2 > n_ctx:
             # diagnostics / over-long input: stem without the fused positional add, then crop + add
             nv.linear(a2, p.conv2_w, x, bias=p.conv2_b, act=nv.ACT_GELU)
@@ -341,17 +373,28 @@ def encoder_forward(enc, mel: Tensor, track_norm: bool = False):
             xc = x3.reshape(B * T2, d).contiguous()
             x = nv.add_rowmod(xc, p.pos_f32, _empty(B * T2, d, dt, dev), T2)
         else:
-            nv.linear(a2, p.conv2_w, x, bias=p.conv2_b, act=nv.ACT_GELU, residual=p.pos[:T2], res_row_mod=T2)
+            nv.linear(a2, p.conv2_w, x, bias=p.conv2_b, act=nv.ACT_GELU, residual=p.pos[:T2], res_row_mod=T2, **skw)
         del a2
         M = B * T2
-        xn, qkv, att = _empty(M, d, dt, dev), _empty(M, 3 * d, dt, dev), _empty(M, d, dt, dev)
+        qkv, att = _empty(M, 3 * d, dt, dev), _empty(M, d, dt, dev)
         hbuf = _empty(M, 4 * d, dt, dev)
-        for bp in p.blocks:
-            nv.layernorm(x, bp.attn_ln.w, bp.attn_ln.b, xn)
-            nv.linear(xn, bp.attn.qkv_w, qkv, bias=bp.attn.qkv_b)
-            nv.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], att, B, T2, T2, p.n_head, causal=False)
-            nv.linear(att, bp.attn.o_w, x, bias=bp.attn.o_b, residual=x)
-            _mlp_inplace(x, xn, hbuf, bp.mlp_ln, bp.mlp)
+        if fused:
+            ckw = dict(stat_in=stats) if M > 128 else {}
+            for bp, bf in zip(p.blocks, fold):
+                nv.linear(x, bf.qkv.w, qkv, bias=bf.qkv.bias, ln_colsum=bf.qkv.colsum, ln_eps=bf.qkv.eps, **ckw)
+                nv.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], att, B, T2, T2, p.n_head, causal=False)
+                nv.linear(att, bp.attn.o_w, x, bias=bp.attn.o_b, residual=x, **skw)
+                nv.linear(x, bf.mlp1.w, hbuf, bias=bf.mlp1.bias, act=nv.ACT_GELU, ln_colsum=bf.mlp1.colsum,
+                          ln_eps=bf.mlp1.eps, **ckw)
+                nv.linear(hbuf, bp.mlp.w2, x, bias=bp.mlp.b2, residual=x, **skw)
+        else:
+            xn = _empty(M, d, dt, dev)
+            for bp in p.blocks:
+                nv.layernorm(x, bp.attn_ln.w, bp.attn_ln.b, xn)
+                nv.linear(xn, bp.attn.qkv_w, qkv, bias=bp.attn.qkv_b)
+                nv.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], att, B, T2, T2, p.n_head, causal=False)
+                nv.linear(att, bp.attn.o_w, x, bias=bp.attn.o_b, residual=x)
+                _mlp_inplace(x, xn, hbuf, bp.mlp_ln, bp.mlp)
         out = _empty(M, d, dt, dev)
         nv.layernorm(x, p.ln_post.w, p.ln_post.b, out)
         out = out.view(B, T2, d)

@@ -30,7 +30,7 @@ class _Epilogue(C.Structure):
                 ("out_f32", C.c_int), ("c_off_ptr", C.c_void_p), ("c_off_mul", C.c_longlong),
                 ("hm_heads", C.c_int), ("hm_T", C.c_int), ("hm_rpb", C.c_int), ("ws", C.c_void_p),
                 ("ws_bytes", C.c_longlong), ("ln_colsum", C.c_void_p), ("ln_eps", C.c_float), ("split_n", C.c_int),
-                ("C2", C.c_void_p)]
+                ("C2", C.c_void_p), ("stat_out", C.c_void_p), ("stat_in", C.c_void_p), ("stat_in_slots", C.c_int)]
 
 
 class _Sample(C.Structure):
@@ -216,12 +216,15 @@ def linear(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias: Optiona
            act: int = ACT_NONE, c_off_ptr: Optional[torch.Tensor] = None, c_off_mul: int = 0,
            tile_hint: int = 0, n: Optional[int] = None, head_major: Optional[tuple] = None,
            ws: Optional[torch.Tensor] = None, ln_colsum: Optional[torch.Tensor] = None, ln_eps: float = 1e-5,
-           out2: Optional[torch.Tensor] = None, split_n: int = 0) -> torch.Tensor:
+           out2: Optional[torch.Tensor] = None, split_n: int = 0, stat_out: Optional[torch.Tensor] = None,
+           stat_in: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[M,N] = residual + tanh(gate) * act(LN?(a)[M,K] @ w[N,K]^T + bias).  All 2-D row-major views.
 
     ln_colsum (bf16, M <= 128): fused LayerNorm of the rows of ``a`` - ``w`` must be W * diag(gamma), ``bias`` must be
     bias + W beta and ``ln_colsum[n] = sum_k w[n, k]``.
     out2 / split_n: columns [0, split_n) go to ``out`` (row-major), the rest to the head-major cache ``out2``.
+    stat_out / stat_in: fp32 ``[M, slots, 2]`` per-row partial (sum, sum of squares) written by the GEMM that produces
+    a residual stream and read by the ln_colsum GEMM that consumes it (M > 128; ``slots = 2 * ceil(N / tile)``).
 
     head_major=(heads, T, rows_per_batch): ``out`` is a K/V cache ``[batch, heads, T, 64]`` (any view of its
     storage) and element (m, n) lands at [m // rpb, n // 64, m % rpb (+ offset), n % 64].
@@ -245,7 +248,7 @@ def linear(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias: Optiona
                    _row_stride(residual) if residual is not None else 0, res_row_mod, _ptr(gate), act, out_f32,
                    _ptr(c_off_ptr), c_off_mul, hm[0], hm[1], hm[2], _ptr(ws),
                    0 if ws is None else ws.numel() * ws.element_size(), _ptr(ln_colsum), float(ln_eps), int(split_n),
-                   _ptr(out2))
+                   _ptr(out2), _ptr(stat_out), _ptr(stat_in), 0 if stat_in is None else stat_in.shape[1])
     fam = ("gemm_tc_bf16" if m > 256 else "gemm_tc_bf16_skinny") if dt == WF_BF16 else "gemm_f32"
     with _Prof(fam, flops=2 * m * n * k, bytes=(m * k + n * k) * a.element_size() + m * n * out.element_size()):
         _check(load().wf_linear(dt, a.data_ptr(), _row_stride(a), w.data_ptr(), _row_stride(w), m, n, k,
