@@ -249,3 +249,62 @@ def test_split_session_streams_give_identical_tokens(av_model, mel2, monkeypatch
     assert outs[1][1] == outs[2][1] == outs[3][1] and outs[1][2] == outs[2][2] == outs[3][2]
     gold = load_decode_golden()["cases"]["greedy_av"]
     assert outs[2][0][0] == gold["tokens"][0][:12]
+
+
+def test_large_v2_width_av_model_fp32_tokens_and_bf16_decode_logits():
+    """large-v2 widths (d=1280, 20 heads, n_text_ctx=768, 750 x 1024 features - BASELINE config 4 with 2+2 layers so
+    that the CPU oracle finishes in seconds): fp32 greedy tokens identical to the oracle; the bf16 decode session
+    (cluster split-K GEMMs with folded LayerNorm, fused q|k,v, head-major K/V caches, bulk-copy attention) must
+    reproduce the oracle's next-token logits within the stated bf16 tolerance."""
+    import whisper
+    from whisper import _engine
+    from whisper.decoding import DecodingTask
+    dims = dict(n_mels=80, n_audio_ctx=1500, n_audio_state=1280, n_audio_head=20, n_audio_layer=2, n_vocab=51865,
+                n_text_ctx=768, n_text_state=1280, n_text_head=20, n_text_layer=2)
+    model = build_model(gated=True, device="cuda", dims=dims)
+    pcm = _pcm(3)
+    mel = torch.stack([whisper.log_mel_spectrogram(p.cuda()) for p in pcm])
+    feat = _feat(3, frames=750)
+    n_new = 5
+    opt32 = whisper.DecodingOptions(language="en", without_timestamps=True, sample_len=n_new, fp16=False)
+    res32 = whisper.decode(model, mel, opt32, x_v=feat.cuda())
+    task = DecodingTask(model, opt32)
+    tk = task.tokenizer
+    spec = odec.DecodeSpec(initial_tokens=tuple(task.initial_tokens), eot=tk.eot, sot=tk.sot, no_speech=tk.no_speech,
+                           suppress_tokens=tuple(task._get_suppress_tokens()),
+                           blank_tokens=tuple(tk.encode(" ") + [tk.eot]), sample_len=n_new, n_ctx=768)
+    sd, od = oracle_sd(model), om.Dims(**dims)
+    want = odec.decode(sd, od, spec, mel.cpu(), feat)
+    assert [r.tokens for r in res32] == [w.tokens for w in want]
+    # bf16 engine: logits of the position that samples the LAST token, given the fp32 tokens as history
+    _engine.clear_sessions()
+    hist = [list(task.initial_tokens) + w.tokens[:-1] for w in want]
+    xa16 = model.encoder(mel.bfloat16())
+    sess = _engine.DecodeSession(model.decoder, xa16, [feat.cuda()], 1, len(hist[0]) + 1)
+    assert sess.fold is not None, "the fused LayerNorm decode path must be the one exercised"
+    suppress = torch.zeros(51865, dtype=torch.uint8, device="cuda")
+    sess.configure_greedy(task.initial_tokens, task.sot_index, suppress, None, tk.eot, tk.no_speech, (-1, -1, -1))
+    sess.tokens[:, : len(hist[0])] = torch.tensor(hist, dtype=torch.int32, device="cuda")
+    for _ in range(len(hist[0])):
+        sess._forward_token()
+        whisper._native.step_advance(sess.state, sess.R)
+    got = sess.logits[:, :51865].float().cpu()
+    xa32 = om.encoder_forward(sd, od, mel.cpu())
+    ref = om.decoder_forward(sd, od, torch.tensor(hist), xa32, xt_list=[feat])[:, -1]
+    e = rel_l2(got, ref)
+    assert e <= BF16_LOGIT_TOL, e
+    # and the unfused bf16 session (LayerNorm kernels, separate q / k,v GEMMs) agrees with the fused one
+    import os
+    os.environ["WF_NO_LN_FUSION"] = "1"
+    try:
+        plain = _engine.DecodeSession(model.decoder, xa16, [feat.cuda()], 1, len(hist[0]) + 1)
+        assert plain.fold is None
+        plain.configure_greedy(task.initial_tokens, task.sot_index, suppress, None, tk.eot, tk.no_speech, (-1, -1, -1))
+        plain.tokens[:, : len(hist[0])] = torch.tensor(hist, dtype=torch.int32, device="cuda")
+        for _ in range(len(hist[0])):
+            plain._forward_token()
+            whisper._native.step_advance(plain.state, plain.R)
+    finally:
+        os.environ["WF_NO_LN_FUSION"] = "0"
+    assert rel_l2(plain.logits[:, :51865].float(), ref) <= BF16_LOGIT_TOL
+    assert rel_l2(got, plain.logits[:, :51865].float().cpu()) <= BF16_LOGIT_TOL

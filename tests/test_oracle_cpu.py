@@ -234,3 +234,37 @@ def test_libwf_exports_every_declared_symbol():
         assert hasattr(lib, name), f"libwf.so does not export {name}"
     assert declared == set(_native.EXPORTED_SYMBOLS), declared ^ set(_native.EXPORTED_SYMBOLS)
     assert _native.load().wf_version() >= 100
+
+
+def test_load_model_accepts_fork_lightning_and_upstream_checkpoints(tmp_path):
+    """checkpoint ingestion.  The same weights saved (a) in the fork's own format, (b) as a Lightning
+    checkpoint with the `model.` prefix and no dims, (c) with upstream Whisper-Flamingo key names must all load into
+    identical parameters (reference whisper/__init__.py:152-159, whisper-flamingo_kloka_crawled.py:172-183)."""
+    import whisper
+    from helpers import TINY, build_model
+    dims = dict(TINY, n_audio_layer=1, n_text_layer=2)
+    model = build_model(gated=True, device="cpu", dims=dims)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    a = tmp_path / "fork.pt"
+    torch.save({"dims": dims, "model_state_dict": sd}, a)
+
+    def upstream(key):
+        key = key.replace("gated_x_attn_layers.0.attn_ln.", "gated_x_attn_ln.")
+        key = key.replace("gated_x_attn_layers.0.attn_gate", "attn_gate")
+        return key.replace("gated_x_attn_layers.0.attn.", "gated_x_attn.")
+
+    b = tmp_path / "lightning.ckpt"
+    torch.save({"state_dict": {"model." + k: v for k, v in sd.items()}, "epoch": 3}, b)
+    c = tmp_path / "upstream.ckpt"
+    up = {"model." + upstream(k): v for k, v in sd.items()}
+    up["model.encoder.video_projection_scalar"] = torch.ones(1)  # upstream-only key: ignored (strict=False)
+    assert any(".gated_x_attn.query.weight" in k for k in up) and not any("gated_x_attn_layers" in k for k in up)
+    torch.save({"state_dict": up}, c)
+    for path in (a, b, c):
+        got = whisper.load_model(str(path), device="cpu", add_gated_x_attn=1, bert_dim=1024, num_langs=1)
+        assert got.dims == whisper.ModelDimensions(**dims)
+        gsd = got.state_dict()
+        assert gsd.keys() == sd.keys()
+        assert all(torch.equal(gsd[k], sd[k]) for k in sd), path
+    with pytest.raises(RuntimeError):
+        whisper.load_model("no-such-model")
