@@ -48,6 +48,11 @@ bool skinny_plan(int M, int N, int K, int tile_hint, int* bn_out, int* cs_out);
 int linear_bf16_skinny(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K,
                        const TcEpilogue& ep, int bn, int cs, cudaStream_t stream);
 
+// gemm_tc2.cu
+bool pair_gemm_usable(int M, int N, int K);
+int linear_bf16_pair(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K,
+                     const TcEpilogue& ep, cudaStream_t stream);
+
 // bias / GELU / gate / residual / convert / store for W (8, 16 or 32) consecutive columns of one output row
 template <int W>
 __device__ __forceinline__ void finish_chunk(float (&v)[W], const TcEpilogue& ep, int m, long long res_row, int n0,

@@ -390,6 +390,8 @@ int linear_bf16_tc(const void* A, long long lda, const void* W, long long ldw, i
   WF_REQUIRE(!e.ln_colsum || (e.stat_in && e.stat_in_slots > 0),
              "linear: a fused LayerNorm over more than 128 rows needs the row statistics of the producing GEMM (M=%d)", M);
   WF_REQUIRE(!(e.stat_out && e.ws), "linear: row statistics cannot be combined with the split-K workspace");
+  if ((tile_hint == 0 || tile_hint == 256) && !e.ws && pair_gemm_usable(M, N, K))
+    return linear_bf16_pair(A, lda, W, ldw, M, N, K, ep, stream);  // large M: 256 x 256 tiles on CTA pairs
   CUtensorMap ma, mb;
   int rc = make_map_bf16(&ma, A, M, K, lda, BM);
   if (rc) return rc;

@@ -356,7 +356,7 @@ def encoder_forward(enc, mel: Tensor, track_norm: bool = False):
         # per-row (sum, sum of squares) partials; the q|k|v and MLP-up GEMMs read the raw x with gamma / beta folded
         # into their weights and normalise in the epilogue.  x is never re-read by a LayerNorm kernel.
         fused = (dt == torch.bfloat16 and not track_norm and T2 <= n_ctx
-                 and os.environ.get("WF_NO_LN_FUSION", "0") != "1")
+                 and os.environ.get("WF_NO_LN_FUSION", "0") != "1" and os.environ.get("WF_NO_ENC_LN_FUSION", "0") != "1")
         fold = encoder_fold(enc, p, dt) if fused else None
         stats = (torch.empty((B * T2, 2 * ((d + STAT_TILE - 1) // STAT_TILE), 2), dtype=torch.float32, device=dev)
                  if fused else None)
