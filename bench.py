@@ -107,11 +107,15 @@ def build_model(workload: str, device):
     return model
 
 
+BEAM = 0  # --beam N: beam search instead of greedy (BASELINE config 3: medium, beam 5)
+
+
 def options():
     import whisper
     # EOT is suppressed so that every clip costs exactly SAMPLE_LEN steps
     return whisper.DecodingOptions(language="en", task="transcribe", without_timestamps=True, temperature=0.0,
-                                   sample_len=SAMPLE_LEN, suppress_tokens="-1,50257", suppress_blank=True, fp16=True)
+                                   sample_len=SAMPLE_LEN, suppress_tokens="-1,50257", suppress_blank=True, fp16=True,
+                                   beam_size=BEAM or None)
 
 
 def hot_path_step(model, pcm_dev, feat_dev, opt):
@@ -211,7 +215,8 @@ def run_product(args):
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"{args.workload} AV (gated x-attn, n_text_ctx=768), B={B}/GPU, 30 s clips, "
-                               f"750x1024 features, greedy {SAMPLE_LEN} tokens (EOT suppressed), bf16",
+                               f"750x1024 features, {'beam-%d' % BEAM if BEAM else 'greedy'} {SAMPLE_LEN} tokens "
+                               f"(EOT suppressed), bf16",
                    "global_batch": B * world, "parallelism": f"dp{world}", "l2": "inputs_larger_than_l2",
                    "random_init_weights": True},
         "e2e": {"value": audio_s / (ms_e2e / 1e3), "unit": "audio-s/s",
@@ -271,8 +276,15 @@ def profile_kernels(model, pcm_dev, feat_dev, opt, B, step_ms):
         ach, peak, unit = f["flops"] / (f["ms"] * 1e-3) / 1e12, pk["tc_sustained"], "TFLOP/s"
     else:
         ach, peak, unit = f["bytes"] / (f["ms"] * 1e-3) / 1e9, pk["hbm"], "GB/s"
+    # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/
+    # r01_ncu_full_attn_decode_hm.txt: 988.0 MB for a cross-attention launch, 499.2 MB for an x-attention launch; the
+    # family alternates the two, algorithmic 983.0 / 491.5 MB) - only for the configuration that was captured
+    traffic = None
+    if top["kernel"] == "attention_decode" and B == 128 and not BEAM and len(model.decoder.blocks) == 32:
+        traffic = 0.5 * (988.0e6 + 499.2e6)
     roof = {"kernel": top["kernel"], "bound": "tensor" if tensor_bound else "hbm", "achieved": round(ach, 1),
-            "peak": peak, "unit": unit, "frac": round(ach / peak, 4), "traffic": None,
+            "peak": peak, "unit": unit, "frac": round(ach / peak, 4), "traffic": traffic,
+            "algorithmic_per_launch": round((f["flops"] if tensor_bound else f["bytes"]) / f["launches"], 1),
             "avg_launch_ms": round(f["ms"] / f["launches"], 4), "peak_source": pk["source"],
             "share_of_step": top["share"]}
     return {"roofline": roof, "kernels": table, "profiled_step_ms": round(total, 2)}
@@ -382,12 +394,15 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="large-v2", choices=list(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--beam", type=int, default=0, help="beam size (0 = greedy, the headline configuration)")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=25.0)
     ap.add_argument("--single-step", action="store_true",
                     help="build the model, run ONE device-resident step and exit (the command profiled under ncu)")
     args = ap.parse_args()
+    global BEAM
+    BEAM = args.beam
     if args.impl == "reference":
         run_reference(args)
     else:

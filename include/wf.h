@@ -134,6 +134,13 @@ int wf_attention_decode(int dtype, const void* q, long long ldq, const void* kc,
                         long long kv_batch_stride, long long kv_head_stride, void* o, long long ldo, int R, int G,
                         int H, const int* len_ptr, int len_add, int len_const, void* workspace,
                         long long workspace_bytes, wf_stream_t stream);
+/* Same for one query per cache entry (G = 1) with a per-position indirection: key j of entry r is read from entry
+ * row_table[r * table_ld + j].  Beam search re-orders hypotheses (BeamSearchDecoder + rearrange_kv_cache,
+ * decoding.py:173-180, 366-368) by rewriting this table instead of moving K/V rows. */
+int wf_attention_decode_paged(int dtype, const void* q, long long ldq, const void* kc, const void* vc, long long ld_kv,
+                              long long kv_batch_stride, long long kv_head_stride, void* o, long long ldo, int R,
+                              int H, const int* len_ptr, int len_add, int len_const, const int* row_table,
+                              int table_ld, void* workspace, long long workspace_bytes, wf_stream_t stream);
 
 /* ---- sampling: whisper/decoding.py:427-442 (SuppressBlank/SuppressTokens), :276-302 (GreedyDecoder),
  *      :697-701 (no_speech_prob), loop bookkeeping of :688-718 ------------------------------------ */

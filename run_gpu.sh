@@ -1,11 +1,15 @@
 #!/bin/bash
-LOG=gpurun_out/run38.log; : > $LOG
-for v in "WF_NO_ENC_LN_FUSION=1" "WF_NO_ENC_LN_FUSION=0" "WF_GEMM_PAIR=0"; do
-echo "== $v" >> $LOG
-env $v WF_TIMING=1 timeout 900 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-profile > gpurun_out/tmp.json 2>> $LOG
+LOG=gpurun_out/run41.log; : > $LOG
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -8 >> $LOG
+for a in "--workload medium --beam 5 --steps 2" ""; do
+echo "== $a" >> $LOG
+WF_TIMING=1 timeout 900 python bench.py $a --no-cpu-baseline --no-profile > gpurun_out/tmp.json 2>> $LOG
 python - >> $LOG <<'P'
 import json
-d=json.loads(open('gpurun_out/tmp.json').read().strip().splitlines()[-1])
-print(round(d['value']), round(d['ms_per_step']), d.get('phases_ms'), round(d['e2e']['value']))
+try:
+    d=json.loads(open('gpurun_out/tmp.json').read().strip().splitlines()[-1])
+    print(round(d['value']), round(d['ms_per_step']), d.get('phases_ms'), round(d['e2e']['value']), d['config']['workload'])
+except Exception as e:
+    print('FAILED', e)
 P
 done

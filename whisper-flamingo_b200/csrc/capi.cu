@@ -150,7 +150,15 @@ int wf_attention_decode(int dtype, const void* q, long long ldq, const void* kc,
                         long long workspace_bytes, wf_stream_t stream) {
   WF_REQUIRE(q && kc && vc && o, "wf_attention_decode: null buffer");
   return attention_decode(dtype, q, ldq, kc, vc, ld_kv, kv_batch_stride, kv_head_stride, o, ldo, R, G, H, len_ptr,
-                          len_add, len_const, workspace, workspace_bytes, S(stream));
+                          len_add, len_const, workspace, workspace_bytes, nullptr, 0, S(stream));
+}
+int wf_attention_decode_paged(int dtype, const void* q, long long ldq, const void* kc, const void* vc, long long ld_kv,
+                              long long kv_batch_stride, long long kv_head_stride, void* o, long long ldo, int R,
+                              int H, const int* len_ptr, int len_add, int len_const, const int* row_table,
+                              int table_ld, void* workspace, long long workspace_bytes, wf_stream_t stream) {
+  WF_REQUIRE(q && kc && vc && o && row_table, "wf_attention_decode_paged: null buffer");
+  return attention_decode(dtype, q, ldq, kc, vc, ld_kv, kv_batch_stride, kv_head_stride, o, ldo, R, 1, H, len_ptr,
+                          len_add, len_const, workspace, workspace_bytes, row_table, table_ld, S(stream));
 }
 
 int wf_sample_greedy(const wf_sample_t* a, wf_stream_t stream) {

@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(DT)
 attn_decode_kernel(const T* __restrict__ q, long long ldq, const T* __restrict__ kc, const T* __restrict__ vc,
                    long long ld_kv, long long kv_batch_stride, long long kv_head_stride, T* __restrict__ o,
                    long long ldo, int H, const int* __restrict__ len_ptr, int len_add, int len_const, int n_splits,
-                   float* __restrict__ partials) {
+                   float* __restrict__ partials, const int* __restrict__ row_table, int table_ld) {
   __shared__ float sq[NQ][HD];
   __shared__ float sp[NQ][DT];
   __shared__ float sred[NQ][DT / 32];
@@ -57,8 +57,12 @@ attn_decode_kernel(const T* __restrict__ q, long long ldq, const T* __restrict__
   }
   __syncthreads();
 
-  const T* kbase = kc + kvb * kv_batch_stride + h * kv_head_stride;
-  const T* vbase = vc + kvb * kv_batch_stride + h * kv_head_stride;
+  // row_table (beam search): key j of cache entry kvb physically lives in entry row_table[kvb * table_ld + j] - the
+  // hypotheses are re-ordered by rewriting this small table instead of moving K/V rows (decoding.py:173-180)
+  const int* tbl = row_table ? row_table + static_cast<long long>(kvb) * table_ld : nullptr;
+  const T* kbase = kc + h * kv_head_stride;
+  const T* vbase = vc + h * kv_head_stride;
+  const long long own = static_cast<long long>(kvb) * kv_batch_stride;
   const int dgrp = lane & 7, ksub = lane >> 3;
 
   float m_run[NQ], l_run[NQ], acc[NQ][8];
@@ -77,7 +81,7 @@ attn_decode_kernel(const T* __restrict__ q, long long ldq, const T* __restrict__
 #pragma unroll
     for (int i = 0; i < NQ; ++i) s[i] = 0.f;
     if (key < len) {
-      const T* kr = kbase + key * ld_kv;
+      const T* kr = kbase + (tbl ? static_cast<long long>(__ldg(tbl + key)) * kv_batch_stride : own) + key * ld_kv;
       float kv[8][8];
 #pragma unroll
       for (int c = 0; c < 8; ++c) ld8(kr + c * 8, kv[c]);
@@ -121,7 +125,7 @@ attn_decode_kernel(const T* __restrict__ q, long long ldq, const T* __restrict__
       const int vkey = tile * DT + kt;
       if (vkey < len) {
         float vv[8];
-        ld8(vbase + vkey * ld_kv + dgrp * 8, vv);
+        ld8(vbase + (tbl ? static_cast<long long>(__ldg(tbl + vkey)) * kv_batch_stride : own) + vkey * ld_kv + dgrp * 8, vv);
 #pragma unroll
         for (int i = 0; i < NQ; ++i) {
           const float p = sp[i][kt];
@@ -565,7 +569,8 @@ template <typename T, int NQ>
 static int launch_decode_attn(const T* q, long long ldq, const T* kc, const T* vc, long long ld_kv,
                               long long kv_batch_stride, long long kv_head_stride, T* o, long long ldo, int R, int H,
                               const int* len_ptr,
-                              int len_add, int len_max, float* ws, long long ws_bytes, cudaStream_t stream) {
+                              int len_add, int len_max, float* ws, long long ws_bytes, const int* row_table,
+                              int table_ld, cudaStream_t stream) {
   const int kvb = R / NQ;
   const int blocks = kvb * H;
   const int max_tiles = (len_max + DT - 1) / DT;
@@ -586,7 +591,7 @@ static int launch_decode_attn(const T* q, long long ldq, const T* kc, const T* v
     WF_REQUIRE(ws && ws_bytes >= static_cast<long long>(R) * H * n_splits * PART * (long long)sizeof(float),
                "attention_decode: workspace too small (need %lld bytes)",
                static_cast<long long>(R) * H * n_splits * PART * (long long)sizeof(float));
-  if constexpr (sizeof(T) == 2) {
+  if constexpr (sizeof(T) == 2) if (!row_table) {
     // head-major cache + long key range: bulk-copy pipelined kernel, one CTA streams a whole (audio, head) item
     // (measured: 5.8 TB/s unsplit vs 4.0 TB/s when the item is cut into 12 one-tile CTAs - the pipeline needs depth)
     static int persist = -1;
@@ -656,7 +661,8 @@ static int launch_decode_attn(const T* q, long long ldq, const T* kc, const T* v
   }
   dim3 grid(blocks, n_splits);
   WF_CHECK_CUDA(launch_pdl(2, attn_decode_kernel<T, NQ>, grid, dim3(DT), 0, stream, q, ldq, kc, vc, ld_kv,
-                           kv_batch_stride, kv_head_stride, o, ldo, H, len_ptr, len_add, len_max, n_splits, ws));
+                           kv_batch_stride, kv_head_stride, o, ldo, H, len_ptr, len_add, len_max, n_splits, ws,
+                           row_table, table_ld));
   count_launch();
   if (n_splits > 1) {
     WF_CHECK_CUDA(launch_pdl(2, attn_decode_combine_kernel<T>, dim3(R * H), dim3(HD), 0, stream, (const float*)ws, o, ldo,
@@ -671,12 +677,12 @@ static int dispatch_decode_attn(const void* q, long long ldq, const void* kc, co
                                 long long kv_batch_stride, long long kv_head_stride, void* o, long long ldo, int R,
                                 int G, int H,
                                 const int* len_ptr, int len_add, int len_max, void* ws, long long ws_bytes,
-                                cudaStream_t stream) {
+                                const int* row_table, int table_ld, cudaStream_t stream) {
 #define WF_DA(NQ)                                                                                              \
   case NQ:                                                                                                     \
     return launch_decode_attn<T, NQ>((const T*)q, ldq, (const T*)kc, (const T*)vc, ld_kv, kv_batch_stride,     \
                                      kv_head_stride, (T*)o, ldo, R, H, len_ptr, len_add, len_max, (float*)ws,  \
-                                     ws_bytes, stream)
+                                     ws_bytes, row_table, table_ld, stream)
   switch (G) {
     WF_DA(1); WF_DA(2); WF_DA(3); WF_DA(4); WF_DA(5); WF_DA(6); WF_DA(8);
     default:
@@ -689,7 +695,8 @@ static int dispatch_decode_attn(const void* q, long long ldq, const void* kc, co
 int attention_decode(int dtype, const void* q, long long ldq, const void* kc, const void* vc, long long ld_kv,
                      long long kv_batch_stride, long long kv_head_stride, void* o, long long ldo, int R, int G, int H,
                      const int* len_ptr, int len_add, int len_const, void* workspace, long long workspace_bytes,
-                     cudaStream_t stream) {
+                     const int* row_table, int table_ld, cudaStream_t stream) {
+  WF_REQUIRE(!row_table || (G == 1 && table_ld >= len_const), "attention_decode: a row table needs G == 1 and table_ld >= max length");
   WF_REQUIRE(R > 0 && G > 0 && H > 0 && R % G == 0, "attention_decode: bad shape R=%d G=%d H=%d", R, G, H);
   WF_REQUIRE(len_const > 0, "attention_decode: len (or max len) must be positive");
   const int al = dtype == WF_BF16 ? 8 : 4;
@@ -699,10 +706,11 @@ int attention_decode(int dtype, const void* q, long long ldq, const void* kc, co
              "attention_decode: K/V base must be 16-byte aligned");
   if (dtype == WF_F32)
     return dispatch_decode_attn<float>(q, ldq, kc, vc, ld_kv, kv_batch_stride, kv_head_stride, o, ldo, R, G, H,
-                                       len_ptr, len_add, len_const, workspace, workspace_bytes, stream);
+                                       len_ptr, len_add, len_const, workspace, workspace_bytes, row_table, table_ld, stream);
   if (dtype == WF_BF16)
     return dispatch_decode_attn<__nv_bfloat16>(q, ldq, kc, vc, ld_kv, kv_batch_stride, kv_head_stride, o, ldo, R, G,
-                                               H, len_ptr, len_add, len_const, workspace, workspace_bytes, stream);
+                                               H, len_ptr, len_add, len_const, workspace, workspace_bytes, row_table,
+                                               table_ld, stream);
   WF_REQUIRE(false, "attention_decode: bad dtype %d", dtype);
 }
 
@@ -819,9 +827,11 @@ __device__ __forceinline__ float uniform01(unsigned long long seed, int row, int
 // state: [0]=t (position of the token fed this step) [1]=n_init [2]=all_done [3]=#rows at EOT this step [4]=sot_index
 //        [5],[6]=low/high word of a per-call RNG seed (temperature > 0), XORed with SampleArgs.seed: the seed changes
 //        from call to call without re-capturing the CUDA graph the launch is part of
-__global__ void __launch_bounds__(256) sample_greedy_kernel(SampleArgs a) {
-  __shared__ ArgMax sh_am[8];
-  __shared__ float sh_f[8];
+// One CTA of 1024 threads per row: the two passes over the 51865 fp32 logits of a row are latency-bound, so the row is
+// spread over 32 warps (256 threads measured 110 us per step at R = 128, i.e. 0.5 TB/s).
+__global__ void __launch_bounds__(1024) sample_greedy_kernel(SampleArgs a) {
+  __shared__ ArgMax sh_am[32];
+  __shared__ float sh_f[32];
   pdl_trigger();
   pdl_wait();
   const int r = blockIdx.x;
@@ -885,7 +895,7 @@ __global__ void __launch_bounds__(256) sample_greedy_kernel(SampleArgs a) {
 
 int sample_greedy(const SampleArgs& a, cudaStream_t stream) {
   WF_REQUIRE(a.R > 0 && a.V > 0 && a.logits && a.tokens && a.state && a.suppress, "sample_greedy: bad arguments");
-  WF_CHECK_CUDA(launch_pdl(3, sample_greedy_kernel, dim3(a.R), dim3(256), 0, stream, a));
+  WF_CHECK_CUDA(launch_pdl(3, sample_greedy_kernel, dim3(a.R), dim3(1024), 0, stream, a));
   count_launch();
   return WF_OK;
 }

@@ -70,8 +70,8 @@ int attention_full_tc(const void* q, long long ldq, const void* k, long long ldk
 // decode.cu
 int attention_decode(int dtype, const void* q, long long ldq, const void* kc, const void* vc, long long ld_kv,
                      long long kv_batch_stride, long long kv_head_stride, void* o, long long ldo, int R, int G, int H,
-                     const int* len_ptr, int len_add, int len_const, void* workspace, long long workspace_bytes,
-                     cudaStream_t stream);
+                     const int* len_ptr, int len_add, int len_const, void* workspace, long long workspace_bytes, const int* row_table,
+                     int table_ld, cudaStream_t stream);
 long long attention_decode_workspace_bytes(int R, int H);
 
 struct SampleArgs {

@@ -531,7 +531,13 @@ class DecodeSession:
         self.no_speech_prob = torch.full((R,), float("nan"), dtype=torch.float32, device=dev)
         self.suppress = torch.zeros(p.n_vocab, dtype=torch.uint8, device=dev)
         self.suppress_first = torch.zeros(p.n_vocab, dtype=torch.uint8, device=dev)
+        # beam search: per-position indirection of the self-attention cache (key j of row r lives in physical row
+        # row_table[r, j]); re-ordering hypotheses rewrites this table instead of moving K/V rows
+        self.row_table = (torch.arange(R, dtype=torch.int32, device=dev)[:, None].repeat(1, t_cap).contiguous()
+                          if G > 1 else None)
         self.use_graph = use_graph and os.environ.get("WF_NO_GRAPH", "0") != "1"
+        self._fwd_graph: Optional[torch.cuda.CUDAGraph] = None
+        self._fwd_graph_kernels = 0
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._graph_kernels = 0
         self._graph_key = None
@@ -597,7 +603,8 @@ class DecodeSession:
             kv = self.self_kv[l]  # [R, 2H, T_cap, 64]; row r, position state[0]: offset state[0] * 64 inside each head
             nv.linear(xn, bp.attn.kv_w, kv.view(-1, 64), bias=bp.attn.kv_b, head_major=(2 * H, Tc, 1),
                       c_off_ptr=st, c_off_mul=64, ws=gws)
-            nv.attention_decode(q, kv, kv[:, H:], 64, 2 * H * Tc * 64, Tc * 64, att, 1, H, st, 1, Tc, self.ws)
+            nv.attention_decode(q, kv, kv[:, H:], 64, 2 * H * Tc * 64, Tc * 64, att, 1, H, st, 1, Tc, self.ws,
+                                row_table=self.row_table)
             nv.linear(att, bp.attn.o_w, x, bias=bp.attn.o_b, residual=x, ws=gws)
             # cross-attention to the encoder output (K/V cached per audio, shared by its G beams)
             nv.layernorm(x, bp.cross_ln.w, bp.cross_ln.b, xn)
@@ -642,7 +649,8 @@ class DecodeSession:
             kv = self.self_kv[l]
             lnlin(bf.self_qkv, q, out2=kv.view(-1, 64), split_n=p.d, head_major=(2 * H, Tc, 1), c_off_ptr=st,
                   c_off_mul=64)
-            nv.attention_decode(q, kv, kv[:, H:], 64, 2 * H * Tc * 64, Tc * 64, att, 1, H, st, 1, Tc, self.ws)
+            nv.attention_decode(q, kv, kv[:, H:], 64, 2 * H * Tc * 64, Tc * 64, att, 1, H, st, 1, Tc, self.ws,
+                                row_table=self.row_table)
             nv.linear(att, bp.attn.o_w, x, bias=bp.attn.o_b, residual=x)
             lnlin(bf.cross_q, q)
             ckv = self.cross_kv[l]
@@ -668,6 +676,7 @@ class DecodeSession:
         self.state.copy_(torch.tensor([0, n_init, 0, 0, sot_index, lo, hi, 0], dtype=torch.int32))
         self.sum_logprobs.zero_()
         self.no_speech_prob.fill_(float("nan"))
+        self.reset_row_table()
         # the masks live in session-owned buffers so that a captured graph stays valid across decode() calls
         self.suppress.copy_(suppress)
         if suppress_first is not None:
@@ -744,22 +753,40 @@ class DecodeSession:
 
     # -- beam search support (host-driven; see decoding.py) ---------------------------------------------
     def forward_at(self, pos: int):
-        """Eager single-position pass used by the beam-search driver: sets state[0] = pos first."""
+        """Single-position pass used by the beam-search driver: sets state[0] = pos, then replays the captured
+        forward graph (or launches the kernels eagerly when graphs are off)."""
         self.state[0] = pos
-        self._forward_token()
+        if not self.use_graph:
+            self._forward_token()
+            return
+        if self._fwd_graph is None:
+            side = torch.cuda.Stream(device=self.dev)
+            side.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.stream(side):
+                self._forward_token()  # warm-up outside capture; it recomputes what the replay computes again
+            torch.cuda.current_stream(self.dev).wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            before = nv.kernel_launch_count()
+            with torch.cuda.graph(g):
+                self._forward_token()
+            self._fwd_graph_kernels = nv.kernel_launch_count() - before
+            self._fwd_graph = g
+        self._fwd_graph.replay()
+        nv.note_graph_replay(self._fwd_graph_kernels)
 
     def reorder_self_kv(self, src_index: Tensor, used_positions: int):
-        d = self.p.d
-        elt = self.self_kv[0].element_size()
-        row_bytes = self.T_cap * 2 * d * elt
-        used = row_bytes  # head-major rows: the used positions are a prefix of every head segment, copy the row
-        # gather through a scratch layer and copy back: the cache buffers keep their addresses (captured graphs
-        # and cached sessions stay valid)
-        if getattr(self, "_kv_scratch", None) is None:
-            self._kv_scratch = torch.empty_like(self.self_kv[0])
-        for kv in self.self_kv:
-            nv.kv_gather_rows(kv, self._kv_scratch, src_index, self.R, row_bytes, used)
-            kv.copy_(self._kv_scratch)
+        """Hypothesis r continues hypothesis src_index[r] (reference rearrange_kv_cache, decoding.py:173-180): its
+        first `used_positions` cache positions are read where the parent read them; later positions are its own."""
+        tbl = self.row_table
+        new = tbl.index_select(0, src_index.long())
+        if used_positions < tbl.shape[1]:
+            new[:, used_positions:] = torch.arange(self.R, dtype=torch.int32, device=self.dev)[:, None]
+        tbl.copy_(new)
+
+    def reset_row_table(self):
+        if self.row_table is not None:
+            self.row_table.copy_(torch.arange(self.R, dtype=torch.int32, device=self.dev)[:, None]
+                                 .expand(-1, self.row_table.shape[1]))
 
 
 class SplitSession:

@@ -76,6 +76,10 @@ _SIGNATURES = {
     "wf_attention_decode": (C.c_int, [C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_longlong,
                                       C.c_longlong, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int,
                                       C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p]),
+    "wf_attention_decode_paged": (C.c_int, [C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_longlong,
+                                            C.c_longlong, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_int,
+                                            C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                            C.c_longlong, C.c_void_p]),
     "wf_sample_greedy": (C.c_int, [C.POINTER(_Sample), C.c_void_p]),
     "wf_step_advance": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "wf_topk_logprobs": (C.c_int, [C.POINTER(_Topk), C.c_void_p]),
@@ -320,12 +324,22 @@ def attention_decode_workspace_bytes(r: int, h: int) -> int:
 
 def attention_decode(q: torch.Tensor, kc: torch.Tensor, vc: torch.Tensor, ld_kv: int, kv_batch_stride: int,
                      kv_head_stride: int, out: torch.Tensor, g: int, h: int, len_ptr: Optional[torch.Tensor],
-                     len_add: int, len_const: int, ws: Optional[torch.Tensor]) -> torch.Tensor:
+                     len_add: int, len_const: int, ws: Optional[torch.Tensor],
+                     row_table: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """row_table (int32 [R, >= max length], g == 1): key j of cache entry r is read from entry row_table[r, j]."""
     r = q.shape[0]
     # algorithmic bytes: K and V rows of every (audio, head) once; dynamic lengths are reported at their bound
     dyn = len_ptr is not None  # growing self-attention cache: charged at half its bound (average over a decode)
     with _Prof("attention_decode_self" if dyn else "attention_decode",
                bytes=2 * (r // g) * h * 64 * (len_const // 2 if dyn else len_const) * q.element_size()):
+        if row_table is not None:
+            assert g == 1 and row_table.dtype == torch.int32 and row_table.shape[0] == r
+            _check(load().wf_attention_decode_paged(
+                dtype_id(q.dtype), q.data_ptr(), _row_stride(q), kc.data_ptr(), vc.data_ptr(), ld_kv, kv_batch_stride,
+                kv_head_stride, out.data_ptr(), _row_stride(out), r, h, _ptr(len_ptr), len_add, len_const,
+                row_table.data_ptr(), _row_stride(row_table), _ptr(ws),
+                0 if ws is None else ws.numel() * ws.element_size(), _stream()))
+            return out
         _check(load().wf_attention_decode(dtype_id(q.dtype), q.data_ptr(), _row_stride(q), kc.data_ptr(),
                                           vc.data_ptr(), ld_kv, kv_batch_stride, kv_head_stride, out.data_ptr(),
                                           _row_stride(out), r, g, h, _ptr(len_ptr), len_add, len_const, _ptr(ws),

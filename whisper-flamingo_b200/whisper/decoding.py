@@ -136,25 +136,35 @@ class _BeamBook:
         self.max_candidates = round(beam_size * (patience or 1.0))
         assert self.max_candidates > 0, f"Invalid beam size ({beam_size}) or patience ({patience})"
         self.finished: List[Dict[tuple, float]] = [{} for _ in range(n_audio)]
+        self._next_id = n_audio  # hypothesis ids; the G prompt rows of audio a start with id a
 
-    def update(self, rows: List[List[int]], sum_lp: np.ndarray, top_lp: np.ndarray, top_id: np.ndarray):
-        next_rows, source, new_sum = [], [], []
+    def update(self, rows: List[List[int]], row_ids: List[int], sum_lp: np.ndarray, top_lp: np.ndarray,
+               top_id: np.ndarray):
+        """One step of BeamSearchDecoder.update (reference :337-383).  The reference keys its candidate dictionaries by
+        the whole token tuple, which makes identical hypotheses (all beams share the prompt at the first step) collapse
+        into one entry; here a hypothesis is identified by an integer id (equal ids <=> equal token sequences), so a
+        candidate key is (parent id, token) - same collapsing, same iteration order, no O(length) tuples."""
+        next_rows, next_ids, source, new_sum = [], [], [], []
+        cand_score = sum_lp.astype(np.float32)[:, None] + top_lp.astype(np.float32)  # fp32 add, as the reference
+        k = top_id.shape[1]
         for a in range(len(self.finished)):
-            scores, sources, done = {}, {}, {}
+            cand: Dict[tuple, tuple] = {}
             for j in range(self.beam):
                 r = a * self.beam + j
-                for lp, tok in zip(top_lp[r], top_id[r]):
-                    seq = tuple(rows[r] + [int(tok)])
-                    scores[seq] = float(np.float32(sum_lp[r]) + np.float32(lp))
-                    sources[seq] = r
-            kept = 0
-            for seq in sorted(scores, key=scores.get, reverse=True):
-                if seq[-1] == self.eot:
-                    done[seq] = scores[seq]
+                rid, sc, ids = row_ids[r], cand_score[r], top_id[r]
+                for c in range(k):
+                    cand[(rid, int(ids[c]))] = (float(sc[c]), r)  # a later identical hypothesis overwrites (as :349-351)
+            kept, done = 0, {}
+            for key in sorted(cand, key=lambda q: cand[q][0], reverse=True):
+                score, r = cand[key]
+                if key[1] == self.eot:
+                    done[tuple(rows[r] + [self.eot])] = score
                 else:
-                    new_sum.append(scores[seq])
-                    next_rows.append(list(seq))
-                    source.append(sources[seq])
+                    new_sum.append(score)
+                    next_rows.append(rows[r] + [key[1]])
+                    self._next_id += 1
+                    next_ids.append(self._next_id)
+                    source.append(r)
                     kept += 1
                     if kept == self.beam:
                         break
@@ -164,7 +174,7 @@ class _BeamBook:
                     break
                 prev[seq] = done[seq]
         completed = all(len(f) >= self.max_candidates for f in self.finished)
-        return next_rows, source, np.asarray(new_sum, dtype=np.float32), completed
+        return next_rows, next_ids, source, np.asarray(new_sum, dtype=np.float32), completed
 
     def finalize(self, rows: List[List[int]], sum_lp: np.ndarray):
         for a, seqs in enumerate(self.finished):
@@ -361,6 +371,7 @@ class DecodingTask:
         R = session.R
         book = _BeamBook(G, tk.eot, self.options.patience, session.B)
         rows = [list(init_rows[r // G]) for r in range(R)]
+        row_ids = [r // G for r in range(R)]
         sum_lp = np.zeros(R, dtype=np.float32)
         suppress, suppress_first, eot, no_speech, ts = session._sampler[:5]
         for _ in range(n_init - 1):  # feed the prompt; the sampler only records no_speech_prob here
@@ -368,9 +379,10 @@ class DecodingTask:
         k = G + 1
         vals = torch.empty((R, k), dtype=torch.float32, device=session.dev)
         idx = torch.empty((R, k), dtype=torch.int32, device=session.dev)
+        identity = list(range(R))
         pos = n_init - 1
         for i in range(n_sample):
-            session.forward_at(pos)
+            session.forward_at(pos)  # one replay of the captured decoder pass
             if pos == self.sot_index and no_speech >= 0:
                 # SOT is the last prompt token (English-only vocabularies): take no_speech_prob from this pass.
                 # The sampler's other outputs (tokens[:, pos + 1], device sum_logprobs) are overwritten / unused here.
@@ -378,12 +390,16 @@ class DecodingTask:
                                  session.state, session.sum_logprobs, session.no_speech_prob, eot, no_speech, ts)
             nv.topk_logprobs(session.logits, session.p.n_vocab, suppress, suppress_first, session.tokens,
                              n_init, len(rows[0]), eot, ts, k, vals, idx)
-            rows, source, sum_lp, completed = book.update(rows, sum_lp, vals.cpu().numpy(), idx.cpu().numpy())
+            rows, row_ids, source, sum_lp, completed = book.update(rows, row_ids, sum_lp, vals.cpu().numpy(),
+                                                                  idx.cpu().numpy())
             pos += 1
-            cur = torch.tensor(rows, dtype=torch.int32, device=session.dev)
-            session.tokens[:, : cur.shape[1]] = cur
-            if source != list(range(R)):
-                session.reorder_self_kv(torch.tensor(source, dtype=torch.int32, device=session.dev), pos)
+            # token history on the device: row r continues row source[r] and appends its new token
+            src_dev = torch.tensor(source, dtype=torch.int64, device=session.dev)
+            L = len(rows[0])
+            if source != identity:
+                session.tokens[:, : L - 1] = session.tokens[:, : L - 1].index_select(0, src_dev)
+                session.reorder_self_kv(src_dev, pos)
+            session.tokens[:, L - 1] = torch.tensor([row[-1] for row in rows], dtype=torch.int32, device=session.dev)
             if completed or len(rows[0]) > self.n_ctx:
                 break
         cand, cand_lp = book.finalize(rows, sum_lp)
