@@ -1,7 +1,8 @@
 #!/bin/bash
-LOG=gpurun_out/run41.log; : > $LOG
+LOG=gpurun_out/run43.log; : > $LOG
 timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -8 >> $LOG
-for a in "--workload medium --beam 5 --steps 2" ""; do
+timeout 300 python tools/microbench.py attn2 2>&1 | grep -v Warning | tail -2 >> $LOG
+for a in "--workload medium --beam 5 --steps 2"; do
 echo "== $a" >> $LOG
 WF_TIMING=1 timeout 900 python bench.py $a --no-cpu-baseline --no-profile > gpurun_out/tmp.json 2>> $LOG
 python - >> $LOG <<'P'

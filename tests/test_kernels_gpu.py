@@ -404,7 +404,9 @@ def test_attention_full_vs_torch(nv, dtype, tol, B, Tq, Tk, H, causal):
                                           (4, 1, 6, 37, True), (1, 1, 6, 300, True), (2, 3, 6, 100, False),
                                           # >= 2 items per SM: the persistent kernel (head-major bf16 only)
                                           (32, 1, 12, 750, False), (20, 5, 16, 1500, False), (64, 1, 6, 300, False),
-                                          (50, 2, 6, 257, False)])
+                                          (50, 2, 6, 257, False),
+                                          # beams sharing a cache: tensor-core multi-query kernel (head-major bf16)
+                                          (4, 8, 6, 700, False), (6, 4, 12, 1500, False), (3, 6, 20, 128, False)])
 @pytest.mark.parametrize("head_major", [False, True])
 def test_attention_decode_vs_torch(nv, dtype, tol, B, G, H, Tk, dyn, head_major):
     d, R, cap = H * 64, B * G, 448

@@ -364,6 +364,172 @@ attn_decode_combine_kernel(const float* __restrict__ partials, T* __restrict__ o
   o[row * ldo + h * HD + d] = from_f32<T>(num / den);
 }
 
+// ---- multi-query variant (beam search / best_of: the G hypotheses of a clip read the same cross / x-attention K,V).
+// The thread-per-key kernels above spend G x 128 FMAs per key and drop to 1.9 TB/s at G = 5; here the G <= 8 query rows
+// are the (zero-padded) 16-row A operand of warp-level tensor-core MMAs: S = Q K^T and O += P V as mma.sync m16n8k16,
+// K/V tiles of 128 keys staged by TMA with the 128-byte swizzle (conflict-free ldmatrix), two stages = 64 KB per CTA,
+// three CTAs per SM.  Each warp owns 32 keys of a tile with its own online softmax; the four partial results are
+// merged once per (clip, head).
+static constexpr int MQ_SMEM_BYTES = 2 * 2 * HM_TILE_BYTES + 2048 + 1024;  // 2 stages x (K + V) + Q tile + alignment
+
+__device__ __forceinline__ const __nv_bfloat16* mq_sw(const uint8_t* tile, int row, int chunk) {
+  return reinterpret_cast<const __nv_bfloat16*>(tile + row * 128 + ((chunk ^ (row & 7)) << 4));
+}
+
+template <int NQ>
+__global__ void __launch_bounds__(DT, 3)
+attn_decode_mq_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
+                      const __nv_bfloat16* __restrict__ q, long long ldq, int rows_per_batch, int rows_per_head,
+                      __nv_bfloat16* __restrict__ o, long long ldo, int H, int len) {
+  static_assert(NQ >= 1 && NQ <= 8, "queries per clip must fit the 8 real rows of the padded 16-row MMA operand");
+  extern __shared__ uint8_t mq_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(mq_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = base + 2 * 2 * HM_TILE_BYTES;  // [16][64] bf16, swizzled like the K/V tiles
+  __shared__ __align__(8) uint64_t full_bar[2];
+  __shared__ float comb_ml[4][8][2];
+  float* comb_o = reinterpret_cast<float*>(base);  // [4 warps][8 rows][64] fp32, aliases stage 0 after the main loop
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_trigger();
+  const int kvb = blockIdx.x / H, h = blockIdx.x % H;
+  const int n_tiles = (len + HM_KEYS - 1) / HM_KEYS;
+  const int row0 = kvb * rows_per_batch + h * rows_per_head;  // first K (and V) row of this (clip, head) in the maps
+
+  auto issue = [&](int tile, int stage) {
+    uint8_t* dst = base + stage * 2 * HM_TILE_BYTES;
+    mbar_arrive_expect_tx(&full_bar[stage], 2 * HM_TILE_BYTES);
+    tma_load_2d(dst, &map_k, &full_bar[stage], 0, row0 + tile * HM_KEYS);
+    tma_load_2d(dst + HM_TILE_BYTES, &map_v, &full_bar[stage], 0, row0 + tile * HM_KEYS);
+  };
+  if (tid == 0) {
+    tma_prefetch_desc(&map_k);
+    tma_prefetch_desc(&map_v);
+    mbar_init(&full_bar[0], 1);
+    mbar_init(&full_bar[1], 1);
+    mbar_fence_init();
+    for (int s2 = 0; s2 < 2; ++s2)
+      if (s2 < n_tiles) issue(s2, s2);  // the cache is static: requested before the dependency wait
+  }
+  pdl_wait();  // the queries come from the previous kernel
+  {
+    const int row = tid >> 3, chunk = tid & 7;  // 16 rows x 8 chunks of 16 B
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (row < NQ) v = *reinterpret_cast<const uint4*>(q + (static_cast<long long>(kvb) * NQ + row) * ldq + h * HD + chunk * 8);
+    *reinterpret_cast<uint4*>(sQ + row * 128 + ((chunk ^ (row & 7)) << 4)) = v;
+  }
+  __syncthreads();
+  uint32_t qa[4][4];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) ldmatrix_x4(qa[ks], mq_sw(sQ, lane & 15, ks * 2 + (lane >> 4)));
+
+  constexpr float sl2 = 0.125f * 1.44269504088896340736f;  // 64^-0.5 * log2(e)
+  float row_m = -INFINITY, row_l = 0.f;                    // this thread's query row = lane / 4 (rows 8..15 are padding)
+  float oacc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) oacc[i][j] = 0.f;
+
+  for (int t = 0; t < n_tiles; ++t) {
+    const int stage = t & 1;
+    const uint8_t* ks_tile = base + stage * 2 * HM_TILE_BYTES;
+    const uint8_t* vs_tile = ks_tile + HM_TILE_BYTES;
+    mbar_wait(&full_bar[stage], (t >> 1) & 1);
+    // ---- S = Q K^T for this warp's 32 keys: 4 n-tiles of 8 keys
+    float s[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+      for (int np = 0; np < 2; ++np) {
+        uint32_t kb[4];
+        const int row = warp * 32 + np * 16 + (lane & 7) + ((lane >> 4) << 3);
+        ldmatrix_x4(kb, mq_sw(ks_tile, row, ks * 2 + ((lane >> 3) & 1)));
+        mma_bf16_16816(s[np * 2], qa[ks], kb[0], kb[1]);
+        mma_bf16_16816(s[np * 2 + 1], qa[ks], kb[2], kb[3]);
+      }
+    }
+    const int kbase = t * HM_KEYS + warp * 32;
+    if (kbase + 32 > len) {  // partial last tile: the rows past the end belong to the next head (or are zero fill)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          if (kbase + nt * 8 + (lane & 3) * 2 + j >= len) s[nt][j] = -INFINITY;
+    }
+    float mx = row_m;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) mx = fmaxf(mx, fmaxf(s[nt][0], s[nt][1]));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    const float m_safe = (mx == -INFINITY) ? 0.f : mx;  // every key of this warp masked so far
+    const float corr = ex2_approx((row_m - m_safe) * sl2);  // row_m = -inf -> 0
+    const float msc = m_safe * sl2;
+    row_m = mx;
+    uint32_t pa[2][4];
+    float psum = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const float p0 = ex2_approx(fmaf(s[nt][0], sl2, -msc));
+      const float p1 = ex2_approx(fmaf(s[nt][1], sl2, -msc));
+      psum += p0 + p1;
+      pa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(p0, p1);
+      pa[nt >> 1][(nt & 1) * 2 + 1] = 0u;  // padding rows 8..15
+    }
+    row_l = row_l * corr + psum;
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) {
+      oacc[dt][0] *= corr;
+      oacc[dt][1] *= corr;
+    }
+    // ---- O += P V : k = this warp's 32 keys (2 steps of 16), n = head_dim (8 tiles of 8)
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+      for (int dp = 0; dp < 4; ++dp) {
+        uint32_t vb[4];
+        const int row = warp * 32 + ks * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
+        ldmatrix_x4_trans(vb, mq_sw(vs_tile, row, dp * 2 + (lane >> 4)));
+        mma_bf16_16816(oacc[dp * 2], pa[ks], vb[0], vb[1]);
+        mma_bf16_16816(oacc[dp * 2 + 1], pa[ks], vb[2], vb[3]);
+      }
+    }
+    __syncthreads();  // every warp is done with this stage
+    if (tid == 0 && t + 2 < n_tiles) issue(t + 2, stage);
+  }
+
+  // ---- merge the four warps' partial (m, l, O) and write the NQ output rows
+  row_l += __shfl_xor_sync(0xffffffffu, row_l, 1);
+  row_l += __shfl_xor_sync(0xffffffffu, row_l, 2);
+  const int r = lane >> 2;
+  if ((lane & 3) == 0) {
+    comb_ml[warp][r][0] = row_m;
+    comb_ml[warp][r][1] = row_l;
+  }
+#pragma unroll
+  for (int dt = 0; dt < 8; ++dt)
+    *reinterpret_cast<float2*>(comb_o + ((warp * 8 + r) * HD + dt * 8 + (lane & 3) * 2)) =
+        make_float2(oacc[dt][0], oacc[dt][1]);
+  __syncthreads();
+  for (int idx = tid; idx < NQ * HD; idx += DT) {
+    const int i = idx / HD, d = idx % HD;
+    float M = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) M = fmaxf(M, comb_ml[w][i][0]);
+    float num = 0.f, den = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float mw = comb_ml[w][i][0];
+      const float sc = (mw == -INFINITY) ? 0.f : ex2_approx((mw - M) * sl2);
+      num = fmaf(sc, comb_o[(w * 8 + i) * HD + d], num);
+      den = fmaf(sc, comb_ml[w][i][1], den);
+    }
+    o[(static_cast<long long>(kvb) * NQ + i) * ldo + h * HD + d] = __float2bfloat16_rn(num / den);
+  }
+}
+
 // ---- persistent variant for static-length caches (cross- and gated x-attention): ONE CTA per SM walks a strided list
 // of (audio, head) items; a producer warp keeps PS_STAGES tiles of K/V (32 KB each, plus the item's query rows) in
 // flight ACROSS item boundaries, four consumer warps run an independent online softmax each over their 32 keys of a
@@ -594,6 +760,27 @@ static int launch_decode_attn(const T* q, long long ldq, const T* kc, const T* v
   if constexpr (sizeof(T) == 2) if (!row_table) {
     // head-major cache + long key range: bulk-copy pipelined kernel, one CTA streams a whole (audio, head) item
     // (measured: 5.8 TB/s unsplit vs 4.0 TB/s when the item is cut into 12 one-tile CTAs - the pipeline needs depth)
+    if (NQ >= 2 && NQ <= 8 && ld_kv == HD && !len_ptr && len_max >= HM_KEYS && kv_batch_stride % HD == 0 &&
+        kv_head_stride % HD == 0 && getenv("WF_DECODE_NO_MQ") == nullptr) {
+      constexpr int NQC = (NQ >= 2 && NQ <= 8) ? NQ : 2;  // the branch is only taken for 2..8
+      const long long rpb = kv_batch_stride / HD, rph = kv_head_stride / HD;
+      CUtensorMap mk, mv;
+      int rc = make_map_bf16(&mk, kc, (kvb - 1) * rpb + (H - 1) * rph + len_max, HD, HD, HM_KEYS);
+      if (rc) return rc;
+      rc = make_map_bf16(&mv, vc, (kvb - 1) * rpb + (H - 1) * rph + len_max, HD, HD, HM_KEYS);
+      if (rc) return rc;
+      static bool mq_configured = false;
+      if (!mq_configured) {
+        WF_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_mq_kernel<NQC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           MQ_SMEM_BYTES));
+        mq_configured = true;
+      }
+      WF_CHECK_CUDA(launch_pdl(2, attn_decode_mq_kernel<NQC>, dim3(blocks), dim3(DT), MQ_SMEM_BYTES, stream, mk, mv,
+                               (const __nv_bfloat16*)q, ldq, static_cast<int>(rpb), static_cast<int>(rph),
+                               (__nv_bfloat16*)o, ldo, H, len_max));
+      count_launch();
+      return WF_OK;
+    }
     static int persist = -1;
     if (persist < 0) {
       const char* e = getenv("WF_DECODE_PERSIST");
