@@ -1,8 +1,7 @@
 #!/bin/bash
-LOG=gpurun_out/run43.log; : > $LOG
-timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -8 >> $LOG
-timeout 300 python tools/microbench.py attn2 2>&1 | grep -v Warning | tail -2 >> $LOG
-for a in "--workload medium --beam 5 --steps 2"; do
+LOG=gpurun_out/run44.log; : > $LOG
+timeout 900 python -m pytest tests/test_kernels_gpu.py -x -q -m gpu -k linear 2>&1 | tail -3 >> $LOG
+for a in "--workload medium --beam 5 --steps 2" ""; do
 echo "== $a" >> $LOG
 WF_TIMING=1 timeout 900 python bench.py $a --no-cpu-baseline --no-profile > gpurun_out/tmp.json 2>> $LOG
 python - >> $LOG <<'P'

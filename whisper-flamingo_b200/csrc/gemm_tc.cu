@@ -357,10 +357,12 @@ int linear_bf16_tc(const void* A, long long lda, const void* W, long long ldw, i
   WF_REQUIRE(M > 0 && N > 0 && K > 0, "linear: empty problem M=%d N=%d K=%d", M, N, K);
   int bn = tile_hint;
   if (bn == 0) {
-    if (M <= 256) {
-      // decode: many narrow tiles stream the weights (split-K with 64-wide tiles was measured slower: the last CTA
-      // of a tile reduces S x 32 KB of partials alone)
-      bn = (N >= 16384) ? 128 : (N >= 4096 ? 64 : 32);
+    if (M <= 2048) {
+      // few row tiles (beam-search decode steps, short prefills): the widest tile that still gives every SM a tile
+      const int m_tiles = (M + BM - 1) / BM;
+      bn = 32;
+      for (int cand = (M <= 256 ? 128 : 256); cand > 32; cand >>= 1)  // M <= 256 streams weights: measured 128 > 256
+        if (static_cast<long long>(m_tiles) * ((N + cand - 1) / cand) >= num_sms()) { bn = cand; break; }
     } else {
       bn = N >= 256 ? 256 : 128;
     }
