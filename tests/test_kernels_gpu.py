@@ -239,9 +239,9 @@ def test_linear_bf16_fused_layernorm_vs_torch(nv, m, n, k):
     assert (out32 - F.gelu(want)).abs().max().item() <= 2e-2 * scale
 
 
-@pytest.mark.parametrize("m,d,n", [(300, 384, 1152), (1500, 1280, 5120), (129, 768, 768)])
+@pytest.mark.parametrize("m,d,n", [(300, 384, 1152), (1500, 1280, 5120), (129, 768, 768), (4100, 1280, 3840)])
 def test_linear_bf16_layernorm_statistics_across_gemms(nv, m, d, n):
-    """Encoder-sized problems (M > 128): the GEMM that writes the residual stream emits per-row (sum, sum of squares)
+    """Encoder-sized problems (M > 128; M >= 2048 runs on CTA pairs): the GEMM that writes the residual stream emits per-row (sum, sum of squares)
     partials, the next GEMM applies the folded LayerNorm from them (reference model.py:30-32 + :35-41)."""
     a = _randn(m, d, dtype=torch.bfloat16, seed=1)
     w0 = _randn(d, d, dtype=torch.bfloat16, seed=2, scale=0.05)
