@@ -140,6 +140,23 @@ def gemm():
         print(row, flush=True)
 
 
+def gemm2():
+    """Epilogue sensitivity of the encoder MLP-up GEMM (M=192000, N=5120, K=1280)."""
+    m, n, k = 192000, 5120, 1280
+    a = torch.randn(m, k, device="cuda").bfloat16()
+    w = torch.randn(n, k, device="cuda").bfloat16() * 0.02
+    bias = torch.randn(n, device="cuda")
+    out = torch.empty(m, n, device="cuda", dtype=torch.bfloat16)
+    out32 = torch.empty(m, n // 4, device="cuda", dtype=torch.float32)
+    for name, fn in (("no bias, no act", lambda i: nv.linear(a, w, out)),
+                     ("bias", lambda i: nv.linear(a, w, out, bias=bias)),
+                     ("bias + gelu", lambda i: nv.linear(a, w, out, bias=bias, act=1)),
+                     ("N=1280 slice, fp32 out", lambda i: nv.linear(a, w[:1280], out32))):
+        us = timeit(fn, 1, iters=5)
+        nn = 1280 if "slice" in name else n
+        print(f"{name:28s}: {us:8.1f}us {2 * m * nn * k / us / 1e6:7.1f}TF", flush=True)
+
+
 def attn():
     print("decode attention (bf16): us, GB/s of K+V bytes")
     for (B, H, Tk, G) in ((128, 20, 1500, 1), (128, 20, 750, 1), (16, 12, 1500, 1), (64, 16, 1500, 5), (1, 6, 1500, 1)):
@@ -209,4 +226,4 @@ def fa():
 
 if __name__ == "__main__":
     for what in sys.argv[1:] or ["gemm", "attn", "ln", "mel", "fa"]:  # also: skinny, skinny2
-        {"gemm": gemm, "attn": attn, "ln": ln, "mel": mel, "fa": fa, "skinny": skinny, "skinny2": skinny2, "skinny3": skinny3, "attn2": attn2}[what]()
+        {"gemm": gemm, "attn": attn, "ln": ln, "mel": mel, "fa": fa, "skinny": skinny, "skinny2": skinny2, "skinny3": skinny3, "attn2": attn2, "gemm2": gemm2}[what]()
