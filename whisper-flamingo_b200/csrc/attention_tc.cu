@@ -21,14 +21,20 @@ static constexpr int FT_M = 128;      // queries per softmax warpgroup
 static constexpr int FT_WG = 2;       // warpgroups (query tiles) per CTA: 256 queries share every K/V tile
 static constexpr int FT_N = 128;      // keys per tile
 static constexpr int FT_D = 64;       // head dim
-static constexpr int FT_STAGES = 3;
+// P (the bf16 probabilities) goes from the softmax threads to the P V MMA through TENSOR memory (tcgen05.st, A operand
+// read from TMEM) instead of a swizzled shared-memory tile: per K/V tile the CTA's shared memory then carries 96 KB
+// (TMA fill + K and V operand reads of two warpgroups + Q) instead of 256 KB - at 128 B/clk the smem-P version spent as
+// long on shared-memory traffic (2048 clk) as on its exponentials.  The freed 64 KB become two more K/V stages.
+static constexpr bool FT_P_IN_TMEM = true;
+static constexpr int FT_STAGES = FT_P_IN_TMEM ? 5 : 3;
 static constexpr int FT_TILE = FT_N * FT_D * 2;             // 16 KB: one K (or V, or Q, or half-P) tile
 static constexpr int FT_OFF_KV = FT_WG * FT_TILE;           // after Q_A, Q_B
 static constexpr int FT_OFF_P = FT_OFF_KV + FT_STAGES * 2 * FT_TILE;
-static constexpr int FT_OFF_BAR = FT_OFF_P + FT_WG * 2 * FT_TILE;
+static constexpr int FT_OFF_BAR = FT_OFF_P + (FT_P_IN_TMEM ? 0 : FT_WG * 2 * FT_TILE);
 static constexpr int FT_SMEM = FT_OFF_BAR + 256 + 1024;
 static constexpr int FT_TMEM_COLS = 512;
 static constexpr int FT_COL_O = 256;                         // S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384)
+static constexpr int FT_COL_P = 384;                         // P_A [384,448) P_B [448,512): 128 keys x bf16 = 64 cells
 static constexpr int FT_THREADS = 128 + FT_WG * 128;
 
 __global__ void __launch_bounds__(FT_THREADS, 1)
@@ -98,13 +104,21 @@ fa_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
     auto issue_pv = [&](int w, int j) {  // O_w += P_w(j) V(j)
       const int st = j % FT_STAGES;
       const uint32_t v_addr = smem_u32(smem + FT_OFF_KV + st * 2 * FT_TILE + FT_TILE);
-      const uint32_t p_addr = smem_u32(smem + FT_OFF_P + w * 2 * FT_TILE);
+      const uint32_t p_addr = smem_u32(smem + FT_OFF_P + (FT_P_IN_TMEM ? 0 : w * 2 * FT_TILE));
+      (void)p_addr;
 #pragma unroll
       for (int kk = 0; kk < FT_N / 16; ++kk) {
-        // A: P half (kk / 4) of 64 keys, 16 keys (32 B) per step; B: V rows 16 kk .. 16 kk + 15 (two 1024-B groups)
-        const uint64_t a_desc = umma_desc_kmajor_sw128(p_addr + (kk >> 2) * FT_TILE) + 2 * (kk & 3);
+        // B: V rows 16 kk .. 16 kk + 15 (two 1024-B groups)
         const uint64_t b_desc = umma_desc_mnmajor_sw128(v_addr + kk * 2048);
-        umma_f16(tmem_base + FT_COL_O + w * FT_D, a_desc, b_desc, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+        if constexpr (FT_P_IN_TMEM) {
+          // A: 16 keys = 8 TMEM cells of this warpgroup's P region
+          umma_f16_ts(tmem_base + FT_COL_O + w * FT_D, tmem_base + FT_COL_P + w * (FT_N / 2) + kk * 8, b_desc, idesc_o,
+                      (j > 0 || kk > 0) ? 1u : 0u);
+        } else {
+          // A: P half (kk / 4) of 64 keys, 16 keys (32 B) per step
+          const uint64_t a_desc = umma_desc_kmajor_sw128(p_addr + (kk >> 2) * FT_TILE) + 2 * (kk & 3);
+          umma_f16(tmem_base + FT_COL_O + w * FT_D, a_desc, b_desc, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+        }
       }
       umma_commit(&o_done[w]);
     };
@@ -143,7 +157,8 @@ fa_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16);
     const uint32_t s_addr = lane_addr + w * FT_N;
     const uint32_t o_addr = lane_addr + FT_COL_O + w * FT_D;
-    uint8_t* p_buf = smem + FT_OFF_P + w * 2 * FT_TILE;
+    uint8_t* p_buf = smem + FT_OFF_P + (FT_P_IN_TMEM ? 0 : w * 2 * FT_TILE);
+    (void)p_buf;
     const float sl2 = 0.125f * 1.44269504088896340736f;              // 64^-0.5 * log2(e)
     float m_run = -INFINITY, l_run = 0.f;
     for (int j = 0; j < n_tiles; ++j) {
@@ -206,18 +221,31 @@ fa_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
       }
       l_run = l_run * alpha + psum;
       m_run = mx;
-      // P -> 128B-swizzled K-major tile (two 64-key halves); its previous reader PV_w(j-1) has completed
+      if constexpr (FT_P_IN_TMEM) {
+        // P -> tensor memory: this thread's row, 64 cells of two bf16; the previous reader PV_w(j-1) has completed
+        // (o_done was waited for above, or this is the first tile)
+        uint32_t pk[2][32];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint8_t* row_base = p_buf + (c >> 1) * FT_TILE + r * 128;
+        for (int c = 0; c < 4; ++c)
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int ch = (c & 1) * 4 + g;                             // 16-byte chunk within the 128-byte row
-          *reinterpret_cast<uint4*>(row_base + ((ch ^ (r & 7)) << 4)) =
-              make_uint4(sv[c][g * 4], sv[c][g * 4 + 1], sv[c][g * 4 + 2], sv[c][g * 4 + 3]);
+          for (int i = 0; i < 16; ++i) pk[c >> 1][(c & 1) * 16 + i] = sv[c][i];
+        tmem_st_32x32(lane_addr + FT_COL_P + w * (FT_N / 2), pk[0]);
+        tmem_st_32x32(lane_addr + FT_COL_P + w * (FT_N / 2) + 32, pk[1]);
+        tmem_st_wait();
+      } else {
+        // P -> 128B-swizzled K-major tile (two 64-key halves); its previous reader PV_w(j-1) has completed
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint8_t* row_base = p_buf + (c >> 1) * FT_TILE + r * 128;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int ch = (c & 1) * 4 + g;                             // 16-byte chunk within the 128-byte row
+            *reinterpret_cast<uint4*>(row_base + ((ch ^ (r & 7)) << 4)) =
+                make_uint4(sv[c][g * 4], sv[c][g * 4 + 1], sv[c][g * 4 + 2], sv[c][g * 4 + 3]);
+          }
         }
+        fence_proxy_async_smem();   // P (generic-proxy stores) must be visible to the tensor core's async proxy
       }
-      fence_proxy_async_smem();   // P (generic-proxy stores) must be visible to the tensor core's async proxy
       tc_fence_before();
       mbar_arrive(&p_full[w]);
     }
