@@ -1,5 +1,5 @@
 #!/bin/bash
-LOG=gpurun_out/run52.log; : > $LOG
+LOG=gpurun_out/run57.log; : > $LOG
 timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -4 >> $LOG
 WF_TIMING=1 timeout 900 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-profile > gpurun_out/tmp.json 2>> $LOG
 python - >> $LOG <<'P'

@@ -42,7 +42,8 @@ struct SkCfg {
   static constexpr int STAT_BYTES = 2 * SK_BM * 2 * 4;  // [atom group][row]{sum, sumsq}
   static constexpr int BAR_BYTES = (2 * STAGES + 1) * 8 + 16;
   static constexpr int SMEM_BYTES = PIPE_BYTES + STAT_BYTES + BAR_BYTES + 1024;
-  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulators (one per MMA-issuing warp)
+  static_assert(TMEM_COLS <= 512, "accumulators do not fit tensor memory");
   static_assert(PIPE_BYTES >= DUMP_BYTES, "the accumulator dump aliases the pipeline stages");
   static_assert(B_ATOM % 1024 == 0, "operand atoms must keep 1024-byte alignment");
   static_assert(SMEM_BYTES <= 227 * 1024, "over the shared-memory budget");
@@ -111,7 +112,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], ln ? 9 : 1);  // MMA commit (+ one arrival per LN-statistics warp)
     }
-    mbar_init(tfull_bar, 1);
+    mbar_init(tfull_bar, nr >= 2 ? 2 : 1);  // one commit per MMA-issuing warp that has rounds
     mbar_fence_init();
   }
   if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
@@ -151,12 +152,19 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       }
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ------------------------------------------------------------ MMA issuer
+  } else if ((warp == 1 || warp == 3) && lane == 0) {
+    // ------------------------------------------------------------ MMA issuers: warp 1 takes the even pipeline rounds
+    // into accumulator 0, warp 3 the odd rounds into accumulator 1 (the epilogue adds them).  One thread sustains
+    // ~350 cycles per round + ~63 per MMA whatever the tile shape (M = 64 operands: same time), and the cost is per issuing
+    // THREAD: a second stream brought N=K=1280 from 6.9 to 5.9 us and K=5120 from 20.0 to 15.4 us.
     constexpr uint32_t idesc = umma_idesc_bf16(SK_BM, BN);
-    int stage = 0;
+    const int me = warp == 1 ? 0 : 1;
+    const uint32_t tmem_d = tmem_base + me * BN;
+    int stage = me % STAGES;
     uint32_t phase = 0;
-    for (int r = 0; r < nr; ++r) {
+    int last = -1;
+    for (int r = me; r < nr; r += 2) last = r;
+    for (int r = me; r < nr; r += 2) {
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
 #pragma unroll
@@ -165,11 +173,12 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(b_atom(stage, a)));
 #pragma unroll
         for (int k = 0; k < SK_BK / SK_UMMA_K; ++k)
-          umma_f16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (r > 0 || a > 0 || k > 0) ? 1u : 0u);
+          umma_f16(tmem_d, a_desc + 2 * k, b_desc + 2 * k, idesc, (r > me || a > 0 || k > 0) ? 1u : 0u);
       }
       umma_commit(&empty_bar[stage]);
-      if (r == nr - 1) umma_commit(tfull_bar);
-      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      if (r == last) umma_commit(tfull_bar);
+      stage += 2;
+      if (stage >= STAGES) { stage -= STAGES; phase ^= 1; }
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue warps, phase A
@@ -206,6 +215,8 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       tc_fence_after();
     }
     if (CS > 1) {
+      // the dump aliases the pipeline stages: every LayerNorm-statistics warp must have finished reading the A tiles
+      if (ln) epi_bar();
       // all TMA loads of this CTA have been consumed and all its MMAs have retired: the stages are free to hold the dump
       const uint32_t tsrc = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
@@ -214,6 +225,13 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         if (nr > 0) {
           tmem_ld_32x32(tsrc + c * 32, r);
           tmem_ld_wait();
+          if (nr >= 2) {  // rounds were dealt to two accumulators
+            uint32_t r2[32];
+            tmem_ld_32x32(tsrc + BN + c * 32, r2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+          }
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) r[j] = 0u;
@@ -272,6 +290,13 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         uint32_t r[32];
         tmem_ld_32x32(tsrc + c * 32, r);
         tmem_ld_wait();
+        if (nr >= 2) {  // rounds were dealt to two accumulators
+          uint32_t r2[32];
+          tmem_ld_32x32(tsrc + BN + c * 32, r2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+        }
         const int n0 = n_blk * BN + c * 32;
         if (m < M && n0 < N) {
           float v[32];
