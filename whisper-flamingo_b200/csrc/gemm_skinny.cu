@@ -3,15 +3,17 @@
 // Replaces reference whisper/model.py:35-41 (Linear.forward) and, when asked, the LayerNorm in front of it
 // (model.py:30-32) for the one-token decoder pass (decoding.py:155-164).  These GEMMs move 3-13 MB of weights and
 // should take a microsecond; the persistent large-tile kernel (gemm_tc.cu) needed 8-26 us for them because ONE
-// CTA walked the whole K extent of its N tile serially.  Measured on B200 (tools/microbench.py skinny2):
-//     t = 1.9 us + 0.30 us per 64-wide k-block, whatever M, the N tile or where the weights come from,
-// of which 0.155 us is the L2->SM operand stream (20 KB per k-block at ~64 B/clk) and the rest the single MMA-issuing
-// thread (~350 cycles per barrier round + ~62 cycles per 128 x 32 x 16 MMA, operand-read bound).
+// CTA walked the whole K extent of its N tile serially.  Measured on B200 (tools/microbench.py skinny2 / skinny3):
+//     t = 1.9 us + 0.30 us per 64-wide k-block, whatever M (16 / 64 / 128 rows, or 64-row MMAs), the N tile (32 .. 128)
+//     or where the weights come from (L2 / HBM);
+// the cost sits in the single MMA-ISSUING THREAD: ~350 cycles per barrier round (wait, fence, commit) + ~63 cycles per
+// tcgen05.mma, while the TMA stream alone needs 0.155 us per 20 KB k-block (~64 B/clk per SM).
 //
-// So this kernel splits K as well as N: a thread-block CLUSTER of CS CTAs owns one 128 x BN output tile, each CTA
+// So this kernel (a) issues MMAs from TWO warps into two TMEM accumulators, (b) moves two swizzle atoms per barrier
+// round and (c) can split K as well as N: a thread-block CLUSTER of CS CTAs owns one 128 x BN output tile, each CTA
 // accumulates a K slice in TMEM with two swizzle atoms (K = 128) per pipeline round, and the partial tiles are reduced
 // through distributed shared memory: every CTA dumps its accumulator to its own smem, cluster barrier, then CTA r
-// sums column slice r of all CS partials (ld.shared::cluster) and runs the fused epilogue for it.  No global
+// sums row slice r of all CS partials (coalesced ld.shared::cluster) and runs the fused epilogue for it.  No global
 // workspace, no atomics, no second kernel.
 //
 // Optional fused LayerNorm: the epilogue warps, idle during the main loop, accumulate sum / sum-of-squares of the raw
@@ -42,7 +44,11 @@ struct SkCfg {
   static constexpr int STAT_BYTES = 2 * SK_BM * 2 * 4;  // [atom group][row]{sum, sumsq}
   static constexpr int BAR_BYTES = (2 * STAGES + 1) * 8 + 16;
   static constexpr int SMEM_BYTES = PIPE_BYTES + STAT_BYTES + BAR_BYTES + 1024;
-  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulators (one per MMA-issuing warp)
+  // MMA-issuing warps, one TMEM accumulator each.  Measured (N=K=1280, 32-wide tile): 1 -> 6.9 us, 2 -> 5.9 us, 3 -> 6.1 us:
+  // with two streams the main loop runs at the ~64 B/clk an SM pulls through the crossbar (0.33 us per 40 KB round).
+  static constexpr int NI = 2;
+  static constexpr int TMEM_RAW = NI * BN;
+  static constexpr int TMEM_COLS = TMEM_RAW <= 32 ? 32 : TMEM_RAW <= 64 ? 64 : TMEM_RAW <= 128 ? 128 : TMEM_RAW <= 256 ? 256 : 512;
   static_assert(TMEM_COLS <= 512, "accumulators do not fit tensor memory");
   static_assert(PIPE_BYTES >= DUMP_BYTES, "the accumulator dump aliases the pipeline stages");
   static_assert(B_ATOM % 1024 == 0, "operand atoms must keep 1024-byte alignment");
@@ -112,7 +118,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], ln ? 9 : 1);  // MMA commit (+ one arrival per LN-statistics warp)
     }
-    mbar_init(tfull_bar, nr >= 2 ? 2 : 1);  // one commit per MMA-issuing warp that has rounds
+    mbar_init(tfull_bar, nr < Cfg::NI ? (nr > 0 ? nr : 1) : Cfg::NI);  // one commit per MMA-issuing warp that has rounds
     mbar_fence_init();
   }
   if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
@@ -152,19 +158,20 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       }
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
-  } else if ((warp == 1 || warp == 3) && lane == 0) {
+  } else if (warp >= 1 && warp <= Cfg::NI && lane == 0) {
     // ------------------------------------------------------------ MMA issuers: warp 1 takes the even pipeline rounds
     // into accumulator 0, warp 3 the odd rounds into accumulator 1 (the epilogue adds them).  One thread sustains
     // ~350 cycles per round + ~63 per MMA whatever the tile shape (M = 64 operands: same time), and the cost is per issuing
     // THREAD: a second stream brought N=K=1280 from 6.9 to 5.9 us and K=5120 from 20.0 to 15.4 us.
     constexpr uint32_t idesc = umma_idesc_bf16(SK_BM, BN);
-    const int me = warp == 1 ? 0 : 1;
+    constexpr int NI = Cfg::NI;
+    const int me = warp - 1;
     const uint32_t tmem_d = tmem_base + me * BN;
     int stage = me % STAGES;
     uint32_t phase = 0;
     int last = -1;
-    for (int r = me; r < nr; r += 2) last = r;
-    for (int r = me; r < nr; r += 2) {
+    for (int r = me; r < nr; r += NI) last = r;
+    for (int r = me; r < nr; r += NI) {
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
 #pragma unroll
@@ -177,8 +184,8 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       }
       umma_commit(&empty_bar[stage]);
       if (r == last) umma_commit(tfull_bar);
-      stage += 2;
-      if (stage >= STAGES) { stage -= STAGES; phase ^= 1; }
+      stage += NI;
+      while (stage >= STAGES) { stage -= STAGES; phase ^= 1; }
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue warps, phase A
@@ -225,12 +232,15 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         if (nr > 0) {
           tmem_ld_32x32(tsrc + c * 32, r);
           tmem_ld_wait();
-          if (nr >= 2) {  // rounds were dealt to two accumulators
-            uint32_t r2[32];
-            tmem_ld_32x32(tsrc + BN + c * 32, r2);
-            tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+          for (int a2 = 1; a2 < Cfg::NI; ++a2) {  // rounds were dealt to NI accumulators
+            if (a2 < nr) {
+              uint32_t r2[32];
+              tmem_ld_32x32(tsrc + a2 * BN + c * 32, r2);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+            }
           }
         } else {
 #pragma unroll
@@ -290,12 +300,15 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         uint32_t r[32];
         tmem_ld_32x32(tsrc + c * 32, r);
         tmem_ld_wait();
-        if (nr >= 2) {  // rounds were dealt to two accumulators
-          uint32_t r2[32];
-          tmem_ld_32x32(tsrc + BN + c * 32, r2);
-          tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+        for (int a2 = 1; a2 < Cfg::NI; ++a2) {  // rounds were dealt to NI accumulators
+          if (a2 < nr) {
+            uint32_t r2[32];
+            tmem_ld_32x32(tsrc + a2 * BN + c * 32, r2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+          }
         }
         const int n0 = n_blk * BN + c * 32;
         if (m < M && n0 < N) {
@@ -400,13 +413,12 @@ static int launch_skinny(const CUtensorMap& ma, const CUtensorMap& mb, int M, in
 }
 
 // Tile width and cluster size for an [M <= 128] x N x K problem.  Measured on B200 inside a CUDA graph with PDL
-// (tools/microbench.py skinny3, M = 128):
-//   * one CTA walks a 64-wide k-atom in ~0.22 us (32-wide tile) .. 0.28 us (128-wide): the SM's shared-memory
-//     bandwidth carries the TMA fill AND the operand reads of four MMAs (the 128-row activation slab is re-read by
-//     every MMA), ~40 .. 64 KB per atom; fixed cost ~2.3 us;
-//   * a cluster costs ~1.1 us for its two barriers plus the DSMEM reduction at ~20 B/clk per SM (1.6 us for 32 KB of
-//     partials), so K is split 2-way only for the narrowest tile and 4-way only when a CTA would otherwise walk
-//     >= 64 atoms:  N=K=1280 6.95 -> 6.39 us (32, cs 2);  N=1280, K=5120 20.2 -> 10.5 us (64, cs 4).
+// (tools/microbench.py skinny3, M = 128, two MMA-issuing warps):
+//   * fixed cost ~2.3 us; one CTA then walks a 128-wide K round (40 KB for a 32-wide tile) in ~0.33 us, the ~64 B/clk an
+//     SM pulls through the crossbar;
+//   * a cluster costs ~1.1 us for its two barriers plus the DSMEM reduction at ~20 B/clk per SM, so K is split (4-way)
+//     only when a CTA would otherwise walk >= 32 rounds:  N=1280, K=5120: 15.4 us (32, cs 1) -> 10.0 us (64, cs 4);
+//     N=K=1280: 5.94 us (32, cs 1) vs 5.98 us (32, cs 2).
 bool skinny_plan(int M, int N, int K, int tile_hint, int* bn_out, int* cs_out) {
   if (M > SK_BM) return false;
   static int mode = -1, force_cs = -1;
@@ -421,7 +433,6 @@ bool skinny_plan(int M, int N, int K, int tile_hint, int* bn_out, int* cs_out) {
   const int rounds = (K + SK_KA * SK_BK - 1) / (SK_KA * SK_BK);
   const int bns[4] = {32, 64, 128, 256};
   int cs = rounds >= 32 ? 4 : 1;
-  if (cs == 1 && rounds >= 8 && !tile_hint && ((N + 31) / 32) * 2 <= sms) cs = 2;  // -> (32, 2)
   if (force_cs) cs = force_cs;
   while (cs > 1 && cs > rounds) cs >>= 1;
   for (;; cs >>= 1) {
