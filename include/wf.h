@@ -142,6 +142,19 @@ int wf_attention_decode_paged(int dtype, const void* q, long long ldq, const voi
                               int H, const int* len_ptr, int len_add, int len_const, const int* row_table,
                               int table_ld, void* workspace, long long workspace_bytes, wf_stream_t stream);
 
+/* ---- one-token cross-attention over the SOURCE rows (absorbed key / value projections, WF_BF16, head_dim 64,
+ *      n_state a multiple of 256 up to 1280).  Same result as wf_attention_decode over K = src Wk^T, V = src Wv^T + bv
+ *      (whisper/model.py:82-108 with xa, :110-134 with xt; per-step recompute of decoding.py:155-164), but the step
+ *      streams src [B, T, d] once for all heads instead of a per-layer K/V cache of twice the size:
+ *        wf_latent_query      qp[r, h, :]  = Wk_h^T q[r, 64h:64h+64]          (wkT = Wk^T, [d, d] row-major bf16)
+ *        wf_latent_attention  ctx[b, h, :] = softmax(src_b qp[b, h, :] / 8)^T src_b     (tcgen05 + cluster kernel)
+ *        wf_latent_value      o[r, 64h:64h+64] = Wv_h ctx[r, h, :] + bv_h     (wv = value.weight rows, ld = ldw)
+ *      qp, ctx: [R, H, d] bf16 contiguous; one query row per source clip (R == B). */
+int wf_latent_query(const void* q, long long ldq, const void* wkT, void* qp, int R, int H, wf_stream_t stream);
+int wf_latent_attention(const void* qp, const void* src, void* ctx, int B, int T, int H, wf_stream_t stream);
+int wf_latent_value(const void* ctx, const void* wv, long long ldw, const float* bv, void* o, long long ldo, int R,
+                    int H, wf_stream_t stream);
+
 /* ---- sampling: whisper/decoding.py:427-442 (SuppressBlank/SuppressTokens), :276-302 (GreedyDecoder),
  *      :697-701 (no_speech_prob), loop bookkeeping of :688-718 ------------------------------------ */
 /* state (device ints): [0]=t position of the token fed this step, [1]=n_init, [2]=all_done,

@@ -544,3 +544,48 @@ def test_errors_are_reported_not_swallowed(nv):
         nv.linear(a, w, torch.empty((8, 8), dtype=torch.bfloat16, device="cuda"))
     with pytest.raises(nv.WfError):
         nv.logmel(torch.zeros(1, 100, device="cuda"), 80, 0)
+
+
+# ----------------------------------------------------------------------------- absorbed ("latent") cross-attention
+def _latent_reference(q, src, wk, wv, bv, H):
+    """model.py:82-108 restated in fp32: K = src Wk^T, V = src Wv^T + bv, o_h = softmax(q_h K_h^T / 8) V_h."""
+    B, T, d = src.shape
+    q, src, wk, wv = q.float(), src.float(), wk.float(), wv.float()
+    k = (src @ wk.T).view(B, T, H, 64).permute(0, 2, 1, 3)
+    v = (src @ wv.T + bv).view(B, T, H, 64).permute(0, 2, 1, 3)
+    qh = q.view(B, H, 1, 64)
+    w = torch.softmax((qh @ k.transpose(-1, -2)) * 0.125, dim=-1)
+    return (w @ v).reshape(B, H * 64)
+
+
+@pytest.mark.parametrize("H,B,T", [(20, 3, 1500), (20, 2, 750), (16, 2, 300), (12, 2, 130), (8, 1, 128), (4, 2, 40),
+                                   (20, 5, 1)])
+def test_latent_cross_attention_matches_kv_attention(nv, H, B, T):
+    from helpers import rel_l2
+    d = 64 * H
+    bf = torch.bfloat16
+    q = _randn(B, d, dtype=bf, seed=1)
+    src = _randn(B, T, d, dtype=bf, seed=2)
+    wk = _randn(d, d, dtype=bf, seed=3, scale=2.0 / math.sqrt(d))   # scores with a spread of a few units
+    wv = _randn(d, d, dtype=bf, seed=4, scale=1.0 / math.sqrt(d))
+    bv = _randn(d, seed=5, scale=0.1)
+    qp = torch.empty(B, H, d, dtype=bf, device="cuda")
+    ctx = torch.full((B, H, d), float("nan"), dtype=bf, device="cuda")
+    out = torch.full((B, d), float("nan"), dtype=bf, device="cuda")
+    nv.latent_query(q, wk.t().contiguous(), qp, H)
+    nv.latent_attention(qp, src, ctx, H)
+    nv.latent_value(ctx, wv, bv, out, H)
+    torch.cuda.synchronize()
+    # stage 1: q' = Wk_h^T q_h
+    qp_ref = torch.einsum("bhj,hjn->bhn", q.float().view(B, H, 64), wk.float().view(H, 64, d))
+    assert rel_l2(qp, qp_ref) < 6e-3
+    # stage 2 (from the kernel's own bf16 q'): softmax over keys, context = weighted sum of source rows
+    sc = torch.einsum("bhn,btn->bht", qp.float(), src.float()) * 0.125
+    ctx_ref = torch.einsum("bht,btn->bhn", torch.softmax(sc, dim=-1), src.float())
+    assert rel_l2(ctx, ctx_ref) < 8e-3
+    # stage 3 (from the kernel's own bf16 context)
+    out3 = torch.einsum("bhn,hjn->bhj", ctx.float(), wv.float().view(H, 64, d)).reshape(B, d) + bv
+    assert rel_l2(out, out3) < 6e-3
+    # end to end against attention over projected K / V (what the reference computes); bf16 tolerance: the K / V
+    # rounding of the cached path is replaced by the rounding of q' and of the context
+    assert rel_l2(out, _latent_reference(q, src, wk, wv, bv, H)) < 1.5e-2

@@ -224,6 +224,28 @@ def fa():
         print(f"attention_full B={B} H={H} T={T}: {us:.1f} us, {4 * B * H * T * T * 64 / us / 1e6:.1f} TFLOP/s")
 
 
+def latent():
+    """Absorbed cross-attention (q' -> stream the source rows once -> value projection) vs the K/V-cache kernel."""
+    print("latent cross-attention, in-graph us per launch; GB/s of source bytes (B*T*d*2)")
+    for (B, H, T) in ((128, 20, 1500), (128, 20, 750), (64, 16, 1500), (16, 12, 1500)):
+        d = H * 64
+        n_rot = 2 if B * T * d * 2 > 200e6 else 4
+        srcs = [torch.randn(B, T, d, device="cuda").bfloat16() for _ in range(n_rot)]
+        q = torch.randn(B, d, device="cuda").bfloat16()
+        wk_t = (torch.randn(d, d, device="cuda") * (2.0 / d ** 0.5)).bfloat16()
+        wv = (torch.randn(d, d, device="cuda") / d ** 0.5).bfloat16()
+        bv = torch.zeros(d, device="cuda")
+        qp = torch.empty(B, H, d, device="cuda", dtype=torch.bfloat16)
+        ctx = torch.empty(B, H, d, device="cuda", dtype=torch.bfloat16)
+        out = torch.empty(B, d, device="cuda", dtype=torch.bfloat16)
+        nv.latent_query(q, wk_t, qp, H)
+        t_q = graph_timeit(lambda i: nv.latent_query(q, wk_t, qp, H), 1)
+        t_a = graph_timeit(lambda i: nv.latent_attention(qp, srcs[i], ctx, H), n_rot, reps=16)
+        t_v = graph_timeit(lambda i: nv.latent_value(ctx, wv, bv, out, H), 1)
+        print(f"B={B} H={H} T={T}: query {t_q:.2f} us | attention {t_a:.1f} us = {B * T * d * 2 / t_a / 1e3:.0f} GB/s "
+              f"| value {t_v:.2f} us", flush=True)
+
+
 if __name__ == "__main__":
     for what in sys.argv[1:] or ["gemm", "attn", "ln", "mel", "fa"]:  # also: skinny, skinny2
-        {"gemm": gemm, "attn": attn, "ln": ln, "mel": mel, "fa": fa, "skinny": skinny, "skinny2": skinny2, "skinny3": skinny3, "attn2": attn2, "gemm2": gemm2}[what]()
+        {"gemm": gemm, "attn": attn, "ln": ln, "mel": mel, "fa": fa, "skinny": skinny, "skinny2": skinny2, "skinny3": skinny3, "attn2": attn2, "gemm2": gemm2, "latent": latent}[what]()

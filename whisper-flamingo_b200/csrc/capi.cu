@@ -161,6 +161,20 @@ int wf_attention_decode_paged(int dtype, const void* q, long long ldq, const voi
                           len_add, len_const, workspace, workspace_bytes, row_table, table_ld, S(stream));
 }
 
+int wf_latent_query(const void* q, long long ldq, const void* wkT, void* qp, int R, int H, wf_stream_t stream) {
+  WF_REQUIRE(q && wkT && qp && R > 0 && H > 0, "wf_latent_query: null buffer / empty problem");
+  return latent_query(q, ldq, wkT, qp, R, H, S(stream));
+}
+int wf_latent_attention(const void* qp, const void* src, void* ctx, int B, int T, int H, wf_stream_t stream) {
+  WF_REQUIRE(qp && src && ctx, "wf_latent_attention: null buffer");
+  return latent_attention(qp, src, ctx, B, T, H, S(stream));
+}
+int wf_latent_value(const void* ctx, const void* wv, long long ldw, const float* bv, void* o, long long ldo, int R,
+                    int H, wf_stream_t stream) {
+  WF_REQUIRE(ctx && wv && o && R > 0 && H > 0, "wf_latent_value: null buffer / empty problem");
+  return latent_value(ctx, wv, ldw, bv, o, ldo, R, H, S(stream));
+}
+
 int wf_sample_greedy(const wf_sample_t* a, wf_stream_t stream) {
   WF_REQUIRE(a != nullptr, "wf_sample_greedy: null args");
   SampleArgs s;

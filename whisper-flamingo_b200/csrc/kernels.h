@@ -67,6 +67,12 @@ int attention_full(int dtype, const void* q, long long ldq, const void* k, long 
 int attention_full_tc(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
                       void* o, long long ldo, int B, int Tq, int Tk, int H, cudaStream_t stream);
 
+// latent.cu (one-token cross-attention over the source rows: absorbed K / V projections, bf16)
+int latent_query(const void* q, long long ldq, const void* wkT, void* qp, int R, int H, cudaStream_t stream);
+int latent_attention(const void* qp, const void* src, void* ctx, int B, int T, int H, cudaStream_t stream);
+int latent_value(const void* ctx, const void* wv, long long ldw, const float* bv, void* o, long long ldo, int R, int H,
+                 cudaStream_t stream);
+
 // decode.cu
 int attention_decode(int dtype, const void* q, long long ldq, const void* kc, const void* vc, long long ld_kv,
                      long long kv_batch_stride, long long kv_head_stride, void* o, long long ldo, int R, int G, int H,

@@ -80,6 +80,10 @@ _SIGNATURES = {
                                             C.c_longlong, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_int,
                                             C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                                             C.c_longlong, C.c_void_p]),
+    "wf_latent_query": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "wf_latent_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "wf_latent_value": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_longlong,
+                                  C.c_int, C.c_int, C.c_void_p]),
     "wf_sample_greedy": (C.c_int, [C.POINTER(_Sample), C.c_void_p]),
     "wf_step_advance": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "wf_topk_logprobs": (C.c_int, [C.POINTER(_Topk), C.c_void_p]),
@@ -344,6 +348,39 @@ def attention_decode(q: torch.Tensor, kc: torch.Tensor, vc: torch.Tensor, ld_kv:
                                           vc.data_ptr(), ld_kv, kv_batch_stride, kv_head_stride, out.data_ptr(),
                                           _row_stride(out), r, g, h, _ptr(len_ptr), len_add, len_const, _ptr(ws),
                                           0 if ws is None else ws.numel() * ws.element_size(), _stream()))
+    return out
+
+
+def latent_query(q: torch.Tensor, wk_t: torch.Tensor, qp: torch.Tensor, h: int) -> torch.Tensor:
+    """qp[r, h, :] = Wk_h^T q[r, 64h:64h+64]; wk_t = key.weight^T ([d, d] contiguous bf16), qp [R, H, d] bf16."""
+    r, d = q.shape[0], h * 64
+    assert q.dtype == wk_t.dtype == qp.dtype == torch.bfloat16 and wk_t.is_contiguous() and qp.is_contiguous()
+    assert wk_t.shape == (d, d) and qp.numel() == r * h * d
+    with _Prof("latent_query", bytes=2 * (d * d + r * d + r * h * d)):
+        _check(load().wf_latent_query(q.data_ptr(), _row_stride(q), wk_t.data_ptr(), qp.data_ptr(), r, h, _stream()))
+    return qp
+
+
+def latent_attention(qp: torch.Tensor, src: torch.Tensor, ctx: torch.Tensor, h: int) -> torch.Tensor:
+    """ctx[b, h, :] = softmax(src[b] qp[b, h, :] / 8)^T src[b]; src [B, T, d] contiguous bf16, qp / ctx [B, H, d]."""
+    b, t, d = src.shape
+    assert src.dtype == qp.dtype == ctx.dtype == torch.bfloat16 and d == 64 * h
+    assert src.is_contiguous() and qp.is_contiguous() and ctx.is_contiguous() and qp.numel() == ctx.numel() == b * d * h
+    # algorithmic bytes: every source row once for all heads
+    with _Prof("latent_attention", bytes=2 * b * t * d):
+        _check(load().wf_latent_attention(qp.data_ptr(), src.data_ptr(), ctx.data_ptr(), b, t, h, _stream()))
+    return ctx
+
+
+def latent_value(ctx: torch.Tensor, wv: torch.Tensor, bv: Optional[torch.Tensor], out: torch.Tensor,
+                 h: int) -> torch.Tensor:
+    """out[r, 64h:64h+64] = Wv_h ctx[r, h, :] + bv_h; wv = value.weight ([d, d] rows, bf16), bv fp32 [d] or None."""
+    r, d = out.shape[0], h * 64
+    assert ctx.dtype == wv.dtype == out.dtype == torch.bfloat16 and ctx.is_contiguous() and ctx.numel() == r * h * d
+    assert bv is None or bv.dtype == torch.float32
+    with _Prof("latent_value", bytes=2 * (d * d + r * d + r * h * d)):
+        _check(load().wf_latent_value(ctx.data_ptr(), wv.data_ptr(), _row_stride(wv), _ptr(bv), out.data_ptr(),
+                                      _row_stride(out), r, h, _stream()))
     return out
 
 
