@@ -227,7 +227,8 @@ def fa():
 def latent():
     """Absorbed cross-attention (q' -> stream the source rows once -> value projection) vs the K/V-cache kernel."""
     print("latent cross-attention, in-graph us per launch; GB/s of source bytes (B*T*d*2)")
-    for (B, H, T) in ((128, 20, 1500), (128, 20, 750), (64, 16, 1500), (16, 12, 1500)):
+    shapes = ((128, 20, 1500), (128, 20, 750), (64, 16, 1500), (16, 12, 1500))
+    for (B, H, T) in shapes[:int(os.environ.get("LATENT_SHAPES", len(shapes)))]:
         d = H * 64
         n_rot = 2 if B * T * d * 2 > 200e6 else 4
         srcs = [torch.randn(B, T, d, device="cuda").bfloat16() for _ in range(n_rot)]

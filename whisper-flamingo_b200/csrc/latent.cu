@@ -14,403 +14,295 @@
 //   latent_attn_kernel   q', src  -> c  [R, H, d]         (tcgen05 + TMA + thread-block cluster, below)
 //   latent_value_kernel  c -> o [R, d]                    (per head a [R,d] x [d,64] GEMM + bias, mma.sync)
 //
-// latent_attn_kernel: one CLUSTER of CS = d / 256 CTAs per clip; CTA r owns latent columns [256 r, 256 r + 256) of
-// src and of q', and the softmax bookkeeping of heads [4 r, 4 r + 4).  Per 128-key tile j:
-//   TMA      : src tile slice [128 keys x 256] -> 4 swizzled 16 KB chunks (2-stage ring), read from HBM exactly once;
-//   tcgen05  : S^T_partial[128 keys x 32 heads] = tile (A, K-major) x q'_slice^T (B)           -> TMEM
-//   softmax warps (thread = key): push the partial scores of 4 heads to their owner CTA (st.shared::cluster), owner sums
-//              the CS partials, keeps the running max / sum of its 4 heads, pushes p (bf16) and the rescale factor
-//              alpha of its heads to every CTA of the cluster;
-//   tcgen05  : C^T[256 latent x 32 heads] += tile^T (A, MN-major: the SAME smem chunks) x P^T (B)   in TMEM
-// so each CTA ends with its 256-column slice of c_h for every head and writes it normalised by 1 / l_h.
+// latent_attn_kernel: one CTA per clip, the whole latent width d in the CTA, 32-key tiles (a tile = 32 contiguous
+// source rows = d / 128 ring stages of [32 keys x 128 columns], loaded by TMA exactly once, ring of ~1.9 tiles):
+//   tcgen05  : S[64 rows (heads) x 32 keys] = q' (A, K-major, resident) x tile^T (B, K-major)        -> TMEM
+//   softmax  : thread = head (its 32 scores in registers, no shuffles), lazy reference maximum, P^T row -> smem
+//   tcgen05  : C^T[128 columns x 32 heads] += tile^T (A, MN-major: the SAME smem bytes) x P^T (B)    -> TMEM,
+//              d / 128 accumulators; each stage is freed by the commit of the MMAs that read it
+// and writes c_h = C^T[:, h] / l_h.  (A first version split d over a 5-CTA cluster and exchanged partial scores
+// through DSMEM: 1.39 TB/s of source bytes, bound by the per-tile exchange chain; git 5357dfb.)
 #include "common.cuh"
 #include "kernels.h"
 
 namespace wf {
 
-static constexpr int LA_KEYS = 128;                 // keys per tile
-static constexpr int LA_DS = 256;                   // latent columns per CTA
-static constexpr int LA_CH = LA_DS / 64;            // 64-column swizzle atoms (chunks) per tile slice
-static constexpr int LA_NH = 32;                    // head columns of both MMAs (H <= 32; unused ones are ignored)
-static constexpr int LA_HPC = LA_DS / 64;           // heads whose softmax a CTA owns (head_dim 64 => H = 4 CS)
-static constexpr int LA_MAX_CS = 5;                 // d <= 1280
-static constexpr int LA_CHUNK = LA_KEYS * 128;      // 16 KB
-static constexpr int LA_STAGE = LA_CH * LA_CHUNK;   // 64 KB
-static constexpr int LA_STAGES = 2;
-static constexpr int LA_QCH = LA_NH * 128;          // 4 KB: one K-major atom of q' (and of P^T)
-static constexpr int LA_OFF_Q = LA_STAGES * LA_STAGE;
-static constexpr int LA_OFF_PO = LA_OFF_Q + LA_CH * LA_QCH;
-static constexpr int LA_PO = 2 * LA_QCH;            // P^T operand [32 heads x 128 keys] = two atoms of 64 keys
-static constexpr int LA_OFF_PI = LA_OFF_PO + 2 * LA_PO;
-static constexpr int LA_PI = LA_NH * LA_KEYS * 2;   // P^T landing buffer (plain [head][key] bf16), filled by the owners
-static constexpr int LA_OFF_XS = LA_OFF_PI + 2 * LA_PI;
-static constexpr int LA_XS = LA_MAX_CS * LA_HPC * LA_KEYS * 4;  // partial scores [source CTA][own head][key] fp32
-static constexpr int LA_OFF_AL = LA_OFF_XS + 2 * LA_XS;         // alpha [2][32] | 1/l [32] | red [3][4 warps][4] fp32
-static constexpr int LA_OFF_BAR = LA_OFF_AL + 1024;
-static constexpr int LA_SMEM = LA_OFF_BAR + 256 + 1024;
-static constexpr int LA_TMEM_COLS = 128;            // S^T(0) S^T(1) C^T(rows 0..127) C^T(rows 128..255), 32 each
+static constexpr int LA_KT = 32;                    // keys per tile
+static constexpr int LA_CHUNK = LA_KT * 128;        // 4 KB: [32 keys x 64 columns] bf16, 128B-swizzled = one TMA box
+static constexpr int LA_STAGE = 2 * LA_CHUNK;       // 8 KB: 128 columns = the A operand of one context accumulator
+static constexpr int LA_NH = 32;                    // head columns of the context MMAs (H <= 32)
+static constexpr int LA_PT = LA_NH * 128;           // P^T operand: 32 rows (heads) x 128 B (64 keys; 32 used)
+static constexpr int LA_MISC = 2048;                // alpha [2][32] | 1/l [32] | flags [2][2] | barriers
+static constexpr int LA_MAX_STAGES = 28;
+static constexpr int LA_SMEM_LIMIT = 227 * 1024;
+static constexpr int LA_TMEM_COLS = 512;            // S (2 x 32) | C^T (d / 128 accumulators x 32)
+static constexpr int LA_TMEM_C = 2 * LA_KT;
 static constexpr int LA_THREADS = 256;
 
-__device__ __forceinline__ void la_cluster_sync() {
-  asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t la_mapa(uint32_t local_smem_addr, uint32_t cta) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta));
-  return r;
-}
-__device__ __forceinline__ void la_st_f32(uint32_t cluster_addr, float v) {
-  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
-}
-__device__ __forceinline__ void la_st_u16(uint32_t cluster_addr, uint16_t v) {
-  asm volatile("st.shared::cluster.u16 [%0], %1;" ::"r"(cluster_addr), "h"(v) : "memory");
-}
-__device__ __forceinline__ void la_arrive_remote(uint32_t cluster_bar_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
-}
-__device__ __forceinline__ void la_fence_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
-__device__ __forceinline__ void la_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
-__device__ __forceinline__ bool la_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+// non-blocking probe (mbarrier.try_wait may suspend the thread for a system-dependent time when the phase is still
+// open, which a thread that polls two barriers cannot afford)
+__device__ __forceinline__ bool la_test_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
   return ok != 0;
 }
-// wait for arrivals made by OTHER CTAs of the cluster (their st.shared::cluster data must be visible afterwards)
-__device__ __forceinline__ void la_wait_cluster(uint64_t* bar, uint32_t parity) {
-  if (la_try_wait_cluster(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!la_try_wait_cluster(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("libwf: cluster mbarrier wait timeout (block %d,%d thread %d parity %u)\n", blockIdx.x, blockIdx.y,
-             threadIdx.x, parity);
-      __trap();
-    }
-  }
-}
-
-__device__ __forceinline__ void la_st_v4(uint32_t cluster_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "r"(a), "r"(b), "r"(c), "r"(d)
-               : "memory");
-}
-__device__ __forceinline__ void la_st_v2(uint32_t cluster_addr, uint32_t a, uint32_t b) {
-  asm volatile("st.shared::cluster.v2.b32 [%0], {%1, %2};" ::"r"(cluster_addr), "r"(a), "r"(b) : "memory");
-}
-
-// -DLA_TIMING: thread 128 of block (0, 0) accumulates the cycles of each phase of its per-tile chain and prints them
-#ifdef LA_TIMING
-#define LA_TICK0() long long la_t = clock64()
-#define LA_TICKW() do { const long long n_ = clock64(); la_acc[6] += n_ - la_t; la_t = n_; } while (0)
-#define LA_TICK(i) do { const long long n_ = clock64(); la_acc[i] += n_ - la_t; la_t = n_; } while (0)
-#define LA_REPORT()                                                                                                 \
-  if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0)                                                               \
-    printf("latent chain cycles/tile: wait_s %lld | ld+push_xs %lld | wait_xs %lld | softmax+push_p %lld | wait_pb " \
-           "%lld | stage+rescale %lld | (ld..tick0 %lld) tiles %d\n", la_acc[6] / n_tiles, la_acc[1] / n_tiles,      \
-           la_acc[2] / n_tiles, la_acc[3] / n_tiles, la_acc[4] / n_tiles, la_acc[5] / n_tiles, la_acc[0] / n_tiles,  \
-           n_tiles)
-#else
-#define LA_TICK0()
-#define LA_TICKW()
-#define LA_TICK(i)
-#define LA_REPORT()
-#endif
+__device__ __forceinline__ void la_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
 // bf16 x bf16 -> fp32, A MN-major (bit 15), B K-major
 __host__ __device__ constexpr uint32_t la_idesc_a_mn(int M, int N) { return umma_idesc_bf16(M, N) | (1u << 15); }
+// MN-major operand, 128B swizzle: rows = K index (128 B = 64 MN elements each), 8-row groups 1024 B apart (SBO),
+// the next 64 MN elements one 4 KB chunk further (LBO)
+__device__ __forceinline__ uint64_t la_desc_mn(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu);
+  d |= static_cast<uint64_t>(LA_CHUNK >> 4) << 16;
+  d |= static_cast<uint64_t>(1024u >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
 
 __global__ void __launch_bounds__(LA_THREADS, 1)
 latent_attn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_q,
-                   __nv_bfloat16* __restrict__ ctx, int T, int H, int CS, float sl2) {
+                   __nv_bfloat16* __restrict__ ctx, int T, int H, int HP, int NS, int NST, float sl2) {
   extern __shared__ uint8_t smem_raw[];
-  // the dynamic shared window starts at the same offset in every CTA of the cluster, so the aligned base does too
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + LA_OFF_BAR);
-  uint64_t* q_full = bars;             // [1]
-  uint64_t* st_full = bars + 1;        // [2]  tile slice landed
-  uint64_t* st_empty = bars + 3;       // [2]  C^T MMAs of the tile have read it
-  uint64_t* s_full = bars + 5;         // [2]  S^T_partial(j) in TMEM
-  uint64_t* s_free = bars + 7;         // [2]  ... read into registers (128 arrivals)
-  uint64_t* xs_full = bars + 9;        // [2]  partial scores of my heads arrived from all CS CTAs
-  uint64_t* pb_full = bars + 11;       // [2]  P^T rows + alpha of all heads arrived from all CS owners
-  uint64_t* p_ready = bars + 13;       // [2]  P^T operand staged, C^T rescaled (128 arrivals)
-  uint64_t* c_done = bars + 15;        // [2]  C^T MMAs of the tile completed
-  uint64_t* fin_full = bars + 17;      // [1]  1 / l of all heads arrived
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  uint8_t* ring = smem;                              // NST stages of [32 keys x 128 columns]
+  uint8_t* qs = ring + NST * LA_STAGE;               // q': d / 64 K-major atoms of HP rows (heads)
+  const int q_atom = HP * 128;
+  uint8_t* pt = qs + 2 * NS * q_atom;                // P^T operand, double-buffered
+  uint8_t* misc = pt + 2 * LA_PT;
+  float* al_buf = reinterpret_cast<float*>(misc);    // [2][32] rescale factor of each head for the tile
+  float* linv_buf = al_buf + 64;                     // [32]
+  int* flag_buf = reinterpret_cast<int*>(al_buf + 96);   // [2][2] "some head of this warp moved its reference maximum"
+  uint64_t* bars = reinterpret_cast<uint64_t*>(misc + 512);
+  uint64_t* full = bars;                             // [NST] stage landed
+  uint64_t* empty = bars + LA_MAX_STAGES;            // [NST] the context MMAs that read the stage completed
+  uint64_t* q_full = bars + 2 * LA_MAX_STAGES;
+  uint64_t* s_full = q_full + 1;                     // [2] scores of a tile in TMEM
+  uint64_t* s_free = s_full + 2;                     // [2] ... copied to registers (64 arrivals)
+  uint64_t* p_ready = s_free + 2;                    // [2] P^T staged, C^T rescaled (128 arrivals)
+  uint64_t* c_done = p_ready + 2;                    // [2] context MMAs of a tile completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(c_done + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int r = blockIdx.x;            // rank in the cluster (cluster = the CS CTAs along x) = latent slice
-  const int b = blockIdx.y;            // clip
-  const int n_tiles = (T + LA_KEYS - 1) / LA_KEYS;
-  const int d = CS * LA_DS;
+  const int b = blockIdx.x;                          // clip
+  const int n_tiles = (T + LA_KT - 1) / LA_KT;
+  const int d = NS * 128;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_x);
     tma_prefetch_desc(&map_q);
   }
   if (warp == 1 && lane == 0) {
+    for (int i = 0; i < NST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&st_full[i], 1); mbar_init(&st_empty[i], 1); mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 128);
-      mbar_init(&xs_full[i], CS); mbar_init(&pb_full[i], CS); mbar_init(&p_ready[i], 128); mbar_init(&c_done[i], 1);
+      mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 64); mbar_init(&p_ready[i], 128); mbar_init(&c_done[i], 1);
     }
-    mbar_init(fin_full, CS);
     mbar_fence_init();
   }
   if (warp == 2) tmem_alloc<LA_TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  la_cluster_sync();   // every CTA's barriers exist before anyone arrives on them remotely
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------------ TMA producer
-    mbar_arrive_expect_tx(q_full, LA_CH * LA_QCH);
-    for (int c = 0; c < LA_CH; ++c)
-      tma_load_2d(smem + LA_OFF_Q + c * LA_QCH, &map_q, q_full, r * LA_DS + c * 64, b * H);
-    for (int j = 0; j < n_tiles; ++j) {
-      const int st = j & 1;
-      mbar_wait(&st_empty[st], ((j >> 1) & 1) ^ 1);
-      mbar_arrive_expect_tx(&st_full[st], LA_STAGE);
-      for (int c = 0; c < LA_CH; ++c)
-        tma_load_2d(smem + st * LA_STAGE + c * LA_CHUNK, &map_x, &st_full[st], r * LA_DS + c * 64, b * T + j * LA_KEYS);
+    const long long total = static_cast<long long>(n_tiles) * NS;
+    int slot = 0, s = 0, j = 0;
+    uint32_t phase = 0;
+    bool q_sent = false;
+    for (long long g = 0; g < total; ++g) {
+      if (g == NST && !q_sent) {
+        // the source rows are static, q' comes from the previous kernel: the first ring-full is requested before the
+        // dependency wait
+        pdl_wait();
+        mbar_arrive_expect_tx(q_full, 2 * NS * q_atom);
+        for (int c = 0; c < 2 * NS; ++c) tma_load_2d(qs + c * q_atom, &map_q, q_full, c * 64, b * H);
+        q_sent = true;
+      }
+      mbar_wait(&empty[slot], phase ^ 1);
+      mbar_arrive_expect_tx(&full[slot], LA_STAGE);
+      tma_load_2d(ring + slot * LA_STAGE, &map_x, &full[slot], s * 128, b * T + j * LA_KT);
+      tma_load_2d(ring + slot * LA_STAGE + LA_CHUNK, &map_x, &full[slot], s * 128 + 64, b * T + j * LA_KT);
+      if (++s == NS) { s = 0; ++j; }
+      if (++slot == NST) { slot = 0; phase ^= 1; }
+    }
+    if (!q_sent) {
+      pdl_wait();
+      mbar_arrive_expect_tx(q_full, 2 * NS * q_atom);
+      for (int c = 0; c < 2 * NS; ++c) tma_load_2d(qs + c * q_atom, &map_q, q_full, c * 64, b * H);
     }
   } else if (warp == 1 && lane == 0) {
     // ------------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc_s = umma_idesc_bf16(LA_KEYS, LA_NH);    // S^T = tile q'^T : both K-major
-    constexpr uint32_t idesc_c = la_idesc_a_mn(128, LA_NH);          // C^T += tile^T P^T : A MN-major
-    auto issue_s = [&](int j) {
-      const int st = j & 1;
-#pragma unroll
-      for (int c = 0; c < LA_CH; ++c) {
-        const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(smem + st * LA_STAGE + c * LA_CHUNK));
-        const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(smem + LA_OFF_Q + c * LA_QCH));
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16(tmem_base + st * LA_NH, a_desc + 2 * k, b_desc + 2 * k, idesc_s, (c | k) != 0);
-      }
-      umma_commit(&s_full[st]);
-    };
-    auto issue_c = [&](int j) {
-      const int st = j & 1;
-      const uint32_t po = smem_u32(smem + LA_OFF_PO + st * LA_PO);
-#pragma unroll
-      for (int mb = 0; mb < 2; ++mb) {
-        const uint32_t a_addr = smem_u32(smem + st * LA_STAGE + 2 * mb * LA_CHUNK);
-#pragma unroll
-        for (int kk = 0; kk < LA_KEYS / 16; ++kk) {
-          // A: 16 keys (two 8-row groups of 1024 B) x 128 latent columns (two 64-column atoms, LBO = one chunk)
-          const uint64_t a_desc = umma_desc_mnmajor_sw128(a_addr + kk * 2048);
-          const uint64_t b_desc = umma_desc_kmajor_sw128(po + (kk >> 2) * LA_QCH) + 2 * (kk & 3);
-          umma_f16(tmem_base + 2 * LA_NH + mb * LA_NH, a_desc, b_desc, idesc_c, (j > 0 || kk > 0) ? 1u : 0u);
-        }
-      }
-      umma_commit(&st_empty[st]);
-      umma_commit(&c_done[st]);
-    };
+    // scores  S[heads (64 rows, H valid) x 32 keys] = q' (A) x stage^T (B), both K-major, K = d in 16-column steps;
+    // context C^T[128 columns x 32 heads] (+)= stage^T (A, MN-major: the same bytes) x P^T (B, K-major), K = 32 keys.
+    // One stage of scores work is issued whenever its bytes have landed; a tile's context MMAs as soon as its P^T is
+    // staged (they free the ring, so they go first).
+#if defined(LA_EXP) && LA_EXP == 4
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, LA_KT);
+#else
+    constexpr uint32_t idesc_s = umma_idesc_bf16(64, LA_KT);
+#endif
+    constexpr uint32_t idesc_c = la_idesc_a_mn(128, LA_NH);
+    const uint32_t ring_a = smem_u32(ring), qs_a = smem_u32(qs), pt_a = smem_u32(pt);
+    int sj = 0, ss = 0, s_slot = 0, cj = 0, c_slot = 0;
+    uint32_t s_phase = 0;
     mbar_wait(q_full, 0);
-    for (int j = 0; j <= n_tiles; ++j) {
-      bool need_s = j < n_tiles, need_c = j > 0;
-      const long long t0 = clock64();
-      while (need_s || need_c) {
-        if (need_c && mbar_try_wait(&p_ready[(j - 1) & 1], ((j - 1) >> 1) & 1)) {
-          tc_fence_after();
-          issue_c(j - 1);
-          need_c = false;
+    long long t0 = clock64();
+    while (cj < n_tiles) {
+      bool progressed = false;
+      if (la_test_wait(&p_ready[cj & 1], (cj >> 1) & 1)) {
+        tc_fence_after();
+        const uint32_t pb = pt_a + (cj & 1) * LA_PT;
+        for (int a = 0; a < NS; ++a) {
+          const uint32_t st = ring_a + c_slot * LA_STAGE;
+#pragma unroll
+          for (int kk = 0; kk < LA_KT / 16; ++kk)
+#if defined(LA_EXP) && (LA_EXP == 1 || LA_EXP == 3)
+            if (a < 0)
+#endif
+            umma_f16(tmem_base + LA_TMEM_C + a * LA_NH, la_desc_mn(st + kk * 2048), umma_desc_kmajor_sw128(pb) + 2 * kk,
+                     idesc_c, (cj > 0 || kk > 0) ? 1u : 0u);
+          umma_commit(&empty[c_slot]);
+          if (++c_slot == NST) c_slot = 0;
         }
-        if (need_s && mbar_try_wait(&st_full[j & 1], (j >> 1) & 1) &&
-            (j < 2 || mbar_try_wait(&s_free[j & 1], ((j >> 1) - 1) & 1))) {
-          tc_fence_after();
-          issue_s(j);
-          need_s = false;
+        umma_commit(&c_done[cj & 1]);
+        ++cj;
+        progressed = true;
+      }
+      if (sj < n_tiles && la_test_wait(&full[s_slot], s_phase) &&
+          (ss != 0 || sj < 2 || la_test_wait(&s_free[sj & 1], ((sj >> 1) - 1) & 1))) {
+        tc_fence_after();
+        const uint32_t st = ring_a + s_slot * LA_STAGE;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const uint64_t a_desc = umma_desc_kmajor_sw128(qs_a + (2 * ss + c) * q_atom);
+          const uint64_t b_desc = umma_desc_kmajor_sw128(st + c * LA_CHUNK);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+#if defined(LA_EXP) && (LA_EXP == 2 || LA_EXP == 3)
+            if ((c | k) == 0)
+#endif
+            umma_f16(tmem_base + (sj & 1) * LA_KT, a_desc + 2 * k, b_desc + 2 * k, idesc_s, (ss | c | k) != 0);
         }
-        if (clock64() - t0 > 4000000000LL) {
-          printf("libwf: latent attention MMA issuer timeout (block %d,%d tile %d need_s %d need_c %d)\n", blockIdx.x,
-                 blockIdx.y, j, int(need_s), int(need_c));
-          __trap();
+        if (++ss == NS) {
+          umma_commit(&s_full[sj & 1]);
+          ss = 0;
+          ++sj;
         }
+        if (++s_slot == NST) { s_slot = 0; s_phase ^= 1; }
+        progressed = true;
+      }
+      if (progressed) {
+        t0 = clock64();
+      } else if (clock64() - t0 > 4000000000LL) {
+        printf("libwf: latent attention MMA issuer timeout (block %d scores tile %d stage %d, context tile %d)\n",
+               blockIdx.x, sj, ss, cj);
+        __trap();
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ softmax (thread = key = TMEM lane)
+    // ------------------------------------------------------------------ softmax (thread = head = TMEM lane of S)
+    const int wq = warp - 4;
     const int tid = threadIdx.x - 128;
-    const int qd = warp - 4;
-    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16);
-    uint32_t rb[8];                                                   // my smem base as seen in CTA c's window
-#pragma unroll
-    for (int c = 0; c < 8; ++c) rb[c] = la_mapa(smem_u32(smem), c < CS ? c : 0);
-    float* al_buf = reinterpret_cast<float*>(smem + LA_OFF_AL);       // [2][32]
-    float* linv_buf = al_buf + 64;                                    // [32]
-    float* red = al_buf + 96;                                         // [3][4][4]
-    float m_run[LA_HPC], l_part[LA_HPC];
-#ifdef LA_TIMING
-    long long la_acc[7] = {0, 0, 0, 0, 0, 0, 0};
-#endif
-#pragma unroll
-    for (int i = 0; i < LA_HPC; ++i) { m_run[i] = -INFINITY; l_part[i] = 0.f; }
-
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
+    // a 64-row accumulator keeps rows 16 q .. 16 q + 15 in lanes 32 q .. 32 q + 15 (profiles/r01_probe_tmem_m64_layout)
+    const int head = wq * 16 + lane;
+    const bool act = wq < 2 && lane < 16 && head < H;
+    float m_ref = -INFINITY, l_run = 0.f;
+    pdl_wait();
     for (int j = 0; j < n_tiles; ++j) {
       const int buf = j & 1;
       const uint32_t ph = (j >> 1) & 1;
-      LA_TICK0();
-      mbar_wait(&s_full[buf], ph);
-      tc_fence_after();
-      LA_TICKW();
-      uint32_t sv[32];
-      tmem_ld_32x32(lane_addr + buf * LA_NH, sv);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(&s_free[buf]);
-      LA_TICK(0);
-      // ---- partial scores of heads 4c .. 4c+3 -> their owner CTA c, slot [my rank][key][4] (one 16-byte store each)
-      {
-        const uint32_t xoff = LA_OFF_XS + buf * LA_XS + (r * LA_KEYS + tid) * 16;
+      uint32_t pk[LA_KT / 2];
+      if (wq < 2) {
+        mbar_wait(&s_full[buf], ph);
+        tc_fence_after();
+        uint32_t sv[32];
+        tmem_ld_32x32(lane_base + buf * LA_KT, sv);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&s_free[buf]);
+        const int nv = min(LA_KT, T - j * LA_KT);
+        float mt = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < LA_MAX_CS; ++c)
-          if (c < CS) la_st_v4(rb[c] + xoff, sv[4 * c], sv[4 * c + 1], sv[4 * c + 2], sv[4 * c + 3]);
-      }
-      la_fence_cluster();
-      la_bar(1);
-      if (tid == 0)
-        for (int c = 0; c < CS; ++c) la_arrive_remote(la_mapa(smem_u32(&xs_full[buf]), c));
-      LA_TICK(1);
-      la_wait_cluster(&xs_full[buf], ph);
-      LA_TICK(2);
-      // ---- owner: full scores of my 4 heads for this key, running max over the tile's 128 keys
-      const float4* xs = reinterpret_cast<const float4*>(smem + LA_OFF_XS + buf * LA_XS);
-      const bool valid = j * LA_KEYS + tid < T;
-      float s[LA_HPC] = {0.f, 0.f, 0.f, 0.f};
-      for (int c = 0; c < CS; ++c) {
-        const float4 v = xs[c * LA_KEYS + tid];
-        s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
-      }
-#pragma unroll
-      for (int hh = 0; hh < LA_HPC; ++hh) {
-        const float mt = warp_max(valid ? s[hh] : -INFINITY);
-        if (lane == 0) red[(buf * 4 + qd) * 4 + hh] = mt;
-      }
-      la_bar(2);
-      float alpha[LA_HPC], p[LA_HPC];
-#pragma unroll
-      for (int hh = 0; hh < LA_HPC; ++hh) {
-        float mt = fmaxf(fmaxf(red[(buf * 4 + 0) * 4 + hh], red[(buf * 4 + 1) * 4 + hh]),
-                         fmaxf(red[(buf * 4 + 2) * 4 + hh], red[(buf * 4 + 3) * 4 + hh]));
-        const float m_new = fmaxf(m_run[hh], mt);
-        alpha[hh] = ex2_approx((m_run[hh] - m_new) * sl2);            // 0 on the first tile
-        p[hh] = valid ? ex2_approx((s[hh] - m_new) * sl2) : 0.f;
-        m_run[hh] = m_new;
-      }
-      const uint32_t p01 = pack_bf16(p[0], p[1]), p23 = pack_bf16(p[2], p[3]);
-      l_part[0] = l_part[0] * alpha[0] + bf16lo(p01);                 // the sums the tensor core will see
-      l_part[1] = l_part[1] * alpha[1] + bf16hi(p01);
-      l_part[2] = l_part[2] * alpha[2] + bf16lo(p23);
-      l_part[3] = l_part[3] * alpha[3] + bf16hi(p23);
-      // ---- push p (bf16, [owner][key][4 heads]: one 8-byte store) and alpha of my heads to every CTA of the cluster
-      {
-        const uint32_t poff = LA_OFF_PI + buf * LA_PI + (r * LA_KEYS + tid) * 8;
-#pragma unroll
-        for (int c = 0; c < LA_MAX_CS; ++c)
-          if (c < CS) la_st_v2(rb[c] + poff, p01, p23);
-        if (tid < LA_HPC * CS) {
-          const int hh = tid & 3, c = tid >> 2;
-          const float a = hh == 0 ? alpha[0] : hh == 1 ? alpha[1] : hh == 2 ? alpha[2] : alpha[3];
-          la_st_f32(la_mapa(smem_u32(smem + LA_OFF_AL + (buf * 32 + r * LA_HPC + hh) * 4), c), a);
+        for (int i = 0; i < LA_KT; ++i) {
+          const float s = i < nv ? __uint_as_float(sv[i]) : -INFINITY;
+          sv[i] = __float_as_uint(s);
+          mt = fmaxf(mt, s);
         }
-      }
-      la_fence_cluster();
-      la_bar(1);
-      if (tid == 0)
-        for (int c = 0; c < CS; ++c) la_arrive_remote(la_mapa(smem_u32(&pb_full[buf]), c));
-      LA_TICK(3);
-      la_wait_cluster(&pb_full[buf], ph);
-      LA_TICK(4);
-      // ---- stage P^T as the K-major swizzled B operand [32 heads x 128 keys]: unit = (owner c, 8 keys) = 64 bytes in,
-      //      four 16-byte rows (one per head) out
-      if (tid < CS * 16) {
-        const int c = tid >> 4, g = tid & 15;
-        const uint4* pi = reinterpret_cast<const uint4*>(smem + LA_OFF_PI + buf * LA_PI + (c * LA_KEYS + g * 8) * 8);
-        const uint4 v0 = pi[0], v1 = pi[1], v2 = pi[2], v3 = pi[3];     // key k: (h0 h1 | h2 h3), two keys per uint4
-        uint8_t* po = smem + LA_OFF_PO + buf * LA_PO + (g >> 3) * LA_QCH;
-        const uint32_t lo[8] = {v0.x, v0.z, v1.x, v1.z, v2.x, v2.z, v3.x, v3.z};
-        const uint32_t hi[8] = {v0.y, v0.w, v1.y, v1.w, v2.y, v2.w, v3.y, v3.w};
-#pragma unroll
-        for (int hh = 0; hh < LA_HPC; ++hh) {
-          const int h = c * LA_HPC + hh;
-          const uint32_t sel = (hh & 1) ? 0x7632u : 0x5410u;
-          uint4 o;
-          if (hh < 2) {
-            o.x = __byte_perm(lo[0], lo[1], sel); o.y = __byte_perm(lo[2], lo[3], sel);
-            o.z = __byte_perm(lo[4], lo[5], sel); o.w = __byte_perm(lo[6], lo[7], sel);
-          } else {
-            o.x = __byte_perm(hi[0], hi[1], sel); o.y = __byte_perm(hi[2], hi[3], sel);
-            o.z = __byte_perm(hi[4], hi[5], sel); o.w = __byte_perm(hi[6], hi[7], sel);
-          }
-          *reinterpret_cast<uint4*>(po + h * 128 + (((g & 7) ^ (h & 7)) << 4)) = o;
+        // the reference maximum only moves when a tile exceeds it by more than 2^8 (p stays <= 256: exact enough in
+        // bf16 / fp32), so the context accumulators are almost never rescaled
+        float alpha = 1.f;
+        bool need = false;
+        if (j == 0) {
+          m_ref = mt;
+        } else if ((mt - m_ref) * sl2 > 8.f) {
+          alpha = ex2_approx((m_ref - mt) * sl2);
+          m_ref = mt;
+          need = act;
         }
+        const float mb = m_ref * sl2;
+        float lsum = 0.f;
+#pragma unroll
+        for (int i = 0; i < LA_KT / 2; ++i) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(sv[2 * i]), sl2, -mb));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(sv[2 * i + 1]), sl2, -mb));
+          pk[i] = pack_bf16(p0, p1);
+          lsum += bf16lo(pk[i]) + bf16hi(pk[i]);      // the sums the tensor core will see
+        }
+        l_run = l_run * alpha + lsum;
+        if (act) al_buf[buf * 32 + head] = alpha;
+        const bool any = __any_sync(0xffffffffu, need);
+        if (lane == 0) flag_buf[buf * 2 + wq] = any ? 1 : 0;
       }
-      // ---- C^T *= alpha (column h), only when some head moved its maximum; C^T MMAs of tile j-1 must be complete
-      if (j > 0) {
-        bool any = false;
-        for (int h = 0; h < H; ++h) any = any || (al_buf[buf * 32 + h] != 1.0f);
+      la_bar(1);
+      const bool rescale = (flag_buf[buf * 2] | flag_buf[buf * 2 + 1]) != 0;
+      if (j >= 2) mbar_wait(&c_done[buf], ((j - 2) >> 1) & 1);     // P^T[buf] is no longer read by tile j - 2
+      if (rescale) {
         mbar_wait(&c_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
         tc_fence_after();
-        if (any) {
+        for (int a = 0; a < NS; ++a) {
+          uint32_t cv[32];
+          tmem_ld_32x32(lane_base + LA_TMEM_C + a * LA_NH, cv);
+          tmem_ld_wait();
 #pragma unroll
-          for (int mb = 0; mb < 2; ++mb) {
-            uint32_t cv[32];
-            tmem_ld_32x32(lane_addr + 2 * LA_NH + mb * LA_NH, cv);
-            tmem_ld_wait();
-#pragma unroll
-            for (int h = 0; h < LA_NH; ++h)
-              if (h < H) cv[h] = __float_as_uint(__uint_as_float(cv[h]) * al_buf[buf * 32 + h]);
-            tmem_st_32x32(lane_addr + 2 * LA_NH + mb * LA_NH, cv);
-          }
-          tmem_st_wait();
+          for (int h = 0; h < LA_NH; ++h)
+            if (h < H) cv[h] = __float_as_uint(__uint_as_float(cv[h]) * al_buf[buf * 32 + h]);
+          tmem_st_32x32(lane_base + LA_TMEM_C + a * LA_NH, cv);
         }
+        tmem_st_wait();
+      }
+      if (act) {
+        uint8_t* row = pt + buf * LA_PT + head * 128;
+#pragma unroll
+        for (int u = 0; u < LA_KT / 8; ++u)
+          *reinterpret_cast<uint4*>(row + ((u ^ (head & 7)) << 4)) =
+              make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
       }
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&p_ready[buf]);
-      LA_TICK(5);
     }
-    LA_REPORT();
-    // ---- 1 / l of my heads -> every CTA
-    {
-      float l[LA_HPC];
-#pragma unroll
-      for (int hh = 0; hh < LA_HPC; ++hh) {
-        const float v = warp_sum(l_part[hh]);
-        if (lane == 0) red[(2 * 4 + qd) * 4 + hh] = v;
-      }
-      la_bar(2);
-#pragma unroll
-      for (int hh = 0; hh < LA_HPC; ++hh)
-        l[hh] = (red[(2 * 4 + 0) * 4 + hh] + red[(2 * 4 + 1) * 4 + hh]) + (red[(2 * 4 + 2) * 4 + hh] + red[(2 * 4 + 3) * 4 + hh]);
-      if (tid < LA_HPC * CS) {
-        const int hh = tid & 3, c = tid >> 2;
-        const float v = hh == 0 ? l[0] : hh == 1 ? l[1] : hh == 2 ? l[2] : l[3];
-        la_st_f32(la_mapa(smem_u32(smem + LA_OFF_AL + (64 + r * LA_HPC + hh) * 4), c), 1.0f / v);
-      }
-      la_fence_cluster();
-      la_bar(1);
-      if (tid == 0)
-        for (int c = 0; c < CS; ++c) la_arrive_remote(la_mapa(smem_u32(fin_full), c));
-      la_wait_cluster(fin_full, 0);
-    }
-    // ---- epilogue: c_h[256 r + 128 mb + tid] = C^T[row][h] / l_h  (thread = latent column, coalesced over the warp)
+    if (act) linv_buf[head] = 1.0f / l_run;
+    la_bar(1);
+    // ---- epilogue: ctx[b, h, 128 a + tid] = C^T[a][tid][h] / l_h   (thread = latent column)
     mbar_wait(&c_done[(n_tiles - 1) & 1], ((n_tiles - 1) >> 1) & 1);
     tc_fence_after();
-#pragma unroll
-    for (int mb = 0; mb < 2; ++mb) {
+    for (int a = 0; a < NS; ++a) {
       uint32_t cv[32];
-      tmem_ld_32x32(lane_addr + 2 * LA_NH + mb * LA_NH, cv);
+      tmem_ld_32x32(lane_base + LA_TMEM_C + a * LA_NH, cv);
       tmem_ld_wait();
-      __nv_bfloat16* out = ctx + static_cast<long long>(b) * H * d + r * LA_DS + mb * 128 + tid;
+      __nv_bfloat16* out = ctx + static_cast<long long>(b) * H * d + a * 128 + tid;
 #pragma unroll
       for (int h = 0; h < LA_NH; ++h)
         if (h < H) out[static_cast<long long>(h) * d] = __float2bfloat16_rn(__uint_as_float(cv[h]) * linv_buf[h]);
@@ -419,7 +311,6 @@ latent_attn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 
   tc_fence_before();
   __syncthreads();
-  la_cluster_sync();   // no CTA leaves (and frees its shared memory) while a peer may still store into it
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<LA_TMEM_COLS>(tmem_base);
@@ -428,34 +319,27 @@ latent_attn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 
 int latent_attention(const void* qp, const void* src, void* ctx, int B, int T, int H, cudaStream_t stream) {
   const int d = H * 64;
-  WF_REQUIRE(B > 0 && T > 0 && H > 0 && d % LA_DS == 0 && d / LA_DS <= LA_MAX_CS,
-             "latent attention: needs head_dim 64 and n_state in {256, 512, 768, 1024, 1280} (got %d heads)", H);
-  const int cs = d / LA_DS;
+  WF_REQUIRE(B > 0 && T > 0 && H > 0 && H <= LA_NH && d % 128 == 0,
+             "latent attention: needs head_dim 64, an even number of heads and at most 32 of them (got %d heads)", H);
+  const int hp = (H + 7) / 8 * 8, ns = d / 128;
+  const int fixed = 1024 + 2 * ns * hp * 128 + 2 * LA_PT + LA_MISC;
+  int nst = (LA_SMEM_LIMIT - fixed) / LA_STAGE;
+  if (nst > LA_MAX_STAGES) nst = LA_MAX_STAGES;
+  WF_REQUIRE(nst > ns, "latent attention: the stage ring (%d) must hold more than one tile (%d stages)", nst, ns);
+  const int smem = fixed + nst * LA_STAGE;
   CUtensorMap mx, mq;
-  int rc = make_map_bf16(&mx, src, static_cast<long long>(B) * T, d, d, LA_KEYS);
+  int rc = make_map_bf16(&mx, src, static_cast<long long>(B) * T, d, d, LA_KT);
   if (rc) return rc;
-  rc = make_map_bf16(&mq, qp, static_cast<long long>(B) * H, d, d, LA_NH);
+  rc = make_map_bf16(&mq, qp, static_cast<long long>(B) * H, d, d, hp);
   if (rc) return rc;
   static bool configured = false;
   if (!configured) {
-    WF_CHECK_CUDA(cudaFuncSetAttribute(latent_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LA_SMEM));
+    WF_CHECK_CUDA(cudaFuncSetAttribute(latent_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LA_SMEM_LIMIT));
     configured = true;
   }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(cs, B);
-  cfg.blockDim = dim3(LA_THREADS);
-  cfg.dynamicSmemBytes = LA_SMEM;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = cs;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
   const float sl2 = 0.125f * 1.44269504088896340736f;   // 64^-0.5 * log2(e)
-  WF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, latent_attn_kernel, mx, mq, reinterpret_cast<__nv_bfloat16*>(ctx), T, H, cs,
-                                   sl2));
+  WF_CHECK_CUDA(launch_pdl(2, latent_attn_kernel, dim3(B), dim3(LA_THREADS), static_cast<size_t>(smem), stream, mx, mq,
+                           reinterpret_cast<__nv_bfloat16*>(ctx), T, H, hp, ns, nst, sl2));
   count_launch();
   return WF_OK;
 }
