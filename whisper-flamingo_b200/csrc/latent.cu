@@ -14,33 +14,39 @@
 //   latent_attn_kernel   q', src  -> c  [R, H, d]         (tcgen05 + TMA + thread-block cluster, below)
 //   latent_value_kernel  c -> o [R, d]                    (per head a [R,d] x [d,64] GEMM + bias, mma.sync)
 //
-// latent_attn_kernel: one CTA per clip, the whole latent width d in the CTA, 32-key tiles (a tile = 32 contiguous
-// source rows = d / 128 ring stages of [32 keys x 128 columns], loaded by TMA exactly once, ring of ~1.9 tiles):
-//   tcgen05  : S[64 rows (heads) x 32 keys] = q' (A, K-major, resident) x tile^T (B, K-major)        -> TMEM
-//   softmax  : thread = head (its 32 scores in registers, no shuffles), lazy reference maximum, P^T row -> smem
-//   tcgen05  : C^T[128 columns x 32 heads] += tile^T (A, MN-major: the SAME smem bytes) x P^T (B)    -> TMEM,
-//              d / 128 accumulators; each stage is freed by the commit of the MMAs that read it
-// and writes c_h = C^T[:, h] / l_h.  (A first version split d over a 5-CTA cluster and exchanged partial scores
-// through DSMEM: 1.39 TB/s of source bytes, bound by the per-tile exchange chain; git 5357dfb.)
+// latent_attn_kernel: one CTA per clip, the whole latent width d in the CTA, 128-key tiles, TWO passes over each tile
+// (a tile is 128 keys x d = 320 KB at d = 1280: it cannot stay in shared memory between the scores and the context
+// product; narrower tiles, a d-split over a cluster and scores on tcgen05 were all measured slower - git history).
+// The second pass finds the tile in L2 (one TMA thread requests A(j) | B(j) | A(j+1) ... in that order, first-pass
+// loads carry an evict_last hint, second-pass loads evict_first), so HBM sees every source row once.
+//   pass A  TMA chunks [128 keys x 64 columns] (ring A) -> four warps, 32 keys each: S^T[keys x heads] += chunk x q'^T
+//           with mma.sync m16n8k16 (ldmatrix from the 128B-swizzled chunk and from the resident q' atoms), scores stay
+//           in registers.  A narrow tcgen05.mma (N = 32) costs ~95 clk whatever its size - operand fetch from shared
+//           memory - so giving it both passes made the tensor pipe the bound (measured); the warp-level MMAs run beside it.
+//   softmax in the accumulator layout; the reference maximum of a head only moves when a score exceeds it by more than
+//           2^8, so the common tile needs no cross-thread reduction at all; P^T (bf16) -> smem
+//   pass B  TMA stages [128 keys x 128 columns] (ring B) -> C^T[128 columns x 32 heads] += stage^T (A, MN-major) x
+//           P^T (B) with tcgen05.mma into TMEM, d / 128 accumulators
+// Output c_h = C^T[:, h] / l_h.
 #include "common.cuh"
 #include "kernels.h"
 
 namespace wf {
 
-static constexpr int LA_KT = 32;                    // keys per tile
-static constexpr int LA_CHUNK = LA_KT * 128;        // 4 KB: [32 keys x 64 columns] bf16, 128B-swizzled = one TMA box
-static constexpr int LA_STAGE = 2 * LA_CHUNK;       // 8 KB: 128 columns = the A operand of one context accumulator
-static constexpr int LA_NH = 32;                    // head columns of the context MMAs (H <= 32)
-static constexpr int LA_PT = LA_NH * 128;           // P^T operand: 32 rows (heads) x 128 B (64 keys; 32 used)
-static constexpr int LA_MISC = 2048;                // alpha [2][32] | 1/l [32] | flags [2][2] | barriers
-static constexpr int LA_MAX_STAGES = 28;
+static constexpr int LA_KT = 128;                   // keys per tile
+static constexpr int LA_CHUNK = LA_KT * 128;        // 16 KB: [128 keys x 64 columns] bf16, 128B-swizzled = one TMA box
+static constexpr int LA_STAGE_B = 2 * LA_CHUNK;     // 32 KB: 128 columns = the A operand of one context accumulator
+static constexpr int LA_NH = 32;                    // head columns of both MMAs (H <= 32)
+static constexpr int LA_PATOM = LA_NH * 128;        // 4 KB: P^T rows (heads) x 64 keys
+static constexpr int LA_PT = 2 * LA_PATOM;          // P^T operand of a tile: 32 heads x 128 keys
+static constexpr int LA_MISC = 3072;                // floats: m_ref[32] alpha[32] 1/l[32] red[4][32] | flags | barriers
+static constexpr int LA_MAX_A = 8, LA_MAX_B = 4;
 static constexpr int LA_SMEM_LIMIT = 227 * 1024;
-static constexpr int LA_TMEM_COLS = 512;            // S (2 x 32) | C^T (d / 128 accumulators x 32)
-static constexpr int LA_TMEM_C = 2 * LA_KT;
+static constexpr int LA_TMEM_COLS = 512;            // C^T: d / 128 accumulators x 32 columns
+static constexpr int LA_TMEM_C = 0;
 static constexpr int LA_THREADS = 256;
 
-// non-blocking probe (mbarrier.try_wait may suspend the thread for a system-dependent time when the phase is still
-// open, which a thread that polls two barriers cannot afford)
+// non-blocking probe of an mbarrier phase (a thread that serves two queues must not sleep in try_wait)
 __device__ __forceinline__ bool la_test_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -52,42 +58,58 @@ __device__ __forceinline__ bool la_test_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+__device__ __forceinline__ void la_ldsm_x4(uint32_t (&r)[4], uint32_t smem_addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_addr));
+}
 __device__ __forceinline__ void la_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ uint64_t la_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void la_tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                               uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], "
+      "[%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+
+// bring one TMA box into L2 only: HBM requests in flight without a shared-memory slot behind each of them
+__device__ __forceinline__ void la_tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1)
+               : "memory");
+}
 
 // bf16 x bf16 -> fp32, A MN-major (bit 15), B K-major
 __host__ __device__ constexpr uint32_t la_idesc_a_mn(int M, int N) { return umma_idesc_bf16(M, N) | (1u << 15); }
-// MN-major operand, 128B swizzle: rows = K index (128 B = 64 MN elements each), 8-row groups 1024 B apart (SBO),
-// the next 64 MN elements one 4 KB chunk further (LBO)
-__device__ __forceinline__ uint64_t la_desc_mn(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu);
-  d |= static_cast<uint64_t>(LA_CHUNK >> 4) << 16;
-  d |= static_cast<uint64_t>(1024u >> 4) << 32;
-  d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
-  return d;
-}
 
 __global__ void __launch_bounds__(LA_THREADS, 1)
 latent_attn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_q,
-                   __nv_bfloat16* __restrict__ ctx, int T, int H, int HP, int NS, int NST, float sl2) {
+                   __nv_bfloat16* __restrict__ ctx, int T, int H, int HP, int NS, int NA, int NB, float sl2) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* ring = smem;                              // NST stages of [32 keys x 128 columns]
-  uint8_t* qs = ring + NST * LA_STAGE;               // q': d / 64 K-major atoms of HP rows (heads)
+  uint8_t* ring_a = smem;                            // NA chunks
+  uint8_t* ring_b = ring_a + NA * LA_CHUNK;          // NB stages
+  uint8_t* qs = ring_b + NB * LA_STAGE_B;            // q': d / 64 K-major atoms of HP rows (heads)
   const int q_atom = HP * 128;
   uint8_t* pt = qs + 2 * NS * q_atom;                // P^T operand, double-buffered
   uint8_t* misc = pt + 2 * LA_PT;
-  float* al_buf = reinterpret_cast<float*>(misc);    // [2][32] rescale factor of each head for the tile
-  float* linv_buf = al_buf + 64;                     // [32]
-  int* flag_buf = reinterpret_cast<int*>(al_buf + 96);   // [2][2] "some head of this warp moved its reference maximum"
-  uint64_t* bars = reinterpret_cast<uint64_t*>(misc + 512);
-  uint64_t* full = bars;                             // [NST] stage landed
-  uint64_t* empty = bars + LA_MAX_STAGES;            // [NST] the context MMAs that read the stage completed
-  uint64_t* q_full = bars + 2 * LA_MAX_STAGES;
-  uint64_t* s_full = q_full + 1;                     // [2] scores of a tile in TMEM
-  uint64_t* s_free = s_full + 2;                     // [2] ... copied to registers (64 arrivals)
-  uint64_t* p_ready = s_free + 2;                    // [2] P^T staged, C^T rescaled (128 arrivals)
+  float* m_buf = reinterpret_cast<float*>(misc);     // [32] reference maximum of each head
+  float* al_buf = m_buf + 32;                        // [32] rescale factor when the reference moved
+  float* linv_buf = al_buf + 32;                     // [32]
+  float* red = linv_buf + 32;                        // [4][32]
+  int* flag_buf = reinterpret_cast<int*>(red + 128); // [2][4]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(misc + 1536);
+  uint64_t* full_a = bars;                           // [NA]
+  uint64_t* empty_a = full_a + LA_MAX_A;
+  uint64_t* full_b = empty_a + LA_MAX_A;             // [NB]
+  uint64_t* empty_b = full_b + LA_MAX_B;
+  uint64_t* q_full = empty_b + LA_MAX_B;
+  uint64_t* p_ready = q_full + 1;                    // [2] P^T staged, C^T rescaled (128 arrivals)
   uint64_t* c_done = p_ready + 2;                    // [2] context MMAs of a tile completed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(c_done + 2);
 
@@ -101,10 +123,11 @@ latent_attn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     tma_prefetch_desc(&map_q);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < NST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < NA; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 4); }
+    for (int i = 0; i < NB; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 64); mbar_init(&p_ready[i], 128); mbar_init(&c_done[i], 1);
+      mbar_init(&p_ready[i], 128); mbar_init(&c_done[i], 1);
     }
     mbar_fence_init();
   }
@@ -115,186 +138,305 @@ latent_attn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0 && lane == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    const long long total = static_cast<long long>(n_tiles) * NS;
-    int slot = 0, s = 0, j = 0;
-    uint32_t phase = 0;
+    // ------------------------------------------------------------------ TMA producer (both passes, one request order)
+    // Pass B of tile j re-reads what pass A of tile j brought into L2, so the two must stay close: the order is
+    // A(0) | B(0) | A(1) | B(1) ...; while pass B waits for a free stage (softmax of its tile still running) the thread
+    // fills ring A with the next tile's chunks, never further than one tile ahead.
+    const uint64_t keep = la_policy_evict_last(), drop = l2_policy_evict_first();
+    const int total_a = n_tiles * 2 * NS;
+    const int q_after = total_a < NA ? total_a : NA;
+    int ja = 0, ca = 0, sa = 0, issued_a = 0;       // pass A cursor: tile, chunk, ring slot
+    int jb = 0, ab = 0, sb = 0;                     // pass B cursor: tile, stage, ring slot
+    uint32_t pha = 0, phb = 0;
     bool q_sent = false;
-    for (long long g = 0; g < total; ++g) {
-      if (g == NST && !q_sent) {
-        // the source rows are static, q' comes from the previous kernel: the first ring-full is requested before the
-        // dependency wait
-        pdl_wait();
+    // HBM latency x the rate one SM needs is more than the rings can hold: chunks are prefetched into L2 PF chunks
+    // ahead of pass A, so both passes load at L2 latency
+    const int PF = NS + 2;
+    int jp = 0, cp = 0;
+    for (int i = 0; i < PF && jp < n_tiles; ++i) {
+      la_tma_prefetch_2d(&map_x, cp * 64, b * T + jp * LA_KT);
+      if (++cp == 2 * NS) { cp = 0; ++jp; }
+    }
+    long long t0 = clock64();
+    while (jb < n_tiles) {
+      if (!q_sent && issued_a == q_after) {
+        pdl_wait();       // q' comes from the previous kernel; the source rows are static
         mbar_arrive_expect_tx(q_full, 2 * NS * q_atom);
-        for (int c = 0; c < 2 * NS; ++c) tma_load_2d(qs + c * q_atom, &map_q, q_full, c * 64, b * H);
+        for (int i = 0; i < 2 * NS; ++i) tma_load_2d(qs + i * q_atom, &map_q, q_full, i * 64, b * H);
         q_sent = true;
       }
-      mbar_wait(&empty[slot], phase ^ 1);
-      mbar_arrive_expect_tx(&full[slot], LA_STAGE);
-      tma_load_2d(ring + slot * LA_STAGE, &map_x, &full[slot], s * 128, b * T + j * LA_KT);
-      tma_load_2d(ring + slot * LA_STAGE + LA_CHUNK, &map_x, &full[slot], s * 128 + 64, b * T + j * LA_KT);
-      if (++s == NS) { s = 0; ++j; }
-      if (++slot == NST) { slot = 0; phase ^= 1; }
-    }
-    if (!q_sent) {
-      pdl_wait();
-      mbar_arrive_expect_tx(q_full, 2 * NS * q_atom);
-      for (int c = 0; c < 2 * NS; ++c) tma_load_2d(qs + c * q_atom, &map_q, q_full, c * 64, b * H);
-    }
-  } else if (warp == 1 && lane == 0) {
-    // ------------------------------------------------------------------ MMA issuer
-    // scores  S[heads (64 rows, H valid) x 32 keys] = q' (A) x stage^T (B), both K-major, K = d in 16-column steps;
-    // context C^T[128 columns x 32 heads] (+)= stage^T (A, MN-major: the same bytes) x P^T (B, K-major), K = 32 keys.
-    // One stage of scores work is issued whenever its bytes have landed; a tile's context MMAs as soon as its P^T is
-    // staged (they free the ring, so they go first).
-#if defined(LA_EXP) && LA_EXP == 4
-    constexpr uint32_t idesc_s = umma_idesc_bf16(128, LA_KT);
-#else
-    constexpr uint32_t idesc_s = umma_idesc_bf16(64, LA_KT);
-#endif
-    constexpr uint32_t idesc_c = la_idesc_a_mn(128, LA_NH);
-    const uint32_t ring_a = smem_u32(ring), qs_a = smem_u32(qs), pt_a = smem_u32(pt);
-    int sj = 0, ss = 0, s_slot = 0, cj = 0, c_slot = 0;
-    uint32_t s_phase = 0;
-    mbar_wait(q_full, 0);
-    long long t0 = clock64();
-    while (cj < n_tiles) {
       bool progressed = false;
-      if (la_test_wait(&p_ready[cj & 1], (cj >> 1) & 1)) {
-        tc_fence_after();
-        const uint32_t pb = pt_a + (cj & 1) * LA_PT;
-        for (int a = 0; a < NS; ++a) {
-          const uint32_t st = ring_a + c_slot * LA_STAGE;
-#pragma unroll
-          for (int kk = 0; kk < LA_KT / 16; ++kk)
-#if defined(LA_EXP) && (LA_EXP == 1 || LA_EXP == 3)
-            if (a < 0)
-#endif
-            umma_f16(tmem_base + LA_TMEM_C + a * LA_NH, la_desc_mn(st + kk * 2048), umma_desc_kmajor_sw128(pb) + 2 * kk,
-                     idesc_c, (cj > 0 || kk > 0) ? 1u : 0u);
-          umma_commit(&empty[c_slot]);
-          if (++c_slot == NST) c_slot = 0;
-        }
-        umma_commit(&c_done[cj & 1]);
-        ++cj;
+      if (ja > jb && la_test_wait(&empty_b[sb], phb ^ 1)) {
+        mbar_arrive_expect_tx(&full_b[sb], LA_STAGE_B);
+        uint8_t* dst = ring_b + sb * LA_STAGE_B;
+        la_tma_load_2d(dst, &map_x, &full_b[sb], ab * 128, b * T + jb * LA_KT, drop);
+        la_tma_load_2d(dst + LA_CHUNK, &map_x, &full_b[sb], ab * 128 + 64, b * T + jb * LA_KT, drop);
+        if (++ab == NS) { ab = 0; ++jb; }
+        if (++sb == NB) { sb = 0; phb ^= 1; }
         progressed = true;
-      }
-      if (sj < n_tiles && la_test_wait(&full[s_slot], s_phase) &&
-          (ss != 0 || sj < 2 || la_test_wait(&s_free[sj & 1], ((sj >> 1) - 1) & 1))) {
-        tc_fence_after();
-        const uint32_t st = ring_a + s_slot * LA_STAGE;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const uint64_t a_desc = umma_desc_kmajor_sw128(qs_a + (2 * ss + c) * q_atom);
-          const uint64_t b_desc = umma_desc_kmajor_sw128(st + c * LA_CHUNK);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-#if defined(LA_EXP) && (LA_EXP == 2 || LA_EXP == 3)
-            if ((c | k) == 0)
-#endif
-            umma_f16(tmem_base + (sj & 1) * LA_KT, a_desc + 2 * k, b_desc + 2 * k, idesc_s, (ss | c | k) != 0);
+      } else if (ja < n_tiles && ja <= jb + 1 && la_test_wait(&empty_a[sa], pha ^ 1)) {
+        mbar_arrive_expect_tx(&full_a[sa], LA_CHUNK);
+        la_tma_load_2d(ring_a + sa * LA_CHUNK, &map_x, &full_a[sa], ca * 64, b * T + ja * LA_KT, keep);
+        if (jp < n_tiles) {
+          la_tma_prefetch_2d(&map_x, cp * 64, b * T + jp * LA_KT);
+          if (++cp == 2 * NS) { cp = 0; ++jp; }
         }
-        if (++ss == NS) {
-          umma_commit(&s_full[sj & 1]);
-          ss = 0;
-          ++sj;
-        }
-        if (++s_slot == NST) { s_slot = 0; s_phase ^= 1; }
+        if (++ca == 2 * NS) { ca = 0; ++ja; }
+        if (++sa == NA) { sa = 0; pha ^= 1; }
+        ++issued_a;
         progressed = true;
       }
       if (progressed) {
         t0 = clock64();
       } else if (clock64() - t0 > 4000000000LL) {
-        printf("libwf: latent attention MMA issuer timeout (block %d scores tile %d stage %d, context tile %d)\n",
-               blockIdx.x, sj, ss, cj);
+        printf("libwf: latent attention producer timeout (block %d, pass A tile %d chunk %d, pass B tile %d stage %d)\n",
+               blockIdx.x, ja, ca, jb, ab);
         __trap();
       }
     }
+  } else if (warp == 3 && lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer, pass B
+    // C^T[128 columns x 32 heads] (+)= stage^T (A, MN-major: rows = keys, two 64-column atoms 16 KB apart) x P^T (B,
+    // K-major, two atoms of 64 keys), K = 128 keys in 16-key steps
+    constexpr uint32_t idesc_c = la_idesc_a_mn(128, LA_NH);
+    const uint32_t rb = smem_u32(ring_b), pa = smem_u32(pt);
+    int slot = 0;
+    uint32_t phase = 0;
+#ifdef LA_TIMING
+    long long tb0[8], tb1[8], tb2[8];
+#endif
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(&p_ready[j & 1], (j >> 1) & 1);
+#ifdef LA_TIMING
+      if (j < 8) tb0[j] = clock64();
+#endif
+      const uint32_t pb = pa + (j & 1) * LA_PT;
+      for (int a = 0; a < NS; ++a) {
+        mbar_wait(&full_b[slot], phase);
+#ifdef LA_TIMING
+        if (a == 0 && j < 8) tb1[j] = clock64();
+#endif
+        tc_fence_after();
+        const uint32_t st = rb + slot * LA_STAGE_B;
+#pragma unroll
+        for (int kk = 0; kk < LA_KT / 16; ++kk)
+#if defined(LA_EXP) && (LA_EXP == 1 || LA_EXP == 3)
+          if (kk == 0)
+#endif
+          umma_f16(tmem_base + LA_TMEM_C + a * LA_NH, umma_desc_mnmajor_sw128(st + kk * 2048),
+                   umma_desc_kmajor_sw128(pb + (kk >> 2) * LA_PATOM) + 2 * (kk & 3), idesc_c, (j > 0 || kk > 0) ? 1u : 0u);
+        umma_commit(&empty_b[slot]);
+        if (++slot == NB) { slot = 0; phase ^= 1; }
+      }
+      umma_commit(&c_done[j & 1]);
+#ifdef LA_TIMING
+      if (j < 8) tb2[j] = clock64();
+#endif
+    }
+#ifdef LA_TIMING
+    if (blockIdx.x == 0) {
+      printf("B base %lld\n", tb0[0]);
+      for (int j = 0; j < 8 && j < n_tiles; ++j)
+        printf("B %d p_ready %lld first-stage %lld issued-all %lld\n", j, tb0[j] - tb0[0], tb1[j] - tb0[0], tb2[j] - tb0[0]);
+    }
+#endif
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ softmax (thread = head = TMEM lane of S)
+    // ------------------------------------------------------------------ pass A + softmax: warp = 32 keys of the tile
     const int wq = warp - 4;
     const int tid = threadIdx.x - 128;
+    const int g = lane >> 2, t = lane & 3;
+    const int nblk = HP >> 3;                          // 8-head column blocks of the score MMAs
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
-    // a 64-row accumulator keeps rows 16 q .. 16 q + 15 in lanes 32 q .. 32 q + 15 (profiles/r01_probe_tmem_m64_layout)
-    const int head = wq * 16 + lane;
-    const bool act = wq < 2 && lane < 16 && head < H;
-    float m_ref = -INFINITY, l_run = 0.f;
+    const uint32_t ra = smem_u32(ring_a), qa = smem_u32(qs);
+    // accumulator element (mt, nb, e): key wq*32 + mt*16 + g + 8*(e>>1), head nb*8 + 2t + (e&1)
+    float l_part[4][2];
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) l_part[nb][0] = l_part[nb][1] = 0.f;
+    if (tid < LA_NH) m_buf[tid] = -INFINITY;
     pdl_wait();
+    la_bar(1);
+    mbar_wait(q_full, 0);
+    // ldmatrix lane addresses inside a chunk / a q' atom (row pitch 128 B, 16-byte units XOR-swizzled by row & 7)
+    const uint32_t a_row = (wq * 32 + (lane & 15)) * 128, a_sw = lane & 7, a_hi = lane >> 4;
+    const uint32_t b_row = (lane & 7) * 128, b_sw = lane & 7, b_hi = lane >> 3;
+    int slot = 0;
+    uint32_t phase = 0;
+#ifdef LA_TIMING
+    long long tc0[8], tc1[8], tc2[8];
+#endif
     for (int j = 0; j < n_tiles; ++j) {
       const int buf = j & 1;
-      const uint32_t ph = (j >> 1) & 1;
-      uint32_t pk[LA_KT / 2];
-      if (wq < 2) {
-        mbar_wait(&s_full[buf], ph);
-        tc_fence_after();
-        uint32_t sv[32];
-        tmem_ld_32x32(lane_base + buf * LA_KT, sv);
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(&s_free[buf]);
-        const int nv = min(LA_KT, T - j * LA_KT);
-        float mt = -INFINITY;
+      float acc[2][4][4];
 #pragma unroll
-        for (int i = 0; i < LA_KT; ++i) {
-          const float s = i < nv ? __uint_as_float(sv[i]) : -INFINITY;
-          sv[i] = __float_as_uint(s);
-          mt = fmaxf(mt, s);
-        }
-        // the reference maximum only moves when a tile exceeds it by more than 2^8 (p stays <= 256: exact enough in
-        // bf16 / fp32), so the context accumulators are almost never rescaled
-        float alpha = 1.f;
-        bool need = false;
-        if (j == 0) {
-          m_ref = mt;
-        } else if ((mt - m_ref) * sl2 > 8.f) {
-          alpha = ex2_approx((m_ref - mt) * sl2);
-          m_ref = mt;
-          need = act;
-        }
-        const float mb = m_ref * sl2;
-        float lsum = 0.f;
+      for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int i = 0; i < LA_KT / 2; ++i) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(sv[2 * i]), sl2, -mb));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(sv[2 * i + 1]), sl2, -mb));
-          pk[i] = pack_bf16(p0, p1);
-          lsum += bf16lo(pk[i]) + bf16hi(pk[i]);      // the sums the tensor core will see
-        }
-        l_run = l_run * alpha + lsum;
-        if (act) al_buf[buf * 32 + head] = alpha;
-        const bool any = __any_sync(0xffffffffu, need);
-        if (lane == 0) flag_buf[buf * 2 + wq] = any ? 1 : 0;
+        for (int nb = 0; nb < 4; ++nb)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[mt][nb][e] = 0.f;
+      for (int c = 0; c < 2 * NS; ++c) {
+        mbar_wait(&full_a[slot], phase);
+#ifdef LA_TIMING
+        if (c == 0 && j < 8) tc0[j] = clock64();
+#endif
+        const uint32_t xs = ra + slot * LA_CHUNK, qc = qa + c * q_atom;
+        uint32_t bf[4][2][4];
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb)
+          if (nb < nblk) {
+#pragma unroll
+            for (int kp = 0; kp < 2; ++kp)
+              la_ldsm_x4(bf[nb][kp], qc + nb * 1024 + b_row + (((kp * 4 + b_hi) ^ b_sw) << 4));
+          }
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            uint32_t af[4];
+            la_ldsm_x4(af, xs + mt * 2048 + a_row + (((ks * 2 + a_hi) ^ a_sw) << 4));
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb)
+              if (nb < nblk) mma_bf16_16816(acc[mt][nb], af, bf[nb][ks >> 1][(ks & 1) * 2], bf[nb][ks >> 1][(ks & 1) * 2 + 1]);
+          }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_a[slot]);
+        if (++slot == NA) { slot = 0; phase ^= 1; }
       }
+#ifdef LA_TIMING
+      if (j < 8) tc1[j] = clock64();
+#endif
+      // ---- does any score leave the window of its head's reference maximum?  (always on the first tile)
+      const int key0 = j * LA_KT + wq * 32 + g;          // + 16 mt + 8 (e >> 1)
+      float mref[4][2];
+      bool exceed = false;
+#pragma unroll
+      for (int nb = 0; nb < 4; ++nb)
+        if (nb < nblk) {
+#pragma unroll
+          for (int ec = 0; ec < 2; ++ec) {
+            const int head = nb * 8 + 2 * t + ec;
+            mref[nb][ec] = head < H ? m_buf[head] : INFINITY;
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+              for (int er = 0; er < 2; ++er)
+                exceed = exceed || (key0 + mt * 16 + er * 8 < T && (acc[mt][nb][er * 2 + ec] - mref[nb][ec]) * sl2 > 8.f);
+          }
+        }
+      const bool w_any = __any_sync(0xffffffffu, exceed);
+      if (lane == 0) flag_buf[buf * 4 + wq] = w_any ? 1 : 0;
       la_bar(1);
-      const bool rescale = (flag_buf[buf * 2] | flag_buf[buf * 2 + 1]) != 0;
-      if (j >= 2) mbar_wait(&c_done[buf], ((j - 2) >> 1) & 1);     // P^T[buf] is no longer read by tile j - 2
-      if (rescale) {
-        mbar_wait(&c_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
-        tc_fence_after();
-        for (int a = 0; a < NS; ++a) {
-          uint32_t cv[32];
-          tmem_ld_32x32(lane_base + LA_TMEM_C + a * LA_NH, cv);
-          tmem_ld_wait();
+      const bool update = (flag_buf[buf * 4] | flag_buf[buf * 4 + 1] | flag_buf[buf * 4 + 2] | flag_buf[buf * 4 + 3]) != 0;
+      if (update) {
+        // move the references to the running maxima, rescale the sums and the context accumulators
 #pragma unroll
-          for (int h = 0; h < LA_NH; ++h)
-            if (h < H) cv[h] = __float_as_uint(__uint_as_float(cv[h]) * al_buf[buf * 32 + h]);
-          tmem_st_32x32(lane_base + LA_TMEM_C + a * LA_NH, cv);
+        for (int nb = 0; nb < 4; ++nb)
+          if (nb < nblk) {
+#pragma unroll
+            for (int ec = 0; ec < 2; ++ec) {
+              float mt_ = -INFINITY;
+#pragma unroll
+              for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int er = 0; er < 2; ++er)
+                  if (key0 + mt * 16 + er * 8 < T) mt_ = fmaxf(mt_, acc[mt][nb][er * 2 + ec]);
+              mt_ = fmaxf(mt_, __shfl_xor_sync(0xffffffffu, mt_, 4));
+              mt_ = fmaxf(mt_, __shfl_xor_sync(0xffffffffu, mt_, 8));
+              mt_ = fmaxf(mt_, __shfl_xor_sync(0xffffffffu, mt_, 16));
+              if (g == 0) red[wq * 32 + nb * 8 + 2 * t + ec] = mt_;
+            }
+          }
+        la_bar(2);
+        if (tid < H) {
+          const float mt_ = fmaxf(fmaxf(red[tid], red[32 + tid]), fmaxf(red[64 + tid], red[96 + tid]));
+          const float m_old = m_buf[tid];
+          const float m_new = fmaxf(m_old, mt_);
+          al_buf[tid] = ex2_approx((m_old - m_new) * sl2);     // 0 on the first tile
+          m_buf[tid] = m_new;
         }
-        tmem_st_wait();
-      }
-      if (act) {
-        uint8_t* row = pt + buf * LA_PT + head * 128;
+        la_bar(3);
 #pragma unroll
-        for (int u = 0; u < LA_KT / 8; ++u)
-          *reinterpret_cast<uint4*>(row + ((u ^ (head & 7)) << 4)) =
-              make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+        for (int nb = 0; nb < 4; ++nb)
+          if (nb < nblk) {
+#pragma unroll
+            for (int ec = 0; ec < 2; ++ec) {
+              const int head = nb * 8 + 2 * t + ec;
+              if (head < H) {
+                l_part[nb][ec] *= al_buf[head];
+                mref[nb][ec] = m_buf[head];
+              }
+            }
+          }
+        if (j > 0) {
+          mbar_wait(&c_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
+          tc_fence_after();
+          for (int a = 0; a < NS; ++a) {
+            uint32_t cv[32];
+            tmem_ld_32x32(lane_base + LA_TMEM_C + a * LA_NH, cv);
+            tmem_ld_wait();
+#pragma unroll
+            for (int h = 0; h < LA_NH; ++h)
+              if (h < H) cv[h] = __float_as_uint(__uint_as_float(cv[h]) * al_buf[h]);
+            tmem_st_32x32(lane_base + LA_TMEM_C + a * LA_NH, cv);
+          }
+          tmem_st_wait();
+        }
       }
+      if (j >= 2) mbar_wait(&c_done[buf], ((j - 2) >> 1) & 1);     // P^T[buf] is no longer read by tile j - 2
+      // ---- P^T element (head, key): atom = 64-key half, row = head (128 B), 16-byte units swizzled by the row
+      uint8_t* pbuf = pt + buf * LA_PT;
+#pragma unroll
+      for (int nb = 0; nb < 4; ++nb)
+        if (nb < nblk) {
+#pragma unroll
+          for (int ec = 0; ec < 2; ++ec) {
+            const int head = nb * 8 + 2 * t + ec;
+            if (head < H) {
+              const float mb = mref[nb][ec] * sl2;
+#pragma unroll
+              for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int er = 0; er < 2; ++er) {
+                  const int kl = wq * 32 + mt * 16 + er * 8 + g;       // key inside the tile
+                  const float p = j * LA_KT + kl < T ? ex2_approx(fmaf(acc[mt][nb][er * 2 + ec], sl2, -mb)) : 0.f;
+                  const __nv_bfloat16 pb = __float2bfloat16_rn(p);
+                  l_part[nb][ec] += __bfloat162float(pb);            // the sums the tensor core will see
+                  *reinterpret_cast<__nv_bfloat16*>(pbuf + (kl >> 6) * LA_PATOM + head * 128 +
+                                                    ((((kl & 63) >> 3) ^ (head & 7)) << 4) + (kl & 7) * 2) = pb;
+                }
+            }
+          }
+        }
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&p_ready[buf]);
+#ifdef LA_TIMING
+      if (j < 8) tc2[j] = clock64();
+#endif
+      // m_buf / al_buf / flag_buf[buf] are rewritten two tiles later at the earliest, behind la_bar(1) of tile j + 1
     }
-    if (act) linv_buf[head] = 1.0f / l_run;
-    la_bar(1);
+#ifdef LA_TIMING
+    if (blockIdx.x == 0 && tid == 0) {
+      printf("C base %lld\n", tc0[0]);
+      for (int j = 0; j < 8 && j < n_tiles; ++j)
+        printf("C %d first-chunk %lld chunks-done %lld p-arrive %lld\n", j, tc0[j] - tc0[0], tc1[j] - tc0[0], tc2[j] - tc0[0]);
+    }
+#endif
+    // ---- 1 / l
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb)
+      if (nb < nblk) {
+#pragma unroll
+        for (int ec = 0; ec < 2; ++ec) {
+          float v = l_part[nb][ec];
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          if (g == 0) red[wq * 32 + nb * 8 + 2 * t + ec] = v;
+        }
+      }
+    la_bar(2);
+    if (tid < H) linv_buf[tid] = 1.0f / ((red[tid] + red[32 + tid]) + (red[64 + tid] + red[96 + tid]));
+    la_bar(3);
     // ---- epilogue: ctx[b, h, 128 a + tid] = C^T[a][tid][h] / l_h   (thread = latent column)
     mbar_wait(&c_done[(n_tiles - 1) & 1], ((n_tiles - 1) >> 1) & 1);
     tc_fence_after();
@@ -323,10 +465,12 @@ int latent_attention(const void* qp, const void* src, void* ctx, int B, int T, i
              "latent attention: needs head_dim 64, an even number of heads and at most 32 of them (got %d heads)", H);
   const int hp = (H + 7) / 8 * 8, ns = d / 128;
   const int fixed = 1024 + 2 * ns * hp * 128 + 2 * LA_PT + LA_MISC;
-  int nst = (LA_SMEM_LIMIT - fixed) / LA_STAGE;
-  if (nst > LA_MAX_STAGES) nst = LA_MAX_STAGES;
-  WF_REQUIRE(nst > ns, "latent attention: the stage ring (%d) must hold more than one tile (%d stages)", nst, ns);
-  const int smem = fixed + nst * LA_STAGE;
+  const int n = (LA_SMEM_LIMIT - fixed) / LA_CHUNK;       // 16 KB units left for the two rings
+  const int nb = n >= 12 ? 3 : 2;
+  int na = n - 2 * nb;
+  if (na > LA_MAX_A) na = LA_MAX_A;
+  WF_REQUIRE(na >= 2, "latent attention: shared memory too small for the rings (%d chunks)", n);
+  const int smem = fixed + (na + 2 * nb) * LA_CHUNK;
   CUtensorMap mx, mq;
   int rc = make_map_bf16(&mx, src, static_cast<long long>(B) * T, d, d, LA_KT);
   if (rc) return rc;
@@ -339,7 +483,7 @@ int latent_attention(const void* qp, const void* src, void* ctx, int B, int T, i
   }
   const float sl2 = 0.125f * 1.44269504088896340736f;   // 64^-0.5 * log2(e)
   WF_CHECK_CUDA(launch_pdl(2, latent_attn_kernel, dim3(B), dim3(LA_THREADS), static_cast<size_t>(smem), stream, mx, mq,
-                           reinterpret_cast<__nv_bfloat16*>(ctx), T, H, hp, ns, nst, sl2));
+                           reinterpret_cast<__nv_bfloat16*>(ctx), T, H, hp, ns, na, nb, sl2));
   count_launch();
   return WF_OK;
 }
