@@ -308,3 +308,40 @@ def test_large_v2_width_av_model_fp32_tokens_and_bf16_decode_logits():
         os.environ["WF_NO_LN_FUSION"] = "0"
     assert rel_l2(plain.logits[:, :51865].float(), ref) <= BF16_LOGIT_TOL
     assert rel_l2(got, plain.logits[:, :51865].float().cpu()) <= BF16_LOGIT_TOL
+    # and the latent cross-attention path (no cross K/V cache: q' = Wk^T q over the encoder rows, csrc/latent.cu)
+    os.environ["WF_LATENT"] = "1"
+    try:
+        lat = _engine.DecodeSession(model.decoder, xa16, [feat.cuda()], 1, len(hist[0]) + 1)
+        assert lat.latent and lat.cross_kv == []
+        lat.configure_greedy(task.initial_tokens, task.sot_index, suppress, None, tk.eot, tk.no_speech, (-1, -1, -1))
+        lat.tokens[:, : len(hist[0])] = torch.tensor(hist, dtype=torch.int32, device="cuda")
+        for _ in range(len(hist[0])):
+            lat._forward_token()
+            whisper._native.step_advance(lat.state, lat.R)
+    finally:
+        del os.environ["WF_LATENT"]
+    assert rel_l2(lat.logits[:, :51865].float(), ref) <= BF16_LOGIT_TOL
+    assert rel_l2(lat.logits[:, :51865].float(), got.cuda()) <= BF16_LOGIT_TOL
+
+
+@pytest.mark.gpu
+def test_bf16_greedy_decode_latent_cross_attention(av_model, mel2, monkeypatch):
+    """The same bf16 greedy decode with the cross-attention on the latent path (forced: it is only the default from
+    112 rows up) - same acceptance as the cached-K/V bf16 engine, and the two engines agree with each other."""
+    import whisper
+    from whisper import _engine
+    gold = load_decode_golden()["cases"]["greedy_av"]
+    feat = _feat(2).cuda()
+    opt = whisper.DecodingOptions(language="en", without_timestamps=True, sample_len=24)
+    _engine.clear_sessions()
+    base = whisper.decode(av_model, mel2, opt, x_v=feat)
+    monkeypatch.setenv("WF_LATENT", "1")
+    res = whisper.decode(av_model, mel2, opt, x_v=feat)
+    sess = _engine._SESSION_CACHE.get(av_model.decoder)
+    assert sess is not None and sess.latent
+    agree = [sum(a == b for a, b in zip(r.tokens, g)) / len(g) for r, g in zip(res, gold["tokens"])]
+    assert all(r.tokens[0] == g[0] for r, g in zip(res, gold["tokens"])) and min(agree) >= 0.5, agree
+    for r, b, lp in zip(res, base, gold["avg_logprob"]):
+        assert abs(r.avg_logprob - lp) < 0.15 and abs(r.avg_logprob - b.avg_logprob) < 0.1
+    monkeypatch.delenv("WF_LATENT")
+    _engine.clear_sessions()

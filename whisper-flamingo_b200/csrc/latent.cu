@@ -19,14 +19,15 @@
 // product; narrower tiles, a d-split over a cluster and scores on tcgen05 were all measured slower - git history).
 // The second pass finds the tile in L2 (one TMA thread requests A(j) | B(j) | A(j+1) ... in that order, first-pass
 // loads carry an evict_last hint, second-pass loads evict_first), so HBM sees every source row once.
-//   pass A  TMA chunks [128 keys x 64 columns] (ring A) -> four warps, 32 keys each: S^T[keys x heads] += chunk x q'^T
-//           with mma.sync m16n8k16 (ldmatrix from the 128B-swizzled chunk and from the resident q' atoms), scores stay
-//           in registers.  A narrow tcgen05.mma (N = 32) costs ~95 clk whatever its size - operand fetch from shared
-//           memory - so giving it both passes made the tensor pipe the bound (measured); the warp-level MMAs run beside it.
-//   softmax in the accumulator layout; the reference maximum of a head only moves when a score exceeds it by more than
-//           2^8, so the common tile needs no cross-thread reduction at all; P^T (bf16) -> smem
+//   pass A  TMA chunks [128 keys x 64 columns] (ring A) -> S^T[128 keys x 32 heads] += chunk (A, K-major) x q'^T (B,
+//           resident) with tcgen05.mma into TMEM; a chunk is freed by the commit of its four MMAs
+//   softmax thread = key; the reference maximum of a head only moves when a score exceeds it by more than 2^8, so the
+//           common tile needs no cross-thread reduction at all; P^T (bf16) -> smem
 //   pass B  TMA stages [128 keys x 128 columns] (ring B) -> C^T[128 columns x 32 heads] += stage^T (A, MN-major) x
 //           P^T (B) with tcgen05.mma into TMEM, d / 128 accumulators
+// Each pass has its own MMA-issuing thread.  The kernel is bound by the tensor pipe: a tcgen05.mma with N = 32 costs
+// ~95 clk whatever its size (operand fetch from shared memory), 160 of them per tile.  Scores on mma.sync in the
+// softmax warps instead (so that the two passes use different pipes) measured slower: ~32 clk per m16n8k16.
 // Output c_h = C^T[:, h] / l_h.
 #include "common.cuh"
 #include "kernels.h"
@@ -42,9 +43,15 @@ static constexpr int LA_PT = 2 * LA_PATOM;          // P^T operand of a tile: 32
 static constexpr int LA_MISC = 3072;                // floats: m_ref[32] alpha[32] 1/l[32] red[4][32] | flags | barriers
 static constexpr int LA_MAX_A = 8, LA_MAX_B = 4;
 static constexpr int LA_SMEM_LIMIT = 227 * 1024;
-static constexpr int LA_TMEM_COLS = 512;            // C^T: d / 128 accumulators x 32 columns
-static constexpr int LA_TMEM_C = 0;
+static constexpr int LA_TMEM_COLS = 512;            // S^T (2 x 32) | C^T (d / 128 accumulators x 32)
+static constexpr int LA_TMEM_C = 2 * LA_NH;
 static constexpr int LA_THREADS = 256;
+#ifndef LA_LEAD
+#define LA_LEAD 1      // tiles pass A may be requested ahead of pass B
+#endif
+#ifndef LA_PF
+#define LA_PF 0        // L2 prefetch ahead of pass A (measured: 124 -> 140 us)
+#endif
 
 // non-blocking probe of an mbarrier phase (a thread that serves two queues must not sleep in try_wait)
 __device__ __forceinline__ bool la_test_wait(uint64_t* bar, uint32_t parity) {
@@ -109,7 +116,9 @@ latent_attn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   uint64_t* full_b = empty_a + LA_MAX_A;             // [NB]
   uint64_t* empty_b = full_b + LA_MAX_B;
   uint64_t* q_full = empty_b + LA_MAX_B;
-  uint64_t* p_ready = q_full + 1;                    // [2] P^T staged, C^T rescaled (128 arrivals)
+  uint64_t* s_full = q_full + 1;                     // [2] scores of a tile in TMEM
+  uint64_t* s_free = s_full + 2;                     // [2] ... copied to registers (128 arrivals)
+  uint64_t* p_ready = s_free + 2;                    // [2] P^T staged, C^T rescaled (128 arrivals)
   uint64_t* c_done = p_ready + 2;                    // [2] context MMAs of a tile completed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(c_done + 2);
 
@@ -123,11 +132,11 @@ latent_attn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     tma_prefetch_desc(&map_q);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < NA; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 4); }
+    for (int i = 0; i < NA; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
     for (int i = 0; i < NB; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&p_ready[i], 128); mbar_init(&c_done[i], 1);
+      mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 128); mbar_init(&p_ready[i], 128); mbar_init(&c_done[i], 1);
     }
     mbar_fence_init();
   }
@@ -151,8 +160,8 @@ latent_attn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     bool q_sent = false;
     // HBM latency x the rate one SM needs is more than the rings can hold: chunks are prefetched into L2 PF chunks
     // ahead of pass A, so both passes load at L2 latency
-    const int PF = NS + 2;
-    int jp = 0, cp = 0;
+    const int PF = LA_PF ? NS + 2 : 0;
+    int jp = LA_PF ? 0 : n_tiles, cp = 0;
     for (int i = 0; i < PF && jp < n_tiles; ++i) {
       la_tma_prefetch_2d(&map_x, cp * 64, b * T + jp * LA_KT);
       if (++cp == 2 * NS) { cp = 0; ++jp; }
@@ -174,7 +183,7 @@ latent_attn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         if (++ab == NS) { ab = 0; ++jb; }
         if (++sb == NB) { sb = 0; phb ^= 1; }
         progressed = true;
-      } else if (ja < n_tiles && ja <= jb + 1 && la_test_wait(&empty_a[sa], pha ^ 1)) {
+      } else if (ja < n_tiles && ja <= jb + LA_LEAD && la_test_wait(&empty_a[sa], pha ^ 1)) {
         mbar_arrive_expect_tx(&full_a[sa], LA_CHUNK);
         la_tma_load_2d(ring_a + sa * LA_CHUNK, &map_x, &full_a[sa], ca * 64, b * T + ja * LA_KT, keep);
         if (jp < n_tiles) {
@@ -194,6 +203,30 @@ latent_attn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         __trap();
       }
     }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer, pass A
+    // S^T[128 keys x 32 heads] = chunk (A, K-major) x q'^T (B, K-major; rows >= HP of an atom alias the next atom and
+    // only produce head columns nobody reads), K = d in 16-column steps
+    constexpr uint32_t idesc_s = umma_idesc_bf16(LA_KT, LA_NH);
+    const uint32_t ra = smem_u32(ring_a), qa = smem_u32(qs);
+    int slot = 0;
+    uint32_t phase = 0;
+    mbar_wait(q_full, 0);
+    for (int j = 0; j < n_tiles; ++j) {
+      if (j >= 2) mbar_wait(&s_free[j & 1], ((j >> 1) - 1) & 1);
+      for (int c = 0; c < 2 * NS; ++c) {
+        mbar_wait(&full_a[slot], phase);
+        tc_fence_after();
+        const uint64_t a_desc = umma_desc_kmajor_sw128(ra + slot * LA_CHUNK);
+        const uint64_t b_desc = umma_desc_kmajor_sw128(qa + c * q_atom);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16(tmem_base + (j & 1) * LA_NH, a_desc + 2 * k, b_desc + 2 * k, idesc_s, (c | k) != 0);
+        umma_commit(&empty_a[slot]);
+        if (++slot == NA) { slot = 0; phase ^= 1; }
+      }
+      umma_commit(&s_full[j & 1]);
+    }
   } else if (warp == 3 && lane == 0) {
     // ------------------------------------------------------------------ MMA issuer, pass B
     // C^T[128 columns x 32 heads] (+)= stage^T (A, MN-major: rows = keys, two 64-column atoms 16 KB apart) x P^T (B,
@@ -202,170 +235,76 @@ latent_attn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     const uint32_t rb = smem_u32(ring_b), pa = smem_u32(pt);
     int slot = 0;
     uint32_t phase = 0;
-#ifdef LA_TIMING
-    long long tb0[8], tb1[8], tb2[8];
-#endif
     for (int j = 0; j < n_tiles; ++j) {
       mbar_wait(&p_ready[j & 1], (j >> 1) & 1);
-#ifdef LA_TIMING
-      if (j < 8) tb0[j] = clock64();
-#endif
       const uint32_t pb = pa + (j & 1) * LA_PT;
       for (int a = 0; a < NS; ++a) {
         mbar_wait(&full_b[slot], phase);
-#ifdef LA_TIMING
-        if (a == 0 && j < 8) tb1[j] = clock64();
-#endif
         tc_fence_after();
         const uint32_t st = rb + slot * LA_STAGE_B;
 #pragma unroll
         for (int kk = 0; kk < LA_KT / 16; ++kk)
-#if defined(LA_EXP) && (LA_EXP == 1 || LA_EXP == 3)
-          if (kk == 0)
-#endif
           umma_f16(tmem_base + LA_TMEM_C + a * LA_NH, umma_desc_mnmajor_sw128(st + kk * 2048),
                    umma_desc_kmajor_sw128(pb + (kk >> 2) * LA_PATOM) + 2 * (kk & 3), idesc_c, (j > 0 || kk > 0) ? 1u : 0u);
         umma_commit(&empty_b[slot]);
         if (++slot == NB) { slot = 0; phase ^= 1; }
       }
       umma_commit(&c_done[j & 1]);
-#ifdef LA_TIMING
-      if (j < 8) tb2[j] = clock64();
-#endif
     }
-#ifdef LA_TIMING
-    if (blockIdx.x == 0) {
-      printf("B base %lld\n", tb0[0]);
-      for (int j = 0; j < 8 && j < n_tiles; ++j)
-        printf("B %d p_ready %lld first-stage %lld issued-all %lld\n", j, tb0[j] - tb0[0], tb1[j] - tb0[0], tb2[j] - tb0[0]);
-    }
-#endif
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ pass A + softmax: warp = 32 keys of the tile
+    // ------------------------------------------------------------------ softmax (thread = key = TMEM lane of S^T)
     const int wq = warp - 4;
     const int tid = threadIdx.x - 128;
-    const int g = lane >> 2, t = lane & 3;
-    const int nblk = HP >> 3;                          // 8-head column blocks of the score MMAs
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
-    const uint32_t ra = smem_u32(ring_a), qa = smem_u32(qs);
-    // accumulator element (mt, nb, e): key wq*32 + mt*16 + g + 8*(e>>1), head nb*8 + 2t + (e&1)
-    float l_part[4][2];
+    float l_part[LA_NH];
 #pragma unroll
-    for (int nb = 0; nb < 4; ++nb) l_part[nb][0] = l_part[nb][1] = 0.f;
+    for (int h = 0; h < LA_NH; ++h) l_part[h] = 0.f;
     if (tid < LA_NH) m_buf[tid] = -INFINITY;
     pdl_wait();
     la_bar(1);
-    mbar_wait(q_full, 0);
-    // ldmatrix lane addresses inside a chunk / a q' atom (row pitch 128 B, 16-byte units XOR-swizzled by row & 7)
-    const uint32_t a_row = (wq * 32 + (lane & 15)) * 128, a_sw = lane & 7, a_hi = lane >> 4;
-    const uint32_t b_row = (lane & 7) * 128, b_sw = lane & 7, b_hi = lane >> 3;
-    int slot = 0;
-    uint32_t phase = 0;
-#ifdef LA_TIMING
-    long long tc0[8], tc1[8], tc2[8];
-#endif
+    // P^T element (head h, my key): atom = 64-key half, row = head (128 B), 16-byte units swizzled by the row
+    const uint32_t p_off = (tid >> 6) * LA_PATOM + (tid & 7) * 2;
+    const uint32_t p_unit = (tid & 63) >> 3;
     for (int j = 0; j < n_tiles; ++j) {
       const int buf = j & 1;
-      float acc[2][4][4];
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int nb = 0; nb < 4; ++nb)
-#pragma unroll
-          for (int e = 0; e < 4; ++e) acc[mt][nb][e] = 0.f;
-      for (int c = 0; c < 2 * NS; ++c) {
-        mbar_wait(&full_a[slot], phase);
-#ifdef LA_TIMING
-        if (c == 0 && j < 8) tc0[j] = clock64();
-#endif
-        const uint32_t xs = ra + slot * LA_CHUNK, qc = qa + c * q_atom;
-        uint32_t bf[4][2][4];
-#pragma unroll
-        for (int nb = 0; nb < 4; ++nb)
-          if (nb < nblk) {
-#pragma unroll
-            for (int kp = 0; kp < 2; ++kp)
-              la_ldsm_x4(bf[nb][kp], qc + nb * 1024 + b_row + (((kp * 4 + b_hi) ^ b_sw) << 4));
-          }
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            uint32_t af[4];
-            la_ldsm_x4(af, xs + mt * 2048 + a_row + (((ks * 2 + a_hi) ^ a_sw) << 4));
-#pragma unroll
-            for (int nb = 0; nb < 4; ++nb)
-              if (nb < nblk) mma_bf16_16816(acc[mt][nb], af, bf[nb][ks >> 1][(ks & 1) * 2], bf[nb][ks >> 1][(ks & 1) * 2 + 1]);
-          }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_a[slot]);
-        if (++slot == NA) { slot = 0; phase ^= 1; }
-      }
-#ifdef LA_TIMING
-      if (j < 8) tc1[j] = clock64();
-#endif
-      // ---- does any score leave the window of its head's reference maximum?  (always on the first tile)
-      const int key0 = j * LA_KT + wq * 32 + g;          // + 16 mt + 8 (e >> 1)
-      float mref[4][2];
+      const uint32_t ph = (j >> 1) & 1;
+      mbar_wait(&s_full[buf], ph);
+      tc_fence_after();
+      uint32_t sv[32];
+      tmem_ld_32x32(lane_base + buf * LA_NH, sv);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&s_free[buf]);
+      const bool valid = j * LA_KT + tid < T;
+      // does any score leave the window of its head's reference maximum?  (always on the first tile)
       bool exceed = false;
 #pragma unroll
-      for (int nb = 0; nb < 4; ++nb)
-        if (nb < nblk) {
-#pragma unroll
-          for (int ec = 0; ec < 2; ++ec) {
-            const int head = nb * 8 + 2 * t + ec;
-            mref[nb][ec] = head < H ? m_buf[head] : INFINITY;
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-              for (int er = 0; er < 2; ++er)
-                exceed = exceed || (key0 + mt * 16 + er * 8 < T && (acc[mt][nb][er * 2 + ec] - mref[nb][ec]) * sl2 > 8.f);
-          }
-        }
-      const bool w_any = __any_sync(0xffffffffu, exceed);
+      for (int h = 0; h < LA_NH; ++h)
+        if (h < H) exceed = exceed || (__uint_as_float(sv[h]) - m_buf[h]) * sl2 > 8.f;
+      const bool w_any = __any_sync(0xffffffffu, exceed && valid);
       if (lane == 0) flag_buf[buf * 4 + wq] = w_any ? 1 : 0;
       la_bar(1);
       const bool update = (flag_buf[buf * 4] | flag_buf[buf * 4 + 1] | flag_buf[buf * 4 + 2] | flag_buf[buf * 4 + 3]) != 0;
       if (update) {
         // move the references to the running maxima, rescale the sums and the context accumulators
 #pragma unroll
-        for (int nb = 0; nb < 4; ++nb)
-          if (nb < nblk) {
-#pragma unroll
-            for (int ec = 0; ec < 2; ++ec) {
-              float mt_ = -INFINITY;
-#pragma unroll
-              for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                for (int er = 0; er < 2; ++er)
-                  if (key0 + mt * 16 + er * 8 < T) mt_ = fmaxf(mt_, acc[mt][nb][er * 2 + ec]);
-              mt_ = fmaxf(mt_, __shfl_xor_sync(0xffffffffu, mt_, 4));
-              mt_ = fmaxf(mt_, __shfl_xor_sync(0xffffffffu, mt_, 8));
-              mt_ = fmaxf(mt_, __shfl_xor_sync(0xffffffffu, mt_, 16));
-              if (g == 0) red[wq * 32 + nb * 8 + 2 * t + ec] = mt_;
-            }
+        for (int h = 0; h < LA_NH; ++h)
+          if (h < H) {
+            const float mt = warp_max(valid ? __uint_as_float(sv[h]) : -INFINITY);
+            if (lane == 0) red[wq * 32 + h] = mt;
           }
         la_bar(2);
         if (tid < H) {
-          const float mt_ = fmaxf(fmaxf(red[tid], red[32 + tid]), fmaxf(red[64 + tid], red[96 + tid]));
+          const float mt = fmaxf(fmaxf(red[tid], red[32 + tid]), fmaxf(red[64 + tid], red[96 + tid]));
           const float m_old = m_buf[tid];
-          const float m_new = fmaxf(m_old, mt_);
+          const float m_new = fmaxf(m_old, mt);
           al_buf[tid] = ex2_approx((m_old - m_new) * sl2);     // 0 on the first tile
           m_buf[tid] = m_new;
         }
         la_bar(3);
 #pragma unroll
-        for (int nb = 0; nb < 4; ++nb)
-          if (nb < nblk) {
-#pragma unroll
-            for (int ec = 0; ec < 2; ++ec) {
-              const int head = nb * 8 + 2 * t + ec;
-              if (head < H) {
-                l_part[nb][ec] *= al_buf[head];
-                mref[nb][ec] = m_buf[head];
-              }
-            }
-          }
+        for (int h = 0; h < LA_NH; ++h)
+          if (h < H) l_part[h] *= al_buf[h];
         if (j > 0) {
           mbar_wait(&c_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
           tc_fence_after();
@@ -382,57 +321,26 @@ latent_attn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         }
       }
       if (j >= 2) mbar_wait(&c_done[buf], ((j - 2) >> 1) & 1);     // P^T[buf] is no longer read by tile j - 2
-      // ---- P^T element (head, key): atom = 64-key half, row = head (128 B), 16-byte units swizzled by the row
-      uint8_t* pbuf = pt + buf * LA_PT;
+      uint8_t* prow = pt + buf * LA_PT + p_off;
 #pragma unroll
-      for (int nb = 0; nb < 4; ++nb)
-        if (nb < nblk) {
-#pragma unroll
-          for (int ec = 0; ec < 2; ++ec) {
-            const int head = nb * 8 + 2 * t + ec;
-            if (head < H) {
-              const float mb = mref[nb][ec] * sl2;
-#pragma unroll
-              for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                for (int er = 0; er < 2; ++er) {
-                  const int kl = wq * 32 + mt * 16 + er * 8 + g;       // key inside the tile
-                  const float p = j * LA_KT + kl < T ? ex2_approx(fmaf(acc[mt][nb][er * 2 + ec], sl2, -mb)) : 0.f;
-                  const __nv_bfloat16 pb = __float2bfloat16_rn(p);
-                  l_part[nb][ec] += __bfloat162float(pb);            // the sums the tensor core will see
-                  *reinterpret_cast<__nv_bfloat16*>(pbuf + (kl >> 6) * LA_PATOM + head * 128 +
-                                                    ((((kl & 63) >> 3) ^ (head & 7)) << 4) + (kl & 7) * 2) = pb;
-                }
-            }
-          }
+      for (int h = 0; h < LA_NH; ++h)
+        if (h < H) {
+          const float p = valid ? ex2_approx((__uint_as_float(sv[h]) - m_buf[h]) * sl2) : 0.f;
+          const __nv_bfloat16 pb = __float2bfloat16_rn(p);
+          l_part[h] += __bfloat162float(pb);                       // the sums the tensor core will see
+          *reinterpret_cast<__nv_bfloat16*>(prow + h * 128 + ((p_unit ^ (h & 7)) << 4)) = pb;
         }
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&p_ready[buf]);
-#ifdef LA_TIMING
-      if (j < 8) tc2[j] = clock64();
-#endif
       // m_buf / al_buf / flag_buf[buf] are rewritten two tiles later at the earliest, behind la_bar(1) of tile j + 1
     }
-#ifdef LA_TIMING
-    if (blockIdx.x == 0 && tid == 0) {
-      printf("C base %lld\n", tc0[0]);
-      for (int j = 0; j < 8 && j < n_tiles; ++j)
-        printf("C %d first-chunk %lld chunks-done %lld p-arrive %lld\n", j, tc0[j] - tc0[0], tc1[j] - tc0[0], tc2[j] - tc0[0]);
-    }
-#endif
     // ---- 1 / l
 #pragma unroll
-    for (int nb = 0; nb < 4; ++nb)
-      if (nb < nblk) {
-#pragma unroll
-        for (int ec = 0; ec < 2; ++ec) {
-          float v = l_part[nb][ec];
-          v += __shfl_xor_sync(0xffffffffu, v, 4);
-          v += __shfl_xor_sync(0xffffffffu, v, 8);
-          v += __shfl_xor_sync(0xffffffffu, v, 16);
-          if (g == 0) red[wq * 32 + nb * 8 + 2 * t + ec] = v;
-        }
+    for (int h = 0; h < LA_NH; ++h)
+      if (h < H) {
+        const float v = warp_sum(l_part[h]);
+        if (lane == 0) red[wq * 32 + h] = v;
       }
     la_bar(2);
     if (tid < H) linv_buf[tid] = 1.0f / ((red[tid] + red[32 + tid]) + (red[64 + tid] + red[96 + tid]));
@@ -466,7 +374,11 @@ int latent_attention(const void* qp, const void* src, void* ctx, int B, int T, i
   const int hp = (H + 7) / 8 * 8, ns = d / 128;
   const int fixed = 1024 + 2 * ns * hp * 128 + 2 * LA_PT + LA_MISC;
   const int n = (LA_SMEM_LIMIT - fixed) / LA_CHUNK;       // 16 KB units left for the two rings
+#ifdef LA_NB_FORCE
+  const int nb = LA_NB_FORCE;
+#else
   const int nb = n >= 12 ? 3 : 2;
+#endif
   int na = n - 2 * nb;
   if (na > LA_MAX_A) na = LA_MAX_A;
   WF_REQUIRE(na >= 2, "latent attention: shared memory too small for the rings (%d chunks)", n);

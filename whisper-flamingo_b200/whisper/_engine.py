@@ -256,6 +256,7 @@ class _BlockFold:
     self_qkv: _LnLinear
     cross_q: Optional[_LnLinear]
     mlp1: _LnLinear
+    cross_wk_t: Optional[Tensor] = None   # [d, d] = key.weight^T of the cross-attention (latent path, built on demand)
 
 
 def _fold_block(blk, bp: _BlockPack, dt) -> _BlockFold:
@@ -269,6 +270,18 @@ def _fold_block(blk, bp: _BlockPack, dt) -> _BlockFold:
                if bp.cross is not None else None)
     return _BlockFold(x_q, ff1, _fold_ln(bp.attn_ln, qkv_master, bp.attn.qkv_b, dt), cross_q,
                       _fold_ln(bp.mlp_ln, blk.mlp[0].weight, bp.mlp.b1, dt))
+
+
+def latent_cross_enabled(rows: int, n_group: int, n_head: int, d: int) -> bool:
+    """Cross-attention of a greedy bf16 decode step over the encoder rows themselves (absorbed key / value projections,
+    csrc/latent.cu) instead of over a per-layer K/V cache.  The kernel is bound by the tensor pipe, the cached path by
+    HBM: it wins once the batch fills the GPU (measured on B200, large-v2: 138 vs 164 us per layer at 128 clips,
+    slower at 64).  WF_LATENT=1 / 0 forces it on / off."""
+    env = os.environ.get("WF_LATENT", "")
+    ok = n_group == 1 and n_head <= 32 and d == 64 * n_head and d % 128 == 0
+    if env in ("0", "1"):
+        return ok and env == "1"
+    return ok and rows >= 112
 
 
 def decoder_fold(dec, p: _DecoderPack, dt) -> List[_BlockFold]:
@@ -513,7 +526,18 @@ class DecodeSession:
         self.Tx = [f.shape[1] for f in feats]
         L = len(p.blocks)
         # ---- per-clip K/V caches (head-major) and step buffers; contents are (re)filled by load()
-        self.cross_kv = [torch.empty((B, 2 * H, Ta, 64), dtype=dt, device=dev) for _ in range(L)]
+        self.latent = self.fold is not None and latent_cross_enabled(R, G, H, d)
+        if self.latent:
+            # no cross-attention K/V arena at all: every layer attends over the same bf16 encoder rows
+            self.cross_kv = []
+            self.xa_src = torch.empty((B, Ta, d), dtype=dt, device=dev)
+            self.qp = torch.empty((R, H, d), dtype=dt, device=dev)
+            self.ctx = torch.empty((R, H, d), dtype=dt, device=dev)
+            for bp, bf in zip(p.blocks, self.fold):
+                if bf.cross_wk_t is None:
+                    bf.cross_wk_t = bp.cross.qkv_w[d:2 * d].t().contiguous()
+        else:
+            self.cross_kv = [torch.empty((B, 2 * H, Ta, 64), dtype=dt, device=dev) for _ in range(L)]
         self.x_kv = [[torch.empty((B, 2 * H, tx, 64), dtype=dt, device=dev) for tx in self.Tx] for _ in range(L)]
         self.self_kv = [torch.zeros((R, 2 * H, t_cap, 64), dtype=dt, device=dev) for _ in range(L)]
         self.gemm_ws = torch.zeros(4096 + 8 * 1024 * 1024, dtype=torch.uint8, device=dev)  # split-K counters + partials
@@ -562,9 +586,12 @@ class DecodeSession:
         p, dt, B, H = self.p, self.dt, self.B, self.p.n_head
         xa2 = _to_dtype(xa, dt).contiguous().view(-1, p.d)
         fprep = [prepare_features(p, f, dt) for f in feats]
+        if self.latent:
+            self.xa_src.view(-1, p.d).copy_(xa2)
         for l, bp in enumerate(p.blocks):
-            nv.linear(xa2, bp.cross.kv_w, self.cross_kv[l].view(-1, 64), bias=bp.cross.kv_b,
-                      head_major=(2 * H, self.Ta, self.Ta))
+            if not self.latent:
+                nv.linear(xa2, bp.cross.kv_w, self.cross_kv[l].view(-1, 64), bias=bp.cross.kv_b,
+                          head_major=(2 * H, self.Ta, self.Ta))
             for i, f in enumerate(fprep):
                 nv.linear(f, bp.x_attn[i].kv_w, self.x_kv[l][i].view(-1, 64), bias=bp.x_attn[i].kv_b,
                           head_major=(2 * H, self.Tx[i], self.Tx[i]))
@@ -653,9 +680,16 @@ class DecodeSession:
                                 row_table=self.row_table)
             nv.linear(att, bp.attn.o_w, x, bias=bp.attn.o_b, residual=x)
             lnlin(bf.cross_q, q)
-            ckv = self.cross_kv[l]
-            nv.attention_decode(q, ckv, ckv[:, H:], 64, 2 * H * self.Ta * 64, self.Ta * 64, att, G, H, None, 0,
-                                self.Ta, self.ws)
+            if self.latent:
+                # q' = Wk_h^T q_h -> softmax(xa q' / 8)^T xa -> Wv_h c_h + bv_h: the step streams xa once for all heads
+                d = p.d
+                nv.latent_query(q, bf.cross_wk_t, self.qp, H)
+                nv.latent_attention(self.qp, self.xa_src, self.ctx, H)
+                nv.latent_value(self.ctx, bp.cross.qkv_w[2 * d:], bp.cross.qkv_b[2 * d:], att, H)
+            else:
+                ckv = self.cross_kv[l]
+                nv.attention_decode(q, ckv, ckv[:, H:], 64, 2 * H * self.Ta * 64, self.Ta * 64, att, G, H, None, 0,
+                                    self.Ta, self.ws)
             nv.linear(att, bp.cross.o_w, x, bias=bp.cross.o_b, residual=x)
             lnlin(bf.mlp1, h, act=nv.ACT_GELU)
             nv.linear(h, bp.mlp.w2, x, bias=bp.mlp.b2, residual=x)
@@ -898,7 +932,9 @@ def get_session(dec, xa: Tensor, feats: Optional[Sequence[Tensor]], n_group: int
         key = (dt, xa.device, xa.shape[0], n_group, t_cap, xa.shape[1], tx, id(p))
         if n_split > 1:
             key = key + (n_split,)
-        if old.shape_key() == key and (not old.gated or n_feats == len(old.Tx)):
+        same_path = (not isinstance(old, DecodeSession) or old.latent ==
+                     (old.fold is not None and latent_cross_enabled(old.R, old.G, p.n_head, p.d)))
+        if old.shape_key() == key and (not old.gated or n_feats == len(old.Tx)) and same_path:
             old.load(xa, old._check_feats(feats))
             return old
     _SESSION_CACHE.pop(dec, None)
