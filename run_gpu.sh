@@ -1,10 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
-(cd whisper-flamingo_b200 && touch csrc/latent.cu && make > /dev/null 2>&1)
-timeout 600 python -m pytest tests/test_engine_gpu.py -x -q -k "latent or large_v2" > gpurun_out/engine_latent_test.log 2>&1
-echo "rc $?" >> gpurun_out/engine_latent_test.log
-tail -15 gpurun_out/engine_latent_test.log
-timeout 600 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_latent.json 2> gpurun_out/bench_latent.err
-echo "rc $?"; tail -3 gpurun_out/bench_latent.err; cat gpurun_out/bench_latent.json
-WF_LATENT=0 timeout 600 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_nolatent.json 2> gpurun_out/bench_nolatent.err
-echo "rc $?"; cat gpurun_out/bench_nolatent.json
+: > gpurun_out/latent_exp.log
+for e in "-DLA_PF=6" "-DLA_PF=12" "-DLA_PF=24"; do
+  (cd whisper-flamingo_b200 && touch csrc/latent.cu && make EXTRA="$e" > /dev/null 2>&1)
+  echo "variant [$e]" >> gpurun_out/latent_exp.log
+  LATENT_SHAPES=2 timeout 120 python tools/microbench.py latent 2>&1 | tail -2 >> gpurun_out/latent_exp.log
+done
+cat gpurun_out/latent_exp.log

@@ -11,23 +11,29 @@
 // every layer, so no per-layer K/V projection pass and no K/V arena exist at all); the extra arithmetic
 // (2 x 2 T d H flop per clip) goes to the tensor cores.  Three kernels:
 //   latent_query_kernel  q [R, d] -> q' [R, H, d]         (per head a [R,64] x [64,d] GEMM, mma.sync)
-//   latent_attn_kernel   q', src  -> c  [R, H, d]         (tcgen05 + TMA + thread-block cluster, below)
+//   latent_attn_kernel   q', src  -> c  [R, H, d]         (tcgen05 + TMA, below)
 //   latent_value_kernel  c -> o [R, d]                    (per head a [R,d] x [d,64] GEMM + bias, mma.sync)
 //
-// latent_attn_kernel: one CTA per clip, the whole latent width d in the CTA, 128-key tiles, TWO passes over each tile
-// (a tile is 128 keys x d = 320 KB at d = 1280: it cannot stay in shared memory between the scores and the context
-// product; narrower tiles, a d-split over a cluster and scores on tcgen05 were all measured slower - git history).
-// The second pass finds the tile in L2 (one TMA thread requests A(j) | B(j) | A(j+1) ... in that order, first-pass
-// loads carry an evict_last hint, second-pass loads evict_first), so HBM sees every source row once.
+// latent_attn_kernel: one CTA per clip, the whole latent width d in the CTA, 128-key tiles, TWO passes over each tile.
+// A tile is 128 keys x d = 320 KB at d = 1280: it cannot stay in shared memory between the scores and the context
+// product.  The alternatives were built and measured first (git history): d split over a 5-CTA cluster with the partial
+// scores exchanged through DSMEM (354 us at 128 clips x 1500 keys, large-v2), one pass over 32-key tiles with a
+// 1.9-tile ring (320 us: the tile-synchronous release serialises load latency, softmax and ~4700 MMAs).  Here the
+// second pass finds the tile in L2 - pass A is requested at most one tile ahead of pass B, first-pass loads carry an
+// evict_last hint, second-pass loads evict_first - so HBM still sees every source row once (124 us).
 //   pass A  TMA chunks [128 keys x 64 columns] (ring A) -> S^T[128 keys x 32 heads] += chunk (A, K-major) x q'^T (B,
 //           resident) with tcgen05.mma into TMEM; a chunk is freed by the commit of its four MMAs
 //   softmax thread = key; the reference maximum of a head only moves when a score exceeds it by more than 2^8, so the
 //           common tile needs no cross-thread reduction at all; P^T (bf16) -> smem
 //   pass B  TMA stages [128 keys x 128 columns] (ring B) -> C^T[128 columns x 32 heads] += stage^T (A, MN-major) x
 //           P^T (B) with tcgen05.mma into TMEM, d / 128 accumulators
-// Each pass has its own MMA-issuing thread.  The kernel is bound by the tensor pipe: a tcgen05.mma with N = 32 costs
-// ~95 clk whatever its size (operand fetch from shared memory), 160 of them per tile.  Scores on mma.sync in the
-// softmax warps instead (so that the two passes use different pipes) measured slower: ~32 clk per m16n8k16.
+// Each pass has its own TMA thread and its own MMA-issuing thread.  What bounds it (profiles/r01_latent_*.txt): a
+// narrow tcgen05.mma (N <= 64) occupies the SM's tensor front end for 40 clk whatever its shape and 53 clk when a
+// single thread issues it (tools/probe/mma_cost.cu), so the 1920 MMAs of a clip cost >= 41 us; on top of that both
+// rings together hold 144 KB, which at ~1.5 us of loaded HBM / L2 latency feeds ~100 GB/s per SM - the issuing
+// threads wait ~400-500 clk per chunk for data.  With the loads removed the kernel runs in 99 us, with pass-A loads
+// only in 114 us.  L2 prefetch ahead of pass A and a longer lead of pass A both thrash L2 (133-178 us); scores on
+// mma.sync in the softmax warps cost ~32 clk per m16n8k16 (141 us).
 // Output c_h = C^T[:, h] / l_h.
 #include "common.cuh"
 #include "kernels.h"
@@ -46,29 +52,14 @@ static constexpr int LA_SMEM_LIMIT = 227 * 1024;
 static constexpr int LA_TMEM_COLS = 512;            // S^T (2 x 32) | C^T (d / 128 accumulators x 32)
 static constexpr int LA_TMEM_C = 2 * LA_NH;
 static constexpr int LA_THREADS = 256;
-#ifndef LA_LEAD
-#define LA_LEAD 1      // tiles pass A may be requested ahead of pass B
-#endif
 #ifndef LA_PF
-#define LA_PF 0        // L2 prefetch ahead of pass A (measured: 124 -> 140 us)
+#define LA_PF 0        // chunks prefetched into L2 ahead of pass A (measured: 6 -> 133 us, 12 -> 141 us, 24 -> 178 us vs 124)
+#endif
+#ifndef LA_LEAD
+#define LA_LEAD 1      // tiles pass A may be requested ahead of pass B (measured: 0 -> 190 us, 2 -> 139 us vs 124)
 #endif
 
-// non-blocking probe of an mbarrier phase (a thread that serves two queues must not sleep in try_wait)
-__device__ __forceinline__ bool la_test_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void la_ldsm_x4(uint32_t (&r)[4], uint32_t smem_addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_addr));
-}
+
 __device__ __forceinline__ void la_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ uint64_t la_policy_evict_last() {
   uint64_t p;
@@ -110,6 +101,7 @@ latent_attn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   float* linv_buf = al_buf + 32;                     // [32]
   float* red = linv_buf + 32;                        // [4][32]
   int* flag_buf = reinterpret_cast<int*>(red + 128); // [2][4]
+  volatile int* prog = flag_buf + 8;                 // [2] tiles fully requested by the pass-A / pass-B producer
   uint64_t* bars = reinterpret_cast<uint64_t*>(misc + 1536);
   uint64_t* full_a = bars;                           // [NA]
   uint64_t* empty_a = full_a + LA_MAX_A;
@@ -135,6 +127,8 @@ latent_attn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     for (int i = 0; i < NA; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
     for (int i = 0; i < NB; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
     mbar_init(q_full, 1);
+    prog[0] = 0;
+    prog[1] = 0;
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 128); mbar_init(&p_ready[i], 128); mbar_init(&c_done[i], 1);
     }
@@ -147,61 +141,81 @@ latent_attn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0 && lane == 0) {
-    // ------------------------------------------------------------------ TMA producer (both passes, one request order)
-    // Pass B of tile j re-reads what pass A of tile j brought into L2, so the two must stay close: the order is
-    // A(0) | B(0) | A(1) | B(1) ...; while pass B waits for a free stage (softmax of its tile still running) the thread
-    // fills ring A with the next tile's chunks, never further than one tile ahead.
-    const uint64_t keep = la_policy_evict_last(), drop = l2_policy_evict_first();
-    const int total_a = n_tiles * 2 * NS;
-    const int q_after = total_a < NA ? total_a : NA;
-    int ja = 0, ca = 0, sa = 0, issued_a = 0;       // pass A cursor: tile, chunk, ring slot
-    int jb = 0, ab = 0, sb = 0;                     // pass B cursor: tile, stage, ring slot
-    uint32_t pha = 0, phb = 0;
+    // ------------------------------------------------------------------ TMA producer, pass A (chunks of 64 columns)
+    // Pass B of tile j re-reads what pass A of tile j brought into L2, so the two request streams stay close: pass A
+    // runs at most LA_LEAD tiles ahead of the tile pass B is requesting, pass B never requests a tile before pass A
+    // has (prog[0] / prog[1] = tiles fully requested by pass A / pass B).  One thread per ring: a single thread
+    // serving both was the bottleneck (~400 clk per request, 30 requests per tile).
+    const uint64_t keep = la_policy_evict_last();
+    int slot = 0, issued = 0;
+    uint32_t phase = 0;
+    const int q_after = n_tiles * 2 * NS < NA ? n_tiles * 2 * NS : NA;
     bool q_sent = false;
-    // HBM latency x the rate one SM needs is more than the rings can hold: chunks are prefetched into L2 PF chunks
-    // ahead of pass A, so both passes load at L2 latency
-    const int PF = LA_PF ? NS + 2 : 0;
-    int jp = LA_PF ? 0 : n_tiles, cp = 0;
-    for (int i = 0; i < PF && jp < n_tiles; ++i) {
-      la_tma_prefetch_2d(&map_x, cp * 64, b * T + jp * LA_KT);
-      if (++cp == 2 * NS) { cp = 0; ++jp; }
-    }
-    long long t0 = clock64();
-    while (jb < n_tiles) {
-      if (!q_sent && issued_a == q_after) {
-        pdl_wait();       // q' comes from the previous kernel; the source rows are static
-        mbar_arrive_expect_tx(q_full, 2 * NS * q_atom);
-        for (int i = 0; i < 2 * NS; ++i) tma_load_2d(qs + i * q_atom, &map_q, q_full, i * 64, b * H);
-        q_sent = true;
+    auto send_q = [&]() {
+      pdl_wait();       // q' comes from the previous kernel; the source rows are static
+      mbar_arrive_expect_tx(q_full, 2 * NS * q_atom);
+      for (int i = 0; i < 2 * NS; ++i) tma_load_2d(qs + i * q_atom, &map_q, q_full, i * 64, b * H);
+      q_sent = true;
+    };
+#if LA_PF > 0
+    // L2 prefetch LA_PF chunks ahead of the ring: HBM requests in flight without a shared-memory slot behind them
+    const int total = n_tiles * 2 * NS;
+    int pj = 0, pc = 0, pg = 0;
+    auto prefetch_next = [&]() {
+      if (pg < total) {
+        la_tma_prefetch_2d(&map_x, pc * 64, b * T + pj * LA_KT);
+        ++pg;
+        if (++pc == 2 * NS) { pc = 0; ++pj; }
       }
-      bool progressed = false;
-      if (ja > jb && la_test_wait(&empty_b[sb], phb ^ 1)) {
-        mbar_arrive_expect_tx(&full_b[sb], LA_STAGE_B);
-        uint8_t* dst = ring_b + sb * LA_STAGE_B;
-        la_tma_load_2d(dst, &map_x, &full_b[sb], ab * 128, b * T + jb * LA_KT, drop);
-        la_tma_load_2d(dst + LA_CHUNK, &map_x, &full_b[sb], ab * 128 + 64, b * T + jb * LA_KT, drop);
-        if (++ab == NS) { ab = 0; ++jb; }
-        if (++sb == NB) { sb = 0; phb ^= 1; }
-        progressed = true;
-      } else if (ja < n_tiles && ja <= jb + LA_LEAD && la_test_wait(&empty_a[sa], pha ^ 1)) {
-        mbar_arrive_expect_tx(&full_a[sa], LA_CHUNK);
-        la_tma_load_2d(ring_a + sa * LA_CHUNK, &map_x, &full_a[sa], ca * 64, b * T + ja * LA_KT, keep);
-        if (jp < n_tiles) {
-          la_tma_prefetch_2d(&map_x, cp * 64, b * T + jp * LA_KT);
-          if (++cp == 2 * NS) { cp = 0; ++jp; }
+    };
+    for (int i = 0; i < LA_PF; ++i) prefetch_next();
+#endif
+    for (int j = 0; j < n_tiles; ++j) {
+      if (j > LA_LEAD) {
+        const long long t0 = clock64();
+        while (prog[1] < j - LA_LEAD) {
+          if (clock64() - t0 > 4000000000LL) {
+            printf("libwf: latent attention pass-A producer timeout (block %d tile %d)\n", blockIdx.x, j);
+            __trap();
+          }
         }
-        if (++ca == 2 * NS) { ca = 0; ++ja; }
-        if (++sa == NA) { sa = 0; pha ^= 1; }
-        ++issued_a;
-        progressed = true;
       }
-      if (progressed) {
-        t0 = clock64();
-      } else if (clock64() - t0 > 4000000000LL) {
-        printf("libwf: latent attention producer timeout (block %d, pass A tile %d chunk %d, pass B tile %d stage %d)\n",
-               blockIdx.x, ja, ca, jb, ab);
-        __trap();
+      for (int c = 0; c < 2 * NS; ++c) {
+        if (!q_sent && issued == q_after) send_q();
+        mbar_wait(&empty_a[slot], phase ^ 1);
+        mbar_arrive_expect_tx(&full_a[slot], LA_CHUNK);
+        la_tma_load_2d(ring_a + slot * LA_CHUNK, &map_x, &full_a[slot], c * 64, b * T + j * LA_KT, keep);
+#if LA_PF > 0
+        prefetch_next();
+#endif
+        ++issued;
+        if (++slot == NA) { slot = 0; phase ^= 1; }
       }
+      prog[0] = j + 1;
+    }
+    if (!q_sent) send_q();
+  } else if (warp == 2 && lane == 0) {
+    // ------------------------------------------------------------------ TMA producer, pass B (stages of 128 columns)
+    const uint64_t drop = l2_policy_evict_first();
+    int slot = 0;
+    uint32_t phase = 0;
+    for (int j = 0; j < n_tiles; ++j) {
+      const long long t0 = clock64();
+      while (prog[0] <= j) {
+        if (clock64() - t0 > 4000000000LL) {
+          printf("libwf: latent attention pass-B producer timeout (block %d tile %d)\n", blockIdx.x, j);
+          __trap();
+        }
+      }
+      for (int a = 0; a < NS; ++a) {
+        mbar_wait(&empty_b[slot], phase ^ 1);
+        mbar_arrive_expect_tx(&full_b[slot], LA_STAGE_B);
+        uint8_t* dst = ring_b + slot * LA_STAGE_B;
+        la_tma_load_2d(dst, &map_x, &full_b[slot], a * 128, b * T + j * LA_KT, drop);
+        la_tma_load_2d(dst + LA_CHUNK, &map_x, &full_b[slot], a * 128 + 64, b * T + j * LA_KT, drop);
+        if (++slot == NB) { slot = 0; phase ^= 1; }
+      }
+      prog[1] = j + 1;
     }
   } else if (warp == 1 && lane == 0) {
     // ------------------------------------------------------------------ MMA issuer, pass A
@@ -212,21 +226,40 @@ latent_attn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     int slot = 0;
     uint32_t phase = 0;
     mbar_wait(q_full, 0);
+#ifdef LA_TIMING
+    long long tw = 0, tm = 0, tcm = 0, ts = 0, tt0 = clock64();
+#define LA_T(acc) do { const long long n_ = clock64(); acc += n_ - tl; tl = n_; } while (0)
+#else
+#define LA_T(acc)
+#endif
     for (int j = 0; j < n_tiles; ++j) {
+#ifdef LA_TIMING
+      long long tl = clock64();
+#endif
       if (j >= 2) mbar_wait(&s_free[j & 1], ((j >> 1) - 1) & 1);
+      LA_T(ts);
       for (int c = 0; c < 2 * NS; ++c) {
         mbar_wait(&full_a[slot], phase);
+        LA_T(tw);
         tc_fence_after();
         const uint64_t a_desc = umma_desc_kmajor_sw128(ra + slot * LA_CHUNK);
         const uint64_t b_desc = umma_desc_kmajor_sw128(qa + c * q_atom);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_f16(tmem_base + (j & 1) * LA_NH, a_desc + 2 * k, b_desc + 2 * k, idesc_s, (c | k) != 0);
+        LA_T(tm);
         umma_commit(&empty_a[slot]);
+        LA_T(tcm);
         if (++slot == NA) { slot = 0; phase ^= 1; }
       }
       umma_commit(&s_full[j & 1]);
     }
+#ifdef LA_TIMING
+    if (blockIdx.x == 0)
+      printf("issuer A per chunk: wait full %lld | 4 MMAs %lld | commit %lld ; per tile: wait s_free %lld ; total/tile %lld\n",
+             tw / (n_tiles * 2 * NS), tm / (n_tiles * 2 * NS), tcm / (n_tiles * 2 * NS), ts / n_tiles,
+             (clock64() - tt0) / n_tiles);
+#endif
   } else if (warp == 3 && lane == 0) {
     // ------------------------------------------------------------------ MMA issuer, pass B
     // C^T[128 columns x 32 heads] (+)= stage^T (A, MN-major: rows = keys, two 64-column atoms 16 KB apart) x P^T (B,
@@ -235,22 +268,37 @@ latent_attn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     const uint32_t rb = smem_u32(ring_b), pa = smem_u32(pt);
     int slot = 0;
     uint32_t phase = 0;
+#ifdef LA_TIMING
+    long long tw = 0, tm = 0, tcm = 0, ts = 0, tt0 = clock64();
+#endif
     for (int j = 0; j < n_tiles; ++j) {
+#ifdef LA_TIMING
+      long long tl = clock64();
+#endif
       mbar_wait(&p_ready[j & 1], (j >> 1) & 1);
+      LA_T(ts);
       const uint32_t pb = pa + (j & 1) * LA_PT;
       for (int a = 0; a < NS; ++a) {
         mbar_wait(&full_b[slot], phase);
+        LA_T(tw);
         tc_fence_after();
         const uint32_t st = rb + slot * LA_STAGE_B;
 #pragma unroll
         for (int kk = 0; kk < LA_KT / 16; ++kk)
           umma_f16(tmem_base + LA_TMEM_C + a * LA_NH, umma_desc_mnmajor_sw128(st + kk * 2048),
                    umma_desc_kmajor_sw128(pb + (kk >> 2) * LA_PATOM) + 2 * (kk & 3), idesc_c, (j > 0 || kk > 0) ? 1u : 0u);
+        LA_T(tm);
         umma_commit(&empty_b[slot]);
+        LA_T(tcm);
         if (++slot == NB) { slot = 0; phase ^= 1; }
       }
       umma_commit(&c_done[j & 1]);
     }
+#ifdef LA_TIMING
+    if (blockIdx.x == 0)
+      printf("issuer B per stage: wait full %lld | 8 MMAs %lld | commit %lld ; per tile: wait p_ready %lld ; total/tile %lld\n",
+             tw / (n_tiles * NS), tm / (n_tiles * NS), tcm / (n_tiles * NS), ts / n_tiles, (clock64() - tt0) / n_tiles);
+#endif
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ softmax (thread = key = TMEM lane of S^T)
     const int wq = warp - 4;
