@@ -55,9 +55,9 @@ static constexpr int LA_THREADS = 256;
 #ifndef LA_PF
 #define LA_PF 0        // chunks prefetched into L2 ahead of pass A (measured: 6 -> 133 us, 12 -> 141 us, 24 -> 178 us vs 124)
 #endif
-#ifndef LA_LEAD
-#define LA_LEAD 1      // tiles pass A may be requested ahead of pass B (measured: 0 -> 190 us, 2 -> 139 us vs 124)
-#endif
+#ifndef LA_AHEAD_PCT
+#define LA_AHEAD_PCT 50    // how far beyond its own tile pass A may be requested ahead of pass B, % of a tile
+#endif                     // (measured: 0 -> 190 us, 25 -> 128, 50 -> 123, 75 -> 129, 100 -> 136; more thrashes L2)
 
 
 __device__ __forceinline__ void la_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
@@ -143,9 +143,8 @@ latent_attn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------------ TMA producer, pass A (chunks of 64 columns)
     // Pass B of tile j re-reads what pass A of tile j brought into L2, so the two request streams stay close: pass A
-    // runs at most LA_LEAD tiles ahead of the tile pass B is requesting, pass B never requests a tile before pass A
-    // has (prog[0] / prog[1] = tiles fully requested by pass A / pass B).  One thread per ring: a single thread
-    // serving both was the bottleneck (~400 clk per request, 30 requests per tile).
+    // runs at most one tile plus LA_AHEAD_PCT % of a tile ahead of pass B, pass B never requests a tile before pass A
+    // has (prog[0] / prog[1] = 64-column chunks requested by pass A / pass B).  One thread per ring.
     const uint64_t keep = la_policy_evict_last();
     int slot = 0, issued = 0;
     uint32_t phase = 0;
@@ -170,18 +169,19 @@ latent_attn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     };
     for (int i = 0; i < LA_PF; ++i) prefetch_next();
 #endif
+    const int lim = 2 * NS + (2 * NS * LA_AHEAD_PCT) / 100;
     for (int j = 0; j < n_tiles; ++j) {
-      if (j > LA_LEAD) {
-        const long long t0 = clock64();
-        while (prog[1] < j - LA_LEAD) {
-          if (clock64() - t0 > 4000000000LL) {
-            printf("libwf: latent attention pass-A producer timeout (block %d tile %d)\n", blockIdx.x, j);
-            __trap();
-          }
-        }
-      }
       for (int c = 0; c < 2 * NS; ++c) {
         if (!q_sent && issued == q_after) send_q();
+        if (issued - prog[1] >= lim) {
+          const long long t0 = clock64();
+          while (issued - prog[1] >= lim) {
+            if (clock64() - t0 > 4000000000LL) {
+              printf("libwf: latent attention pass-A producer timeout (block %d tile %d)\n", blockIdx.x, j);
+              __trap();
+            }
+          }
+        }
         mbar_wait(&empty_a[slot], phase ^ 1);
         mbar_arrive_expect_tx(&full_a[slot], LA_CHUNK);
         la_tma_load_2d(ring_a + slot * LA_CHUNK, &map_x, &full_a[slot], c * 64, b * T + j * LA_KT, keep);
@@ -189,9 +189,9 @@ latent_attn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         prefetch_next();
 #endif
         ++issued;
+        prog[0] = issued;
         if (++slot == NA) { slot = 0; phase ^= 1; }
       }
-      prog[0] = j + 1;
     }
     if (!q_sent) send_q();
   } else if (warp == 2 && lane == 0) {
@@ -201,7 +201,7 @@ latent_attn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     uint32_t phase = 0;
     for (int j = 0; j < n_tiles; ++j) {
       const long long t0 = clock64();
-      while (prog[0] <= j) {
+      while (prog[0] < (j + 1) * 2 * NS) {
         if (clock64() - t0 > 4000000000LL) {
           printf("libwf: latent attention pass-B producer timeout (block %d tile %d)\n", blockIdx.x, j);
           __trap();
@@ -214,8 +214,8 @@ latent_attn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         la_tma_load_2d(dst, &map_x, &full_b[slot], a * 128, b * T + j * LA_KT, drop);
         la_tma_load_2d(dst + LA_CHUNK, &map_x, &full_b[slot], a * 128 + 64, b * T + j * LA_KT, drop);
         if (++slot == NB) { slot = 0; phase ^= 1; }
+        prog[1] = (j * NS + a + 1) * 2;
       }
-      prog[1] = j + 1;
     }
   } else if (warp == 1 && lane == 0) {
     // ------------------------------------------------------------------ MMA issuer, pass A
