@@ -589,3 +589,37 @@ def test_latent_cross_attention_matches_kv_attention(nv, H, B, T):
     # end to end against attention over projected K / V (what the reference computes); bf16 tolerance: the K / V
     # rounding of the cached path is replaced by the rounding of q' and of the context
     assert rel_l2(out, _latent_reference(q, src, wk, wv, bv, H)) < 1.5e-2
+
+
+def test_latent_cross_attention_headline_size(nv):
+    """BASELINE config 4 shapes (128 clips x 1500 encoder rows, 20 heads): the latent path against attention over
+    projected K / V, and two properties that do not need a reference: the result does not depend on which clips share
+    the launch (clip 5 alone == clip 5 inside the batch, bit for bit) and the context of every head is a convex
+    combination of source rows (bounded by the row-wise min / max of its clip)."""
+    from helpers import rel_l2
+    H, B, T = 20, 128, 1500
+    d = 64 * H
+    bf = torch.bfloat16
+    q = _randn(B, d, dtype=bf, seed=11)
+    src = _randn(B, T, d, dtype=bf, seed=12)
+    wk = _randn(d, d, dtype=bf, seed=13, scale=2.0 / math.sqrt(d))
+    wv = _randn(d, d, dtype=bf, seed=14, scale=1.0 / math.sqrt(d))
+    bv = _randn(d, seed=15, scale=0.1)
+    qp = torch.empty(B, H, d, dtype=bf, device="cuda")
+    ctx = torch.full((B, H, d), float("nan"), dtype=bf, device="cuda")
+    out = torch.full((B, d), float("nan"), dtype=bf, device="cuda")
+    nv.latent_query(q, wk.t().contiguous(), qp, H)
+    nv.latent_attention(qp, src, ctx, H)
+    nv.latent_value(ctx, wv, bv, out, H)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all() and torch.isfinite(ctx.float()).all()
+    for lo in range(0, B, 16):   # reference in slices: fp32 K and V of 16 clips are 2 x 123 MB
+        ref = _latent_reference(q[lo:lo + 16], src[lo:lo + 16], wk, wv, bv, H)
+        assert rel_l2(out[lo:lo + 16], ref) < 1.5e-2
+    lo_, hi_ = src.float().amin(dim=1), src.float().amax(dim=1)          # [B, d]
+    c = ctx.float()
+    assert (c >= lo_[:, None, :] - 2e-2).all() and (c <= hi_[:, None, :] + 2e-2).all()
+    one = torch.empty(1, H, d, dtype=bf, device="cuda")
+    nv.latent_attention(qp[5:6].contiguous(), src[5:6].contiguous(), one, H)
+    torch.cuda.synchronize()
+    assert torch.equal(one[0], ctx[5])
