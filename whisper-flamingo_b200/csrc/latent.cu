@@ -40,14 +40,18 @@
 
 namespace wf {
 
-static constexpr int LA_KT = 128;                   // keys per tile
+#ifndef LA_KEYS_PER_TILE
+#define LA_KEYS_PER_TILE 128
+#endif
+static constexpr int LA_KT = LA_KEYS_PER_TILE;      // keys per tile (128; 64 halves the L2 footprint, M = 64 score MMAs)
+static_assert(LA_KT == 64 || LA_KT == 128, "score MMAs are 64 or 128 rows");
 static constexpr int LA_CHUNK = LA_KT * 128;        // 16 KB: [128 keys x 64 columns] bf16, 128B-swizzled = one TMA box
 static constexpr int LA_STAGE_B = 2 * LA_CHUNK;     // 32 KB: 128 columns = the A operand of one context accumulator
 static constexpr int LA_NH = 32;                    // head columns of both MMAs (H <= 32)
 static constexpr int LA_PATOM = LA_NH * 128;        // 4 KB: P^T rows (heads) x 64 keys
-static constexpr int LA_PT = 2 * LA_PATOM;          // P^T operand of a tile: 32 heads x 128 keys
+static constexpr int LA_PT = (LA_KT / 64) * LA_PATOM;   // P^T operand of a tile: 32 heads x LA_KT keys
 static constexpr int LA_MISC = 3072;                // floats: m_ref[32] alpha[32] 1/l[32] red[4][32] | flags | barriers
-static constexpr int LA_MAX_A = 8, LA_MAX_B = 4;
+static constexpr int LA_MAX_A = 16, LA_MAX_B = 6;
 static constexpr int LA_SMEM_LIMIT = 227 * 1024;
 static constexpr int LA_TMEM_COLS = 512;            // S^T (2 x 32) | C^T (d / 128 accumulators x 32)
 static constexpr int LA_TMEM_C = 2 * LA_NH;
@@ -66,6 +70,11 @@ __device__ __forceinline__ uint64_t la_policy_evict_last() {
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
+__device__ __forceinline__ uint64_t la_policy_evict_normal() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
 __device__ __forceinline__ void la_tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
                                                uint64_t policy) {
   asm volatile(
@@ -82,6 +91,17 @@ __device__ __forceinline__ void la_tma_prefetch_2d(const CUtensorMap* map, int c
                : "memory");
 }
 
+// MN-major operand, 128B swizzle: rows = K index (128 B = 64 MN elements each), 8-row groups 1024 B apart (SBO), the
+// next 64 MN elements one chunk further (LBO)
+__device__ __forceinline__ uint64_t la_desc_mn(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu);
+  d |= static_cast<uint64_t>(LA_CHUNK >> 4) << 16;
+  d |= static_cast<uint64_t>(1024u >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
 // bf16 x bf16 -> fp32, A MN-major (bit 15), B K-major
 __host__ __device__ constexpr uint32_t la_idesc_a_mn(int M, int N) { return umma_idesc_bf16(M, N) | (1u << 15); }
 
@@ -145,7 +165,11 @@ latent_attn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     // Pass B of tile j re-reads what pass A of tile j brought into L2, so the two request streams stay close: pass A
     // runs at most one tile plus LA_AHEAD_PCT % of a tile ahead of pass B, pass B never requests a tile before pass A
     // has (prog[0] / prog[1] = 64-column chunks requested by pass A / pass B).  One thread per ring.
+#if defined(LA_HINT) && (LA_HINT & 1)
+    const uint64_t keep = la_policy_evict_normal();
+#else
     const uint64_t keep = la_policy_evict_last();
+#endif
     int slot = 0, issued = 0;
     uint32_t phase = 0;
     const int q_after = n_tiles * 2 * NS < NA ? n_tiles * 2 * NS : NA;
@@ -196,7 +220,11 @@ latent_attn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     if (!q_sent) send_q();
   } else if (warp == 2 && lane == 0) {
     // ------------------------------------------------------------------ TMA producer, pass B (stages of 128 columns)
+#if defined(LA_HINT) && (LA_HINT & 2)
+    const uint64_t drop = la_policy_evict_normal();
+#else
     const uint64_t drop = l2_policy_evict_first();
+#endif
     int slot = 0;
     uint32_t phase = 0;
     for (int j = 0; j < n_tiles; ++j) {
@@ -285,7 +313,7 @@ latent_attn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         const uint32_t st = rb + slot * LA_STAGE_B;
 #pragma unroll
         for (int kk = 0; kk < LA_KT / 16; ++kk)
-          umma_f16(tmem_base + LA_TMEM_C + a * LA_NH, umma_desc_mnmajor_sw128(st + kk * 2048),
+          umma_f16(tmem_base + LA_TMEM_C + a * LA_NH, la_desc_mn(st + kk * 2048),
                    umma_desc_kmajor_sw128(pb + (kk >> 2) * LA_PATOM) + 2 * (kk & 3), idesc_c, (j > 0 || kk > 0) ? 1u : 0u);
         LA_T(tm);
         umma_commit(&empty_b[slot]);
@@ -311,8 +339,12 @@ latent_attn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     pdl_wait();
     la_bar(1);
     // P^T element (head h, my key): atom = 64-key half, row = head (128 B), 16-byte units swizzled by the row
-    const uint32_t p_off = (tid >> 6) * LA_PATOM + (tid & 7) * 2;
-    const uint32_t p_unit = (tid & 63) >> 3;
+    // my key inside the tile: a 128-row accumulator keeps row r in lane r, a 64-row one keeps rows 16 q .. 16 q + 15
+    // in lanes 32 q .. 32 q + 15 (profiles/r01_probe_tmem_m64_layout.txt)
+    const int key = LA_KT == 128 ? tid : wq * 16 + (lane & 15);
+    const bool lane_on = LA_KT == 128 || lane < 16;
+    const uint32_t p_off = (key >> 6) * LA_PATOM + (key & 7) * 2;
+    const uint32_t p_unit = (key & 63) >> 3;
     for (int j = 0; j < n_tiles; ++j) {
       const int buf = j & 1;
       const uint32_t ph = (j >> 1) & 1;
@@ -323,7 +355,7 @@ latent_attn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&s_free[buf]);
-      const bool valid = j * LA_KT + tid < T;
+      const bool valid = lane_on && j * LA_KT + key < T;
       // does any score leave the window of its head's reference maximum?  (always on the first tile)
       bool exceed = false;
 #pragma unroll
@@ -421,12 +453,13 @@ int latent_attention(const void* qp, const void* src, void* ctx, int B, int T, i
              "latent attention: needs head_dim 64, an even number of heads and at most 32 of them (got %d heads)", H);
   const int hp = (H + 7) / 8 * 8, ns = d / 128;
   const int fixed = 1024 + 2 * ns * hp * 128 + 2 * LA_PT + LA_MISC;
-  const int n = (LA_SMEM_LIMIT - fixed) / LA_CHUNK;       // 16 KB units left for the two rings
+  const int n = (LA_SMEM_LIMIT - fixed) / LA_CHUNK;       // chunk-sized units left for the two rings
 #ifdef LA_NB_FORCE
-  const int nb = LA_NB_FORCE;
+  int nb = LA_NB_FORCE;
 #else
-  const int nb = n >= 12 ? 3 : 2;
+  int nb = (LA_KT == 128 ? (n >= 12 ? 3 : 2) : 4);
 #endif
+  if (nb > LA_MAX_B) nb = LA_MAX_B;
   int na = n - 2 * nb;
   if (na > LA_MAX_A) na = LA_MAX_A;
   WF_REQUIRE(na >= 2, "latent attention: shared memory too small for the rings (%d chunks)", n);
