@@ -239,9 +239,9 @@ def run_product(args):
 
 # DRAM bytes (read + write) per launch of a kernel family from the committed `ncu --set full` captures under profiles/
 # (large-v2 AV, B=128, greedy): attention_decode alternates a cross-attention (988.0 MB) and an x-attention (499.2 MB)
-# launch with the K/V-cache path and is x-attention only (497.0 MB) with the latent path; latent_attention: 568.0 MB read
-# + 4.5 MB written against 491.5 MB of source rows - 16 % of the second pass misses L2 (r01_ncu_full_latent_attn.txt)
-NCU_TRAFFIC = {"attention_decode": 497.0e6, "latent_attention": 572.5e6}
+# launch with the K/V-cache path and is x-attention only (497.0 MB) with the latent path; latent_attention: 608.7 MB read
+# + 4.0 MB written against 491.5 MB of source rows - part of the second pass misses L2 (r01_ncu_full_latent_attn.txt)
+NCU_TRAFFIC = {"attention_decode": 497.0e6, "latent_attention": 612.7e6}
 
 
 def launch_floor_ms(dev, n=256):

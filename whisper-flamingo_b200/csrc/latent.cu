@@ -21,8 +21,9 @@
 // 1.9-tile ring (320 us: the tile-synchronous release serialises load latency, softmax and ~4700 MMAs).  Here the
 // second pass finds the tile in L2 - pass A is requested at most one tile ahead of pass B, first-pass loads carry an
 // evict_last hint, second-pass loads evict_first - so HBM still sees every source row once (124 us).
-//   pass A  TMA chunks [128 keys x 64 columns] (ring A) -> S^T[128 keys x 32 heads] += chunk (A, K-major) x q'^T (B,
-//           resident) with tcgen05.mma into TMEM; a chunk is freed by the commit of its four MMAs
+//   pass A  TMA chunks [128 keys x 64 columns] + the matching 64-column atom of q' (ring A; q' is re-read from L2 for
+//           every tile so that its 60 KB go to the rings) -> S^T[128 keys x 32 heads] += chunk (A, K-major) x q'^T (B)
+//           with tcgen05.mma into TMEM; a slot is freed by the commit of its four MMAs
 //   softmax thread = key; the reference maximum of a head only moves when a score exceeds it by more than 2^8, so the
 //           common tile needs no cross-thread reduction at all; P^T (bf16) -> smem
 //   pass B  TMA stages [128 keys x 128 columns] (ring B) -> C^T[128 columns x 32 heads] += stage^T (A, MN-major) x
@@ -59,6 +60,10 @@ static constexpr int LA_THREADS = 256;
 #ifndef LA_PF
 #define LA_PF 0        // chunks prefetched into L2 ahead of pass A (measured: 6 -> 133 us, 12 -> 141 us, 24 -> 178 us vs 124)
 #endif
+#ifndef LA_STREAM_Q
+#define LA_STREAM_Q 1      // 1: the q' atom of a chunk travels with the chunk through ring A (re-read from L2 every tile)
+#endif                     //    instead of all of q' staying resident: 60 KB more for the rings at d = 1280
+                           //    (measured: resident, rings 5 + 2: 123 us; streamed, 7 + 2: 129 us, 5 + 3: 115 us, 4 + 4: 114 us)
 #ifndef LA_AHEAD_PCT
 #define LA_AHEAD_PCT 50    // how far beyond its own tile pass A may be requested ahead of pass B, % of a tile
 #endif                     // (measured: 0 -> 190 us, 25 -> 128, 50 -> 123, 75 -> 129, 100 -> 136; more thrashes L2)
@@ -110,11 +115,12 @@ latent_attn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                    __nv_bfloat16* __restrict__ ctx, int T, int H, int HP, int NS, int NA, int NB, float sl2) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* ring_a = smem;                            // NA chunks
-  uint8_t* ring_b = ring_a + NA * LA_CHUNK;          // NB stages
-  uint8_t* qs = ring_b + NB * LA_STAGE_B;            // q': d / 64 K-major atoms of HP rows (heads)
   const int q_atom = HP * 128;
-  uint8_t* pt = qs + 2 * NS * q_atom;                // P^T operand, double-buffered
+  const int slot_a = LA_CHUNK + (LA_STREAM_Q ? q_atom : 0);   // ring-A slot: chunk (+ its q' atom)
+  uint8_t* ring_a = smem;                            // NA slots
+  uint8_t* ring_b = ring_a + NA * slot_a;            // NB stages
+  uint8_t* qs = ring_b + NB * LA_STAGE_B;            // q': d / 64 K-major atoms of HP rows (heads), unless streamed
+  uint8_t* pt = qs + (LA_STREAM_Q ? 0 : 2 * NS * q_atom);   // P^T operand, double-buffered
   uint8_t* misc = pt + 2 * LA_PT;
   float* m_buf = reinterpret_cast<float*>(misc);     // [32] reference maximum of each head
   float* al_buf = m_buf + 32;                        // [32] rescale factor when the reference moved
@@ -176,8 +182,14 @@ latent_attn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     bool q_sent = false;
     auto send_q = [&]() {
       pdl_wait();       // q' comes from the previous kernel; the source rows are static
+#if LA_STREAM_Q
+      // the chunks requested so far wait for their q' atoms (slot i holds chunk i: issued <= NA)
+      for (int i = 0; i < issued; ++i)
+        tma_load_2d(ring_a + i * slot_a + LA_CHUNK, &map_q, &full_a[i], (i % (2 * NS)) * 64, b * H);
+#else
       mbar_arrive_expect_tx(q_full, 2 * NS * q_atom);
       for (int i = 0; i < 2 * NS; ++i) tma_load_2d(qs + i * q_atom, &map_q, q_full, i * 64, b * H);
+#endif
       q_sent = true;
     };
 #if LA_PF > 0
@@ -207,8 +219,11 @@ latent_attn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           }
         }
         mbar_wait(&empty_a[slot], phase ^ 1);
-        mbar_arrive_expect_tx(&full_a[slot], LA_CHUNK);
-        la_tma_load_2d(ring_a + slot * LA_CHUNK, &map_x, &full_a[slot], c * 64, b * T + j * LA_KT, keep);
+        mbar_arrive_expect_tx(&full_a[slot], slot_a);
+        la_tma_load_2d(ring_a + slot * slot_a, &map_x, &full_a[slot], c * 64, b * T + j * LA_KT, keep);
+#if LA_STREAM_Q
+        if (q_sent) tma_load_2d(ring_a + slot * slot_a + LA_CHUNK, &map_q, &full_a[slot], c * 64, b * H);
+#endif
 #if LA_PF > 0
         prefetch_next();
 #endif
@@ -253,7 +268,9 @@ latent_attn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     const uint32_t ra = smem_u32(ring_a), qa = smem_u32(qs);
     int slot = 0;
     uint32_t phase = 0;
+#if !LA_STREAM_Q
     mbar_wait(q_full, 0);
+#endif
 #ifdef LA_TIMING
     long long tw = 0, tm = 0, tcm = 0, ts = 0, tt0 = clock64();
 #define LA_T(acc) do { const long long n_ = clock64(); acc += n_ - tl; tl = n_; } while (0)
@@ -270,8 +287,8 @@ latent_attn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         mbar_wait(&full_a[slot], phase);
         LA_T(tw);
         tc_fence_after();
-        const uint64_t a_desc = umma_desc_kmajor_sw128(ra + slot * LA_CHUNK);
-        const uint64_t b_desc = umma_desc_kmajor_sw128(qa + c * q_atom);
+        const uint64_t a_desc = umma_desc_kmajor_sw128(ra + slot * slot_a);
+        const uint64_t b_desc = umma_desc_kmajor_sw128(LA_STREAM_Q ? ra + slot * slot_a + LA_CHUNK : qa + c * q_atom);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_f16(tmem_base + (j & 1) * LA_NH, a_desc + 2 * k, b_desc + 2 * k, idesc_s, (c | k) != 0);
@@ -452,7 +469,9 @@ int latent_attention(const void* qp, const void* src, void* ctx, int B, int T, i
   WF_REQUIRE(B > 0 && T > 0 && H > 0 && H <= LA_NH && d % 128 == 0,
              "latent attention: needs head_dim 64, an even number of heads and at most 32 of them (got %d heads)", H);
   const int hp = (H + 7) / 8 * 8, ns = d / 128;
-  const int fixed = 1024 + 2 * ns * hp * 128 + 2 * LA_PT + LA_MISC;
+  const int q_atom = hp * 128;
+  const int fixed = 1024 + (LA_STREAM_Q ? 0 : 2 * ns * q_atom) + 2 * LA_PT + LA_MISC;
+  const int slot_a = LA_CHUNK + (LA_STREAM_Q ? q_atom : 0);
   const int n = (LA_SMEM_LIMIT - fixed) / LA_CHUNK;       // chunk-sized units left for the two rings
 #ifdef LA_NB_FORCE
   int nb = LA_NB_FORCE;
@@ -460,10 +479,10 @@ int latent_attention(const void* qp, const void* src, void* ctx, int B, int T, i
   int nb = (LA_KT == 128 ? (n >= 12 ? 3 : 2) : 4);
 #endif
   if (nb > LA_MAX_B) nb = LA_MAX_B;
-  int na = n - 2 * nb;
+  int na = (LA_SMEM_LIMIT - fixed - nb * LA_STAGE_B) / slot_a;
   if (na > LA_MAX_A) na = LA_MAX_A;
   WF_REQUIRE(na >= 2, "latent attention: shared memory too small for the rings (%d chunks)", n);
-  const int smem = fixed + (na + 2 * nb) * LA_CHUNK;
+  const int smem = fixed + na * slot_a + nb * LA_STAGE_B;
   CUtensorMap mx, mq;
   int rc = make_map_bf16(&mx, src, static_cast<long long>(B) * T, d, d, LA_KT);
   if (rc) return rc;
