@@ -20,7 +20,7 @@
 // scores exchanged through DSMEM (354 us at 128 clips x 1500 keys, large-v2), one pass over 32-key tiles with a
 // 1.9-tile ring (320 us: the tile-synchronous release serialises load latency, softmax and ~4700 MMAs).  Here the
 // second pass finds the tile in L2 - pass A is requested at most one tile ahead of pass B, first-pass loads carry an
-// evict_last hint, second-pass loads evict_first - so HBM still sees every source row once (124 us).
+// evict_last hint, second-pass loads evict_first - so HBM sees (nearly) every source row once.
 //   pass A  TMA chunks [128 keys x 64 columns] + the matching 64-column atom of q' (ring A; q' is re-read from L2 for
 //           every tile so that its 60 KB go to the rings) -> S^T[128 keys x 32 heads] += chunk (A, K-major) x q'^T (B)
 //           with tcgen05.mma into TMEM; a slot is freed by the commit of its four MMAs
@@ -30,11 +30,13 @@
 //           P^T (B) with tcgen05.mma into TMEM, d / 128 accumulators
 // Each pass has its own TMA thread and its own MMA-issuing thread.  What bounds it (profiles/r01_latent_*.txt): a
 // narrow tcgen05.mma (N <= 64) occupies the SM's tensor front end for 40 clk whatever its shape and 53 clk when a
-// single thread issues it (tools/probe/mma_cost.cu), so the 1920 MMAs of a clip cost >= 41 us; on top of that both
-// rings together hold 144 KB, which at ~1.5 us of loaded HBM / L2 latency feeds ~100 GB/s per SM - the issuing
-// threads wait ~400-500 clk per chunk for data.  With the loads removed the kernel runs in 99 us, with pass-A loads
-// only in 114 us.  L2 prefetch ahead of pass A and a longer lead of pass A both thrash L2 (133-178 us); scores on
-// mma.sync in the softmax warps cost ~32 clk per m16n8k16 (141 us).
+// single thread issues it (tools/probe/mma_cost.cu), so the 1920 MMAs of a clip cost >= 41 us; the wall is the data
+// path: with q' resident the two rings held 144 KB, which at ~1.5 us of loaded HBM / L2 latency feeds ~100 GB/s per
+// SM - the issuing threads waited ~400-500 clk per chunk (124 us; 99 us with all loads removed, 114 us with pass-A
+// loads only).  Streaming q' with the chunks gives the rings 191 KB: 115 us.  L2 prefetch ahead of pass A and a
+// longer lead of pass A both thrash L2 (133-178 us), the second pass must carry evict_first (152 us without), 64-key
+// tiles pay more in hand-offs than they save in L2 misses (167 us), scores on mma.sync in the softmax warps cost
+// ~32 clk per m16n8k16 (141 us).
 // Output c_h = C^T[:, h] / l_h.
 #include "common.cuh"
 #include "kernels.h"
