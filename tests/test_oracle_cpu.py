@@ -268,3 +268,40 @@ def test_load_model_accepts_fork_lightning_and_upstream_checkpoints(tmp_path):
         assert all(torch.equal(gsd[k], sd[k]) for k in sd), path
     with pytest.raises(RuntimeError):
         whisper.load_model("no-such-model")
+
+
+# ----------------------------------------------------------------------------- latent cross-attention (host side)
+def test_absorbed_projection_identity_against_oracle_mha():
+    """The algebra csrc/latent.cu relies on, in fp64 against the oracle's restatement of model.py:82-108:
+    with q'_h = Wk_h^T q_h, c_h = softmax(xa q'_h / 8)^T xa and o_h = Wv_h c_h + bv_h the one-token cross-attention
+    equals attention over K = xa Wk^T, V = xa Wv^T + bv (the softmax weights sum to one, so the value bias passes)."""
+    g = torch.Generator().manual_seed(7)
+    B, T, H = 2, 37, 3
+    d = 64 * H
+    r = lambda *shape: torch.randn(*shape, generator=g, dtype=torch.float64)
+    sd = {"a.query.weight": r(d, d) / d ** 0.5, "a.query.bias": r(d) * 0.1, "a.key.weight": r(d, d) / d ** 0.5,
+          "a.value.weight": r(d, d) / d ** 0.5, "a.value.bias": r(d) * 0.1, "a.out.weight": r(d, d) / d ** 0.5,
+          "a.out.bias": r(d) * 0.1}
+    x, xa = r(B, 1, d), r(B, T, d)
+    want = om.mha(sd, "a", H, x, xa)
+    q = x[:, 0] @ sd["a.query.weight"].T + sd["a.query.bias"]                          # [B, d]
+    qp = torch.einsum("bhj,hjn->bhn", q.view(B, H, 64), sd["a.key.weight"].view(H, 64, d))    # q'_h = Wk_h^T q_h
+    w = torch.softmax(torch.einsum("bhn,btn->bht", qp, xa) * 0.125, dim=-1)
+    c = torch.einsum("bht,btn->bhn", w, xa)                                            # context in source space
+    o = torch.einsum("bhn,hjn->bhj", c, sd["a.value.weight"].view(H, 64, d)).reshape(B, d) + sd["a.value.bias"]
+    got = (o @ sd["a.out.weight"].T + sd["a.out.bias"])[:, None]
+    # the oracle keeps the reference's fp32 softmax (model.py:104), everything else here is fp64
+    assert torch.allclose(got, want, rtol=0, atol=5e-7), float((got - want).abs().max())
+
+
+def test_latent_path_gate(monkeypatch):
+    """whisper/_engine.py:latent_cross_enabled - greedy rows only, head_dim 64, at most 32 heads, default from 112 rows."""
+    from whisper._engine import latent_cross_enabled as on
+    monkeypatch.delenv("WF_LATENT", raising=False)
+    assert on(128, 1, 20, 1280) and on(112, 1, 16, 1024) and not on(111, 1, 20, 1280)
+    assert not on(128, 5, 16, 1024)            # beams share a cache: cached-K/V multi-query kernel
+    assert not on(128, 1, 40, 2560) and not on(128, 1, 20, 1024) and not on(128, 1, 5, 320)
+    monkeypatch.setenv("WF_LATENT", "1")
+    assert on(2, 1, 6, 384) and not on(2, 5, 6, 384)
+    monkeypatch.setenv("WF_LATENT", "0")
+    assert not on(128, 1, 20, 1280)
