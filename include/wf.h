@@ -202,6 +202,11 @@ int wf_topk_logprobs(const wf_topk_t* args, wf_stream_t stream);
 int wf_kv_gather_rows(const void* src, void* dst, const int* src_index, int R, long long row_bytes,
                       long long used_bytes, wf_stream_t stream);
 
+/* Test hook for the temperature > 0 sampler (decoding.py:286-287 replaced by Gumbel-max over a counter RNG):
+ * out_min_max[0], [1] (device floats) = smallest / largest of n uniforms drawn the way wf_sample_greedy draws them.
+ * Both must lie strictly inside (0, 1), otherwise -log(-log u) is infinite and a random token wins the argmax. */
+int wf_debug_uniform_range(unsigned long long seed, long long n, float* out_min_max, wf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -206,7 +206,8 @@ def _run_group(sd, dims: om.Dims, spec: DecodeSpec, xa: Tensor, feat: Optional[T
     sum_lp = torch.zeros(tokens.shape[0])
     no_speech = [float("nan")] * tokens.shape[0]
     beam = BeamState(spec) if spec.beam_size is not None else None
-    xt_list = None if feat is None else [feat]
+    # one feature tensor, or a list of them (multi-"language" gated x-attention, model.py:171-199)
+    xt_list = None if feat is None else (list(feat) if isinstance(feat, (list, tuple)) else [feat])
     for i in range(spec.sample_len):
         logits = om.decoder_forward(sd, dims, tokens, xa, xt_list=xt_list)
         if i == 0 and spec.no_speech is not None:
@@ -251,6 +252,29 @@ def decode(sd, dims: om.Dims, spec: DecodeSpec, mel: Tensor, feat: Optional[Tens
     out = []
     g = spec.beam_size
     for b in range(xa.shape[0]):  # reference beams: one audio at a time
-        f = None if feat is None else feat[b:b + 1].repeat_interleave(g, 0)
+        if feat is None:
+            f = None
+        elif isinstance(feat, (list, tuple)):
+            f = [x[b:b + 1].repeat_interleave(g, 0) for x in feat]
+        else:
+            f = feat[b:b + 1].repeat_interleave(g, 0)
         out += _run_group(sd, dims, spec, xa[b:b + 1].repeat_interleave(g, 0), f, g, trace)
     return out
+
+
+@torch.no_grad()
+def detect_language(sd, dims: om.Dims, xa: Tensor, sot: int, language_tokens: Sequence[int],
+                    feat=None) -> Tuple[List[int], Tensor]:
+    """detect_language, decoding.py:18-77: one decoder pass over [sot], every non-language logit set to -inf,
+    argmax + softmax.  Returns (most probable language token per clip, probabilities [B, len(language_tokens)] in the
+    order of ``language_tokens``).  ``feat``: feature tensor / list for a gated x-attn model - the reference's
+    ``Whisper.logits`` forgets it and crashes there (model.py:374-375), the restatement supplies it."""
+    x = torch.tensor([[sot]] * xa.shape[0])
+    xt_list = None if feat is None else (list(feat) if isinstance(feat, (list, tuple)) else [feat])
+    logits = om.decoder_forward(sd, dims, x, xa, xt_list=xt_list)[:, 0]
+    mask = torch.ones(logits.shape[-1], dtype=torch.bool)
+    mask[list(language_tokens)] = False
+    logits[:, mask] = -np.inf
+    best = logits.argmax(dim=-1).tolist()
+    probs = logits.softmax(dim=-1)[:, list(language_tokens)]
+    return best, probs

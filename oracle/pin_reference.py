@@ -245,6 +245,65 @@ def main():
         "segments": [{k: (s[k] if k != "tokens" else list(map(int, s[k]))) for k in
                       ("id", "seek", "start", "end", "text", "tokens", "temperature", "avg_logprob", "no_speech_prob")}
                      for s in tr["segments"]]}
+    # 3f. detect_language (decoding.py:18-77) on the audio-only model, 2 clips; and decode() with language=None
+    ltoks, lprobs = model_a.detect_language(mel2)
+    tk_a = DecodingTask(model_a, opt).tokenizer
+    lang_ids = list(tk_a.all_language_tokens)
+    xa2_or = om.encoder_forward(sd_a, odims, mel2)
+    o_best, o_probs = odec.detect_language(sd_a, odims, xa2_or, tk_a.sot, lang_ids)
+    assert o_best == ltoks.tolist(), "detected language tokens differ"
+    for i in range(2):
+        check(f"language probs clip {i}", o_probs[i].numpy(), [lprobs[i][c] for c in tk_a.all_language_codes], 1e-6)
+    opt_auto = DecodingOptions(language=None, without_timestamps=True, sample_len=12, fp16=False)
+    res_auto = model_a.decode(mel2, opt_auto)
+    print(f"  [ok] detect_language: tokens {ltoks.tolist()} -> {[r.language for r in res_auto]}")
+    dec_gold["detect_language"] = {
+        "language_tokens": ltoks.tolist(), "languages": [r.language for r in res_auto],
+        "top_prob": [max(p.values()) for p in lprobs],
+        "probs_en": [p["en"] for p in lprobs],
+        "auto_tokens": [r.tokens for r in res_auto], "auto_avg_logprob": [r.avg_logprob for r in res_auto]}
+    # oracle decode with the detected language spliced into the prompt, clip by clip
+    for i in range(2):
+        init = list(spec.initial_tokens)
+        init[spec.sot_index + 1] = int(ltoks[i])
+        sp = odec.DecodeSpec(**{**spec.__dict__, "initial_tokens": tuple(init), "sample_len": 12})
+        got = odec.decode(sd_a, odims, sp, mel2[i:i + 1])
+        assert got[0].tokens == res_auto[i].tokens, f"language=None decode differs (clip {i})"
+    print("  [ok] decode(language=None) tokens identical to the oracle with the detected language token")
+    # 3g. multi-feature gated x-attention (num_langs = 3, the fork's real calling mode: trilingual.py:256,304):
+    # teacher-forced logits and a greedy loop with xt_list of 3 tensors of different lengths / widths
+    model_m = Whisper(dims, 0.0, False, 256, 1, 1024, 3).eval()
+    synth.init_synthetic_(model_m, seed=0)
+    sd_m = om.cast_state_dict_fp32(model_m.state_dict())
+    feats3 = [synth.synthetic_features(2, n_frames=n, dim=w, seed=4321 + j)
+              for j, (n, w) in enumerate(((100, 1024), (37, 1024), (64, 384)))]
+    toks2 = toks.repeat(2, 1)
+    with torch.no_grad():
+        xa_m = model_m.encoder(mel2)
+        lg_m = model_m.decoder(toks2, xa_m, xt_list=feats3)
+        lg_m2 = model_m.decoder(toks2, xa_m, xt_list=feats3[:2])   # fewer tensors than num_langs is allowed
+        lg_mo = om.decoder_forward(sd_m, odims, toks2, om.encoder_forward(sd_m, odims, mel2), xt_list=feats3)
+    check("multi-feature decoder logits (oracle vs ref)", lg_mo, lg_m, 2e-4)
+    task_m = DecodingTask(model_m, opt_av)
+    task_m.decoder.reset()
+    tokens_m = torch.tensor([task_m.initial_tokens]).repeat(2, 1)
+    sum_lp_m = torch.zeros(2)
+    with torch.no_grad():
+        for i in range(12):
+            lgs = model_m.decoder(tokens_m, xa_m, xt_list=feats3)[:, -1]
+            for f in task_m.logit_filters:
+                f.apply(lgs, tokens_m)
+            tokens_m, done = task_m.decoder.update(tokens_m, lgs, sum_lp_m)
+    spec_m = odec.DecodeSpec(**{**spec_av.__dict__, "sample_len": 12})
+    ores_m = odec.decode(sd_m, odims, spec_m, mel2, feats3)
+    ref_m = [row[task_m.sample_begin:] for row in tokens_m.tolist()]
+    assert [r.tokens for r in ores_m] == ref_m, "multi-feature greedy tokens differ"
+    print(f"  [ok] multi-feature (3 tensors) greedy tokens identical: {ref_m[0][:6]}...")
+    net_multi = {"logits3_samples": lg_m.reshape(-1)[::1009].numpy(), "logits2_samples": lg_m2.reshape(-1)[::1009].numpy(),
+                 "tokens": toks2.numpy()}
+    np.savez_compressed(os.path.join(GOLD, "net_tiny_multi.npz"), **net_multi)
+    dec_gold["greedy_multi3"] = {"spec": spec_to_json(spec_m), "tokens": ref_m,
+                                 "feat_shapes": [[100, 1024], [37, 1024], [64, 384]], "feat_seeds": [4321, 4322, 4323]}
     with open(os.path.join(GOLD, "decode_tiny.json"), "w") as fh:
         json.dump({"meta": meta, "dims": TINY, "cases": dec_gold}, fh, indent=1)
     print("golden fixtures written to", GOLD)

@@ -406,7 +406,10 @@ def test_attention_full_vs_torch(nv, dtype, tol, B, Tq, Tk, H, causal):
                                           (32, 1, 12, 750, False), (20, 5, 16, 1500, False), (64, 1, 6, 300, False),
                                           (50, 2, 6, 257, False),
                                           # beams sharing a cache: tensor-core multi-query kernel (head-major bf16)
-                                          (4, 8, 6, 700, False), (6, 4, 12, 1500, False), (3, 6, 20, 128, False)])
+                                          (4, 8, 6, 700, False), (6, 4, 12, 1500, False), (3, 6, 20, 128, False),
+                                          # any group size: 7 in one pass, 10 / 15 / 17 in chunks of <= 8 queries
+                                          (3, 7, 6, 1500, False), (2, 10, 12, 750, False), (2, 15, 6, 300, False),
+                                          (2, 17, 6, 100, False), (2, 9, 6, 40, True)])
 @pytest.mark.parametrize("head_major", [False, True])
 def test_attention_decode_vs_torch(nv, dtype, tol, B, G, H, Tk, dyn, head_major):
     d, R, cap = H * 64, B * G, 448
@@ -429,7 +432,52 @@ def test_attention_decode_vs_torch(nv, dtype, tol, B, G, H, Tk, dyn, head_major)
     assert (out.float() - want).abs().max().item() <= tol
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("R,H,cap,length", [(10, 6, 32, 17), (130, 16, 70, 70), (320, 16, 69, 41), (7, 20, 448, 300)])
+def test_attention_decode_paged_row_table_vs_torch(nv, dtype, tol, R, H, cap, length):
+    """wf_attention_decode_paged (beam search: reference rearrange_kv_cache, decoding.py:173-180, done by rewriting a
+    [rows, T_cap] table instead of moving K/V): key j of row r is read from cache entry row_table[r, j].  Checked with a
+    random table per position against a torch gather, head-major cache [R, 2H, T_cap, 64] with the length in device
+    memory - the layout and call the R > 128 beam session (BASELINE config 3) makes."""
+    d = H * 64
+    q = _randn(R, d, dtype=dtype, seed=11)
+    cache = _randn(R, 2 * H, cap, 64, dtype=dtype, seed=12)
+    g = torch.Generator(device="cpu").manual_seed(13)
+    table = torch.randint(0, R, (R, cap), generator=g, dtype=torch.int32).cuda()
+    out = torch.full((R, d), float("nan"), dtype=dtype, device="cuda")
+    ws = torch.empty(nv.attention_decode_workspace_bytes(R, H), dtype=torch.uint8, device="cuda")
+    lp = torch.tensor([length - 1], dtype=torch.int32, device="cuda")
+    nv.attention_decode(q, cache, cache[:, H:], 64, 2 * H * cap * 64, cap * 64, out, 1, H, lp, 1, cap, ws,
+                        row_table=table)
+    # gathered[r, :, j] = cache[table[r, j], :, j]
+    idx = table[:, :length].long()
+    pos = torch.arange(length, device="cuda")[None, :].expand(R, -1)
+    gathered = cache.float()[idx, :, pos]                       # [R, length, 2H, 64]
+    k = gathered[:, :, :H].reshape(R * length, d)
+    v = gathered[:, :, H:].reshape(R * length, d)
+    want = _ref_attention(q, k, v, R, 1, length, H, False)
+    assert (out.float() - want).abs().max().item() <= tol
+    # identity table == the un-paged call
+    ident = torch.arange(R, dtype=torch.int32, device="cuda")[:, None].repeat(1, cap).contiguous()
+    out2 = torch.empty_like(out)
+    nv.attention_decode(q, cache, cache[:, H:], 64, 2 * H * cap * 64, cap * 64, out2, 1, H, lp, 1, cap, ws,
+                        row_table=ident)
+    out3 = torch.empty_like(out)
+    nv.attention_decode(q, cache, cache[:, H:], 64, 2 * H * cap * 64, cap * 64, out3, 1, H, lp, 1, cap, ws)
+    assert (out2.float() - out3.float()).abs().max().item() <= tol
+
+
 # ----------------------------------------------------------------------------- sampling
+def test_sampler_uniform_is_strictly_inside_unit_interval(nv):
+    """The Gumbel-max sampler draws u with a counter RNG; u == 1 (or 0) makes -log(-log u) infinite and that token wins
+    whatever its logit (24 random bits + 0.5 rounds up to 2^24 in fp32).  2^28 draws hit the extreme
+    buckets of a 23-bit uniform ~32 times each: min / max must be exactly the ends of [2^-24, 1 - 2^-24]."""
+    lo, hi = nv.debug_uniform_range(1234, 1 << 28, "cuda")
+    assert 0.0 < lo and hi < 1.0, (lo, hi)
+    assert lo == 2.0 ** -24 and hi == 1.0 - 2.0 ** -24, (lo, hi)
+    assert math.isfinite(-math.log(-math.log(hi))) and math.isfinite(-math.log(-math.log(lo)))
+
+
 def test_sample_greedy_and_topk_vs_torch(nv):
     R, V, eot, nosp = 6, 51865, 50257, 50362
     logits = _randn(R, V + 7, seed=1, scale=2.0)

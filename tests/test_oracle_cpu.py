@@ -146,6 +146,44 @@ def test_oracle_beam_matches_reference_golden():
     assert abs(res[0].avg_logprob - gold["avg_logprob"]) < 1e-5
 
 
+def test_oracle_detect_language_matches_reference_golden():
+    """detect_language restatement (decoding.py:18-77) against the reference's output on 2 clips."""
+    from whisper.tokenizer import get_tokenizer
+    gold = load_decode_golden()["cases"]["detect_language"]
+    model = build_model(gated=False)
+    sd, dims = oracle_sd(model), om.Dims(**TINY)
+    mel = torch.from_numpy(np.stack([omel.log_mel_spectrogram(p, 80) for p in _pcm(2)]))
+    tk = get_tokenizer(True, num_languages=99)
+    with torch.no_grad():
+        best, probs = odec.detect_language(sd, dims, om.encoder_forward(sd, dims, mel), tk.sot,
+                                           list(tk.all_language_tokens))
+    assert best == gold["language_tokens"]
+    codes = list(tk.all_language_codes)
+    assert [codes[int(i)] for i in probs.argmax(-1)] == gold["languages"]
+    for i in range(2):
+        assert abs(float(probs[i].max()) - gold["top_prob"][i]) < 1e-6
+        assert abs(float(probs[i, codes.index("en")]) - gold["probs_en"][i]) < 1e-7
+
+
+def test_oracle_multi_feature_greedy_matches_reference_golden():
+    """xt_list with 3 tensors of different lengths / widths (model.py:171-199), greedy tokens of the reference loop."""
+    from whisper._synthetic import synthetic_features
+    gold = load_decode_golden()["cases"]["greedy_multi3"]
+    spec = spec_from_json(gold["spec"])
+    spec.sample_len = 6
+    model = build_model(gated=True, num_langs=3)
+    mel = torch.from_numpy(np.stack([omel.log_mel_spectrogram(p, 80) for p in _pcm(2)]))
+    feats = [synthetic_features(2, n_frames=s[0], dim=s[1], seed=seed)
+             for s, seed in zip(gold["feat_shapes"], gold["feat_seeds"])]
+    res = odec.decode(oracle_sd(model), om.Dims(**TINY), spec, mel, feats)
+    assert [r.tokens for r in res] == [t[:6] for t in gold["tokens"]]
+    g = np.load(f"{GOLDEN}/net_tiny_multi.npz")
+    sd, dims = oracle_sd(model), om.Dims(**TINY)
+    with torch.no_grad():
+        lg = om.decoder_forward(sd, dims, torch.from_numpy(g["tokens"]), om.encoder_forward(sd, dims, mel), xt_list=feats)
+    assert np.abs(lg.reshape(-1)[::1009].numpy() - g["logits3_samples"]).max() < 2e-3
+
+
 # ----------------------------------------------------------------------------- host logic of the drop-in
 def test_tokenizer_special_ids_and_suppress_set():
     from whisper.tokenizer import get_tokenizer
@@ -219,6 +257,19 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(root, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f"{f} imports the oracle"
+                assert not re.search(r"^\s*(from|import)\s+baseline", src, re.M), f"{f} imports the reference arm"
+                assert "ref_whisper" not in src and "/root/reference" not in src, f"{f} reaches for the reference"
+
+
+def test_reference_arm_is_only_used_by_bench_and_is_git_ignored():
+    """baseline/reference_arm.py drives the unmodified reference for bench.py; the staged copy stays out of history."""
+    repo = os.path.join(os.path.dirname(GOLDEN), "..")
+    ignore = open(os.path.join(repo, ".gitignore")).read()
+    assert "baseline/_ref/" in ignore
+    gpurunignore = os.path.join(repo, ".gpurunignore")
+    assert not os.path.exists(gpurunignore) or "baseline/_ref" not in open(gpurunignore).read()
+    from baseline import reference_arm as ra
+    assert ra.CANDIDATES[0].endswith("baseline/_ref/whisper") and ra.CANDIDATES[1] == "/root/reference/whisper"
 
 
 # ----------------------------------------------------------------------------- C ABI surface

@@ -292,10 +292,9 @@ int attention_full_tc(const void* q, long long ldq, const void* k, long long ldk
   if (rc) return rc;
   rc = make_map_bf16(&mv, v, static_cast<long long>(B) * Tk, static_cast<long long>(H) * FT_D, ldv, FT_N);
   if (rc) return rc;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;  // function attributes are per device
+  if (configured.first_use()) {
     WF_CHECK_CUDA(cudaFuncSetAttribute(fa_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
-    configured = true;
   }
   dim3 grid((Tq + FT_WG * FT_M - 1) / (FT_WG * FT_M), H, B);
   fa_tc_kernel<<<grid, FT_THREADS, FT_SMEM, stream>>>(mq, mk, mv, reinterpret_cast<__nv_bfloat16*>(o), ldo, Tq, Tk);

@@ -45,15 +45,20 @@ int launch_priority(int kind) {
   return kind == 2 ? least : greatest;
 }
 
+int current_device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+  return dev < PerDeviceOnce::MAX_DEV ? dev : PerDeviceOnce::MAX_DEV - 1;
+}
+
 int num_sms() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
-      sms = 148;
+  static int sms[PerDeviceOnce::MAX_DEV] = {};
+  const int dev = current_device_slot();
+  if (!sms[dev]) {
+    if (cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms[dev] <= 0)
+      sms[dev] = 148;
   }
-  return sms;
+  return sms[dev];
 }
 
 static LinearEpilogue to_cpp(const wf_epilogue_t* e) {
@@ -204,6 +209,10 @@ int wf_kv_gather_rows(const void* src, void* dst, const int* src_index, int R, l
                       long long used_bytes, wf_stream_t stream) {
   WF_REQUIRE(src && dst && src_index, "wf_kv_gather_rows: null buffer");
   return kv_gather_rows(src, dst, src_index, R, row_bytes, used_bytes, S(stream));
+}
+
+int wf_debug_uniform_range(unsigned long long seed, long long n, float* out_min_max, wf_stream_t stream) {
+  return debug_uniform_range(seed, n, out_min_max, S(stream));
 }
 
 }  // extern "C"

@@ -41,7 +41,21 @@ void count_launch();
     WF_CHECK_CUDA(cudaPeekAtLastError());   \
   } while (0)
 
-int num_sms();
+int num_sms();  // of the CURRENT device
+// cudaFuncSetAttribute and __device__ symbols are per device: a once-flag per (call site, device), so that a process
+// that drives several GPUs (model.to("cuda:1"), no torchrun) configures every kernel on each of them.
+struct PerDeviceOnce {
+  static constexpr int MAX_DEV = 64;
+  bool done[MAX_DEV] = {};
+  bool first_use() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= MAX_DEV) return true;  // unknown device: always configure
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
+int current_device_slot();  // cudaGetDevice clamped to [0, PerDeviceOnce::MAX_DEV)
 // 2-D row-major bf16 matrix [rows, cols], row stride ld elements -> TMA map with box [box_rows, 64 cols], 128B swizzle
 int make_map_bf16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows);
 

@@ -35,7 +35,8 @@ __global__ void __launch_bounds__(DT)
 attn_decode_kernel(const T* __restrict__ q, long long ldq, const T* __restrict__ kc, const T* __restrict__ vc,
                    long long ld_kv, long long kv_batch_stride, long long kv_head_stride, T* __restrict__ o,
                    long long ldo, int H, const int* __restrict__ len_ptr, int len_add, int len_const, int n_splits,
-                   float* __restrict__ partials, const int* __restrict__ row_table, int table_ld) {
+                   float* __restrict__ partials, const int* __restrict__ row_table, int table_ld, int q_group,
+                   int q_first) {
   __shared__ float sq[NQ][HD];
   __shared__ float sp[NQ][DT];
   __shared__ float sred[NQ][DT / 32];
@@ -53,7 +54,7 @@ attn_decode_kernel(const T* __restrict__ q, long long ldq, const T* __restrict__
 
   for (int i = tid; i < NQ * HD; i += DT) {
     const int qi = i / HD, d = i % HD;
-    sq[qi][d] = to_f32(q[(static_cast<long long>(kvb) * NQ + qi) * ldq + h * HD + d]) * 0.125f;
+    sq[qi][d] = to_f32(q[(static_cast<long long>(kvb) * q_group + q_first + qi) * ldq + h * HD + d]) * 0.125f;
   }
   __syncthreads();
 
@@ -161,7 +162,7 @@ attn_decode_kernel(const T* __restrict__ q, long long ldq, const T* __restrict__
     float a = 0.f, l = 0.f;
 #pragma unroll
     for (int w = 0; w < DT / 32; ++w) { a += sacc[w][i][d]; l += sred[i][w]; }
-    const long long row = static_cast<long long>(kvb) * NQ + i;
+    const long long row = static_cast<long long>(kvb) * q_group + q_first + i;
     if (n_splits == 1) {
       o[row * ldo + h * HD + d] = from_f32<T>(a / l);
     } else {
@@ -185,7 +186,8 @@ __global__ void __launch_bounds__(DT, 2)
 attn_decode_hm_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const __nv_bfloat16* __restrict__ kc,
                       const __nv_bfloat16* __restrict__ vc, long long kv_batch_stride, long long kv_head_stride,
                       __nv_bfloat16* __restrict__ o, long long ldo, int H, const int* __restrict__ len_ptr,
-                      int len_add, int len_const, int n_splits, float* __restrict__ partials) {
+                      int len_add, int len_const, int n_splits, float* __restrict__ partials, int q_group,
+                      int q_first) {
   extern __shared__ uint8_t hm_raw[];
   uint8_t* stage_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(hm_raw) + 127) & ~uintptr_t(127));
   __shared__ __align__(8) uint64_t full_bar[HM_STAGES];
@@ -227,7 +229,7 @@ attn_decode_hm_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const 
   if (!len_ptr) pdl_wait();  // q (and everything written below) depends on the previous kernel
   for (int i = tid; i < NQ * HD; i += DT) {
     const int qi = i / HD, d = i % HD;
-    sq[qi][d] = __bfloat162float(q[(static_cast<long long>(kvb) * NQ + qi) * ldq + h * HD + d]) * 0.125f;
+    sq[qi][d] = __bfloat162float(q[(static_cast<long long>(kvb) * q_group + q_first + qi) * ldq + h * HD + d]) * 0.125f;
   }
   __syncthreads();
 
@@ -333,7 +335,7 @@ attn_decode_hm_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const 
     float a = 0.f, l = 0.f;
 #pragma unroll
     for (int w = 0; w < DT / 32; ++w) { a += sacc[w][i][d]; l += sred[i][w]; }
-    const long long row = static_cast<long long>(kvb) * NQ + i;
+    const long long row = static_cast<long long>(kvb) * q_group + q_first + i;
     if (n_splits == 1) {
       o[row * ldo + h * HD + d] = __float2bfloat16_rn(a / l);
     } else {
@@ -346,10 +348,12 @@ attn_decode_hm_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const 
 
 template <typename T>
 __global__ void __launch_bounds__(HD)
-attn_decode_combine_kernel(const float* __restrict__ partials, T* __restrict__ o, long long ldo, int H, int n_splits) {
+attn_decode_combine_kernel(const float* __restrict__ partials, T* __restrict__ o, long long ldo, int H, int n_splits,
+                           int nq, int q_group, int q_first) {
   pdl_trigger();
   pdl_wait();
-  const long long row = blockIdx.x / H;
+  const int item = blockIdx.x / H;  // (cache entry, query of this launch's chunk)
+  const long long row = static_cast<long long>(item / nq) * q_group + q_first + item % nq;
   const int h = blockIdx.x % H, d = threadIdx.x;
   const float* pp = partials + (row * H + h) * n_splits * PART;
   float M = -INFINITY;
@@ -380,7 +384,7 @@ template <int NQ>
 __global__ void __launch_bounds__(DT, 3)
 attn_decode_mq_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
                       const __nv_bfloat16* __restrict__ q, long long ldq, int rows_per_batch, int rows_per_head,
-                      __nv_bfloat16* __restrict__ o, long long ldo, int H, int len) {
+                      __nv_bfloat16* __restrict__ o, long long ldo, int H, int len, int q_group, int q_first) {
   static_assert(NQ >= 1 && NQ <= 8, "queries per clip must fit the 8 real rows of the padded 16-row MMA operand");
   extern __shared__ uint8_t mq_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(mq_raw) + 1023) & ~uintptr_t(1023));
@@ -413,7 +417,8 @@ attn_decode_mq_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_co
   {
     const int row = tid >> 3, chunk = tid & 7;  // 16 rows x 8 chunks of 16 B
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (row < NQ) v = *reinterpret_cast<const uint4*>(q + (static_cast<long long>(kvb) * NQ + row) * ldq + h * HD + chunk * 8);
+    if (row < NQ)
+      v = *reinterpret_cast<const uint4*>(q + (static_cast<long long>(kvb) * q_group + q_first + row) * ldq + h * HD + chunk * 8);
     *reinterpret_cast<uint4*>(sQ + row * 128 + ((chunk ^ (row & 7)) << 4)) = v;
   }
   __syncthreads();
@@ -526,7 +531,7 @@ attn_decode_mq_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_co
       num = fmaf(sc, comb_o[(w * 8 + i) * HD + d], num);
       den = fmaf(sc, comb_ml[w][i][1], den);
     }
-    o[(static_cast<long long>(kvb) * NQ + i) * ldo + h * HD + d] = __float2bfloat16_rn(num / den);
+    o[(static_cast<long long>(kvb) * q_group + q_first + i) * ldo + h * HD + d] = __float2bfloat16_rn(num / den);
   }
 }
 
@@ -550,7 +555,8 @@ template <int NQ>
 __global__ void __launch_bounds__(PS_THREADS, 1)
 attn_decode_ps_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const __nv_bfloat16* __restrict__ kc,
                       const __nv_bfloat16* __restrict__ vc, long long kv_batch_stride, long long kv_head_stride,
-                      __nv_bfloat16* __restrict__ o, long long ldo, int H, int len, int n_items) {
+                      __nv_bfloat16* __restrict__ o, long long ldo, int H, int len, int n_items, int q_group,
+                      int q_first) {
   using L = PsSmem<NQ>;
   extern __shared__ uint8_t ps_raw[];
   uint8_t* stage_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ps_raw) + 127) & ~uintptr_t(127));
@@ -599,7 +605,8 @@ attn_decode_ps_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const 
 #pragma unroll
             for (int i = 0; i < NQ; ++i)
               bulk_load_1d(dst + 2 * HM_TILE_BYTES + i * HD * 2,
-                           q + (static_cast<long long>(kvb) * NQ + i) * ldq + h * HD, HD * 2, &full_bar[stage]);
+                           q + (static_cast<long long>(kvb) * q_group + q_first + i) * ldq + h * HD, HD * 2,
+                           &full_bar[stage]);
           }
           if (++stage == PS_STAGES) { stage = 0; phase ^= 1; }
         }
@@ -722,7 +729,7 @@ attn_decode_ps_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const 
         num = fmaf(sc, comb_acc[parity][w][i][d], num);
         den = fmaf(sc, comb_ml[parity][w][i][1], den);
       }
-      o[(static_cast<long long>(kvb) * NQ + i) * ldo + h * HD + d] = __float2bfloat16_rn(num / den);
+      o[(static_cast<long long>(kvb) * q_group + q_first + i) * ldo + h * HD + d] = __float2bfloat16_rn(num / den);
     }
   }
 }
@@ -736,8 +743,10 @@ static int launch_decode_attn(const T* q, long long ldq, const T* kc, const T* v
                               long long kv_batch_stride, long long kv_head_stride, T* o, long long ldo, int R, int H,
                               const int* len_ptr,
                               int len_add, int len_max, float* ws, long long ws_bytes, const int* row_table,
-                              int table_ld, cudaStream_t stream) {
-  const int kvb = R / NQ;
+                              int table_ld, int q_group, int q_first, cudaStream_t stream) {
+  // R = rows of the whole problem (q_group per cache entry); this launch serves queries [q_first, q_first + NQ) of
+  // every entry
+  const int kvb = R / q_group;
   const int blocks = kvb * H;
   const int max_tiles = (len_max + DT - 1) / DT;
   // Granularity: a (audio, head) item streams up to 1500 x 256 B; with one CTA per item a 2560-item grid is
@@ -769,15 +778,14 @@ static int launch_decode_attn(const T* q, long long ldq, const T* kc, const T* v
       if (rc) return rc;
       rc = make_map_bf16(&mv, vc, (kvb - 1) * rpb + (H - 1) * rph + len_max, HD, HD, HM_KEYS);
       if (rc) return rc;
-      static bool mq_configured = false;
-      if (!mq_configured) {
+      static PerDeviceOnce mq_configured;  // function attributes are per device
+      if (mq_configured.first_use()) {
         WF_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_mq_kernel<NQC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            MQ_SMEM_BYTES));
-        mq_configured = true;
       }
       WF_CHECK_CUDA(launch_pdl(2, attn_decode_mq_kernel<NQC>, dim3(blocks), dim3(DT), MQ_SMEM_BYTES, stream, mk, mv,
                                (const __nv_bfloat16*)q, ldq, static_cast<int>(rpb), static_cast<int>(rph),
-                               (__nv_bfloat16*)o, ldo, H, len_max));
+                               (__nv_bfloat16*)o, ldo, H, len_max, q_group, q_first));
       count_launch();
       return WF_OK;
     }
@@ -788,14 +796,13 @@ static int launch_decode_attn(const T* q, long long ldq, const T* kc, const T* v
     }
     if (persist && ld_kv == HD && !len_ptr && len_max >= 256 && blocks >= 2 * num_sms()) {
       using L = PsSmem<NQ>;
-      static bool ps_configured = false;
-      if (!ps_configured) {
+      static PerDeviceOnce ps_configured;  // function attributes are per device
+      if (ps_configured.first_use()) {
         WF_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_ps_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            L::DYN_BYTES));
-        ps_configured = true;
       }
       WF_CHECK_CUDA(launch_pdl(2, attn_decode_ps_kernel<NQ>, dim3(num_sms()), dim3(PS_THREADS), L::DYN_BYTES, stream, q,
-                               ldq, kc, vc, kv_batch_stride, kv_head_stride, o, ldo, H, len_max, blocks));
+                               ldq, kc, vc, kv_batch_stride, kv_head_stride, o, ldo, H, len_max, blocks, q_group, q_first));
       count_launch();
       return WF_OK;
     }
@@ -810,11 +817,10 @@ static int launch_decode_attn(const T* q, long long ldq, const T* kc, const T* v
         const char* e = getenv("WF_ATTN_SMEM_PAD");
         pad = e ? atoi(e) : 0;
       }
-      static bool configured = false;
-      if (!configured) {
+      static PerDeviceOnce configured;  // function attributes are per device
+      if (configured.first_use()) {
         WF_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_hm_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            HM_SMEM_BYTES + pad));
-        configured = true;
       }
       dim3 hgrid(blocks, hs);
       // Two stages (64 KB per CTA) let THREE CTAs share an SM instead of two: the softmax barriers and the prologue /
@@ -826,21 +832,22 @@ static int launch_decode_attn(const T* q, long long ldq, const T* kc, const T* v
       }
       if (two) {
         constexpr int SM2 = 2 * 2 * HM_TILE_BYTES + 128;
-        static bool c2 = false;
-        if (!c2) {
+        static PerDeviceOnce c2;  // function attributes are per device
+        if (c2.first_use()) {
           WF_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_hm_kernel<NQ, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM2));
-          c2 = true;
         }
         WF_CHECK_CUDA(launch_pdl(2, attn_decode_hm_kernel<NQ, 2>, hgrid, dim3(DT), SM2, stream, q, ldq, kc, vc,
-                                 kv_batch_stride, kv_head_stride, o, ldo, H, len_ptr, len_add, len_max, hs, ws));
+                                 kv_batch_stride, kv_head_stride, o, ldo, H, len_ptr, len_add, len_max, hs, ws, q_group,
+                                 q_first));
       } else {
         WF_CHECK_CUDA(launch_pdl(2, attn_decode_hm_kernel<NQ>, hgrid, dim3(DT), HM_SMEM_BYTES + pad, stream, q, ldq, kc, vc,
-                                 kv_batch_stride, kv_head_stride, o, ldo, H, len_ptr, len_add, len_max, hs, ws));
+                                 kv_batch_stride, kv_head_stride, o, ldo, H, len_ptr, len_add, len_max, hs, ws, q_group,
+                                 q_first));
       }
       count_launch();
       if (hs > 1) {
-        WF_CHECK_CUDA(launch_pdl(2, attn_decode_combine_kernel<T>, dim3(R * H), dim3(HD), 0, stream, (const float*)ws, o,
-                                 ldo, H, hs));
+        WF_CHECK_CUDA(launch_pdl(2, attn_decode_combine_kernel<T>, dim3(kvb * NQ * H), dim3(HD), 0, stream,
+                                 (const float*)ws, o, ldo, H, hs, NQ, q_group, q_first));
         count_launch();
       }
       return WF_OK;
@@ -849,11 +856,11 @@ static int launch_decode_attn(const T* q, long long ldq, const T* kc, const T* v
   dim3 grid(blocks, n_splits);
   WF_CHECK_CUDA(launch_pdl(2, attn_decode_kernel<T, NQ>, grid, dim3(DT), 0, stream, q, ldq, kc, vc, ld_kv,
                            kv_batch_stride, kv_head_stride, o, ldo, H, len_ptr, len_add, len_max, n_splits, ws,
-                           row_table, table_ld));
+                           row_table, table_ld, q_group, q_first));
   count_launch();
   if (n_splits > 1) {
-    WF_CHECK_CUDA(launch_pdl(2, attn_decode_combine_kernel<T>, dim3(R * H), dim3(HD), 0, stream, (const float*)ws, o, ldo,
-                             H, n_splits));
+    WF_CHECK_CUDA(launch_pdl(2, attn_decode_combine_kernel<T>, dim3(kvb * NQ * H), dim3(HD), 0, stream, (const float*)ws,
+                             o, ldo, H, n_splits, NQ, q_group, q_first));
     count_launch();
   }
   return WF_OK;
@@ -865,17 +872,22 @@ static int dispatch_decode_attn(const void* q, long long ldq, const void* kc, co
                                 int G, int H,
                                 const int* len_ptr, int len_add, int len_max, void* ws, long long ws_bytes,
                                 const int* row_table, int table_ld, cudaStream_t stream) {
+  // Any G: the hypotheses of a cache entry are served in chunks of at most 8 queries (one launch per chunk, each
+  // streaming the entry's K/V once); beam_size / best_of up to 8 is a single pass.
 #define WF_DA(NQ)                                                                                              \
   case NQ:                                                                                                     \
-    return launch_decode_attn<T, NQ>((const T*)q, ldq, (const T*)kc, (const T*)vc, ld_kv, kv_batch_stride,     \
-                                     kv_head_stride, (T*)o, ldo, R, H, len_ptr, len_add, len_max, (float*)ws,  \
-                                     ws_bytes, row_table, table_ld, stream)
-  switch (G) {
-    WF_DA(1); WF_DA(2); WF_DA(3); WF_DA(4); WF_DA(5); WF_DA(6); WF_DA(8);
-    default:
-      set_error("attention_decode: unsupported queries-per-audio G=%d (supported 1,2,3,4,5,6,8)", G);
-      return WF_ERR_UNSUPPORTED;
+    rc = launch_decode_attn<T, NQ>((const T*)q, ldq, (const T*)kc, (const T*)vc, ld_kv, kv_batch_stride,       \
+                                   kv_head_stride, (T*)o, ldo, R, H, len_ptr, len_add, len_max, (float*)ws,    \
+                                   ws_bytes, row_table, table_ld, G, first, stream);                           \
+    break
+  for (int first = 0; first < G; first += 8) {
+    int rc = WF_OK;
+    switch (G - first < 8 ? G - first : 8) {
+      WF_DA(1); WF_DA(2); WF_DA(3); WF_DA(4); WF_DA(5); WF_DA(6); WF_DA(7); WF_DA(8);
+    }
+    if (rc) return rc;
   }
+  return WF_OK;
 #undef WF_DA
 }
 
@@ -1008,7 +1020,36 @@ __device__ __forceinline__ float uniform01(unsigned long long seed, int row, int
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
   z ^= z >> 31;
-  return (static_cast<float>(z >> 40) + 0.5f) * (1.0f / 16777216.0f);
+  // 23 random bits + 0.5 is exact in fp32 (24 significant bits), so u lies strictly inside (0, 1): [2^-24, 1 - 2^-24].
+  // (24 bits + 0.5 rounds 0xFFFFFF + 0.5 up to 2^24, u == 1, Gumbel = +inf: that token would win whatever its logit.)
+  return (static_cast<float>(z >> 41) + 0.5f) * (1.0f / 8388608.0f);
+}
+
+// test hook: min / max of n consecutive draws (token ids first + i of row `row`, position `pos`), float-as-int atomics
+__global__ void uniform_range_kernel(unsigned long long seed, int row, int pos, long long first, long long n,
+                                     unsigned int* out) {
+  float lo = 2.f, hi = -1.f;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const long long t = first + i;
+    const float u = uniform01(seed + static_cast<unsigned long long>(t >> 20), row, pos, static_cast<int>(t & 0xFFFFF));
+    lo = fminf(lo, u);
+    hi = fmaxf(hi, u);
+  }
+  lo = -warp_max(-lo);
+  hi = warp_max(hi);
+  if ((threadIdx.x & 31) == 0) {  // u > 0, so the unsigned integer order of the bit patterns is the float order
+    atomicMin(&out[0], __float_as_uint(lo));
+    atomicMax(&out[1], __float_as_uint(hi));
+  }
+}
+int debug_uniform_range(unsigned long long seed, long long n, float* out_min_max, cudaStream_t stream) {
+  WF_REQUIRE(n > 0 && out_min_max, "debug_uniform_range: bad arguments");
+  const unsigned int init[2] = {0x7f800000u, 0u};
+  WF_CHECK_CUDA(cudaMemcpyAsync(out_min_max, init, sizeof(init), cudaMemcpyHostToDevice, stream));
+  uniform_range_kernel<<<num_sms() * 8, 256, 0, stream>>>(seed, 3, 7, 0, n, reinterpret_cast<unsigned int*>(out_min_max));
+  WF_CHECK_LAUNCH();
+  return WF_OK;
 }
 
 // state: [0]=t (position of the token fed this step) [1]=n_init [2]=all_done [3]=#rows at EOT this step [4]=sot_index

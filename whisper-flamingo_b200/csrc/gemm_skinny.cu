@@ -375,11 +375,10 @@ template <int BN, int STAGES>
 static int launch_skinny(const CUtensorMap& ma, const CUtensorMap& mb, int M, int N, int K, const TcEpilogue& ep, int cs,
                          cudaStream_t stream) {
   using Cfg = SkCfg<BN, STAGES>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;  // function attributes are per device
+  if (configured.first_use()) {
     WF_CHECK_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::SMEM_BYTES));
-    configured = true;
   }
   const int tiles = (N + BN - 1) / BN;
   cudaLaunchConfig_t cfg = {};

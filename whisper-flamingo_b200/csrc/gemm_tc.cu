@@ -319,11 +319,10 @@ template <int BN, int STAGES>
 static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, int M, int N, int K, TcEpilogue ep,
                      void* ws, long long ws_bytes, cudaStream_t stream) {
   using Cfg = TcCfg<BN, STAGES>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;  // function attributes are per device
+  if (configured.first_use()) {
     WF_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::SMEM_BYTES));
-    configured = true;
   }
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int k_blocks = (K + BK - 1) / BK;

@@ -274,10 +274,9 @@ int linear_bf16_pair(const void* A, long long lda, const void* W, long long ldw,
   if (rc) return rc;
   rc = make_map_bf16(&mb, W, N, K, ldw, P_BN / 2);
   if (rc) return rc;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;  // function attributes are per device
+  if (configured.first_use()) {
     WF_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
-    configured = true;
   }
   const int tiles = ((M + 2 * P_BM - 1) / (2 * P_BM)) * ((N + P_BN - 1) / P_BN);
   int clusters = num_sms() / 2;

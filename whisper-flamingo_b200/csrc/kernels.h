@@ -123,5 +123,7 @@ struct TopkArgs {
 int topk_logprobs(const TopkArgs& a, cudaStream_t stream);
 int kv_gather_rows(const void* src, void* dst, const int* src_index, int R, long long row_bytes, long long used_bytes,
                    cudaStream_t stream);
+// test hook: out_min_max[0..1] (device) = min / max of n draws of the sampling RNG's uniform
+int debug_uniform_range(unsigned long long seed, long long n, float* out_min_max, cudaStream_t stream);
 
 }  // namespace wf

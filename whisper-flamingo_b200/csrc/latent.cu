@@ -490,10 +490,9 @@ int latent_attention(const void* qp, const void* src, void* ctx, int B, int T, i
   if (rc) return rc;
   rc = make_map_bf16(&mq, qp, static_cast<long long>(B) * H, d, d, hp);
   if (rc) return rc;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;  // function attributes are per device
+  if (configured.first_use()) {
     WF_CHECK_CUDA(cudaFuncSetAttribute(latent_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LA_SMEM_LIMIT));
-    configured = true;
   }
   const float sl2 = 0.125f * 1.44269504088896340736f;   // 64^-0.5 * log2(e)
   WF_CHECK_CUDA(launch_pdl(2, latent_attn_kernel, dim3(B), dim3(LA_THREADS), static_cast<size_t>(smem), stream, mx, mq,

@@ -35,7 +35,7 @@ struct MelTables {
   int nnz[2];
 };
 __device__ MelTables g_tab;
-static bool g_filters_set[2] = {false, false};
+static bool g_filters_set[PerDeviceOnce::MAX_DEV][2] = {};  // the __device__ table exists once per device
 static bool g_consts_set = false;
 
 int logmel_set_filters(int n_mels, const float* dense) {
@@ -63,8 +63,10 @@ int logmel_set_filters(int n_mels, const float* dense) {
     for (int k = lo; k <= hi; ++k) host.w[set][off++] = dense[m * NBINS + k];
   }
   host.nnz[set] = off;
+  // `host` accumulates both sets; the upload replaces the current device's whole table.  A set uploaded earlier to
+  // ANOTHER device only is not valid here until it has been set on this device too.
   WF_CHECK_CUDA(cudaMemcpyToSymbol(g_tab, &host, sizeof(MelTables)));
-  g_filters_set[set] = true;
+  g_filters_set[current_device_slot()][set] = true;
   return WF_OK;
 }
 
@@ -272,10 +274,9 @@ static int launch_logmel(const float* pcm, int n_clips, int n_samples, long long
   const int groups = (n_frames + FRAMES_PER_GROUP - 1) / FRAMES_PER_GROUP;
   const long long total = static_cast<long long>(n_clips) * groups;
   const int smem = static_cast<int>(sizeof(MelSmem<NMELS>));
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;  // function attributes are per device
+  if (configured.first_use()) {
     WF_CHECK_CUDA(cudaFuncSetAttribute(logmel_fft_kernel<NMELS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
   }
   WF_CHECK_CUDA(cudaMemsetAsync(keys, 0x80, (n_clips + 1) * sizeof(int), stream));
   const long long max_grid = 2LL * num_sms();
@@ -297,7 +298,8 @@ static int launch_logmel(const float* pcm, int n_clips, int n_samples, long long
 int logmel_f32(const float* pcm, int n_clips, int n_samples, long long clip_stride, int n_mels, int mode, float* out,
                void* workspace, cudaStream_t stream) {
   WF_REQUIRE(n_mels == 80 || n_mels == 128, "Unsupported n_mels: %d", n_mels);
-  WF_REQUIRE(g_filters_set[n_mels == 80 ? 0 : 1], "wf_logmel_set_filters(%d) has not been called", n_mels);
+  WF_REQUIRE(g_filters_set[current_device_slot()][n_mels == 80 ? 0 : 1],
+             "wf_logmel_set_filters(%d) has not been called on this device", n_mels);
   WF_REQUIRE(n_clips > 0 && n_clips <= 65535, "logmel: n_clips=%d out of range [1, 65535]", n_clips);
   WF_REQUIRE(n_samples > NFFT / 2, "logmel: reflect padding needs more than %d samples (got %d)", NFFT / 2, n_samples);
   WF_REQUIRE(n_samples / HOP > 0, "logmel: no complete frame in %d samples", n_samples);

@@ -417,6 +417,32 @@ def encoder_forward(enc, mel: Tensor, track_norm: bool = False):
 
 
 # ============================================================================ feature preparation (x-attn inputs)
+def validate_features(feats: Optional[Sequence[Tensor]], n_batch: int, device, n_langs: int) -> List[Tensor]:
+    """Shape / device checks of the gated x-attention inputs.  The reference fails with a broadcasting or device error
+    inside ``q @ k`` (model.py:98-102) when a feature tensor does not match the audio batch; here the K/V projection
+    writes into a pre-sized arena, so a mismatch must be refused before any kernel runs."""
+    if feats is None:
+        raise TypeError("object of type 'NoneType' has no len(): a gated x-attn model needs its feature input "
+                        "(xt_list= / x_v=)")
+    feats = list(feats)
+    if len(feats) > n_langs:
+        raise ValueError(f"Got {len(feats)} translations but only support up to {n_langs}")
+    for i, f in enumerate(feats):
+        if not torch.is_tensor(f) or f.dim() != 3:
+            raise ValueError(f"feature tensor {i} must be (batch, T_x, width), got "
+                             f"{tuple(f.shape) if torch.is_tensor(f) else type(f)}")
+        if f.shape[0] != n_batch:
+            raise ValueError(f"feature tensor {i} has batch {f.shape[0]} but the audio batch is {n_batch} "
+                             f"(shape {tuple(f.shape)}); features are per clip and are not broadcast")
+        if f.shape[1] < 1:
+            raise ValueError(f"feature tensor {i} is empty (shape {tuple(f.shape)})")
+        if not f.is_cuda or f.device != device:
+            raise ValueError(f"feature tensor {i} lives on {f.device} but the audio features are on {device}")
+        if not f.is_floating_point():
+            raise ValueError(f"feature tensor {i} must be floating point, got {f.dtype}")
+    return feats
+
+
 @torch.no_grad()
 def prepare_features(p: _DecoderPack, xt: Tensor, dt: torch.dtype) -> Tensor:
     """xt_projection (if widths differ) + learned positional embedding + cast (reference model.py:316-325).
@@ -439,6 +465,51 @@ def prepare_features(p: _DecoderPack, xt: Tensor, dt: torch.dtype) -> Tensor:
     return nv.add_rowmod(src, p.pos_emb, _empty(B * Tx, w, dt, xt.device), Tx)
 
 
+# ============================================================================ one block over full sequences
+class _BlockScratch:
+    """Activation buffers of the unfused block pass (teacher-forced decoder, stand-alone block calls)."""
+
+    def __init__(self, M: int, d: int, dt, dev):
+        self.xn, self.q, self.att = _empty(M, d, dt, dev), _empty(M, d, dt, dev), _empty(M, d, dt, dev)
+        self.qkv, self.h = _empty(M, 3 * d, dt, dev), _empty(M, 4 * d, dt, dev)
+
+
+def _block_forward(bp: _BlockPack, ws: _BlockScratch, x: Tensor, B: int, t: int, H: int, xa2: Optional[Tensor], Ta: int,
+                   feats: Sequence[Tensor], causal: bool) -> Tensor:
+    """ResidualAttentionBlock.forward (reference model.py:201-215) on rows x [B * t, d]; returns the new residual
+    stream (x itself, updated in place, unless several feature tensors force a copy).
+    Order: gated x-attn over every feature tensor from the SAME input (deltas summed, :184-199) + gated FF ->
+    self-attention -> cross-attention (when xa2 is given) -> MLP."""
+    d, dt, dev = x.shape[1], x.dtype, x.device
+    xn, q, att, qkv, hbuf = ws.xn, ws.q, ws.att, ws.qkv, ws.h
+    if bp.x_attn and feats is not None:
+        if len(feats) > 0:
+            acc = x if len(feats) <= 1 else x.clone()
+            for i, f in enumerate(feats):
+                Tx = f.shape[0] // B
+                nv.layernorm(x, bp.x_ln[i].w, bp.x_ln[i].b, xn)
+                nv.linear(xn, bp.x_attn[i].q_w, q, bias=bp.x_attn[i].q_b)
+                kv_x = _empty(B * Tx, 2 * d, dt, dev)
+                nv.linear(f, bp.x_attn[i].kv_w, kv_x, bias=bp.x_attn[i].kv_b)
+                nv.attention(q, kv_x[:, :d], kv_x[:, d:], att, B, t, Tx, H, causal=False)
+                nv.linear(att, bp.x_attn[i].o_w, acc, bias=bp.x_attn[i].o_b, residual=acc, gate=bp.x_gate[i])
+            x = acc
+        _mlp_inplace(x, xn, hbuf, bp.ff_ln, bp.ff, gate=bp.ff_gate)
+    nv.layernorm(x, bp.attn_ln.w, bp.attn_ln.b, xn)
+    nv.linear(xn, bp.attn.qkv_w, qkv, bias=bp.attn.qkv_b)
+    nv.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], att, B, t, t, H, causal=causal)
+    nv.linear(att, bp.attn.o_w, x, bias=bp.attn.o_b, residual=x)
+    if bp.cross is not None and xa2 is not None:
+        kv_a = _empty(B * Ta, 2 * d, dt, dev)
+        nv.layernorm(x, bp.cross_ln.w, bp.cross_ln.b, xn)
+        nv.linear(xn, bp.cross.q_w, q, bias=bp.cross.q_b)
+        nv.linear(xa2, bp.cross.kv_w, kv_a, bias=bp.cross.kv_b)
+        nv.attention(q, kv_a[:, :d], kv_a[:, d:], att, B, t, Ta, H, causal=False)
+        nv.linear(att, bp.cross.o_w, x, bias=bp.cross.o_b, residual=x)
+    _mlp_inplace(x, xn, hbuf, bp.mlp_ln, bp.mlp)
+    return x
+
+
 # ============================================================================ teacher-forced decoder pass
 @torch.no_grad()
 def decoder_forward(dec, tokens: Tensor, xa: Tensor, xt_list: Optional[Sequence[Tensor]]):
@@ -448,12 +519,12 @@ def decoder_forward(dec, tokens: Tensor, xa: Tensor, xt_list: Optional[Sequence[
     with torch.cuda.device(xa.device):
         p = decoder_pack(dec, dt)
         gated = len(p.blocks) > 0 and len(p.blocks[0].x_attn) > 0
-        if gated:
-            if xt_list is None:
-                raise TypeError("object of type 'NoneType' has no len(): a gated x-attn model needs xt_list")
-            if len(xt_list) > len(p.blocks[0].x_attn):
-                raise ValueError(f"Got {len(xt_list)} translations but only support up to {len(p.blocks[0].x_attn)}")
         B, t = tokens.shape
+        if xa.dim() != 3 or xa.shape[0] != B or xa.shape[2] != p.d:
+            raise ValueError(f"xa must be ({B}, T, {p.d}) for tokens of shape {tuple(tokens.shape)}, got "
+                             f"{tuple(xa.shape)}")
+        if gated:
+            xt_list = validate_features(xt_list, B, xa.device, len(p.blocks[0].x_attn))
         if t > p.n_ctx:
             raise RuntimeError(f"token length {t} exceeds n_text_ctx {p.n_ctx}")
         d, H, dev = p.d, p.n_head, xa.device
@@ -464,32 +535,10 @@ def decoder_forward(dec, tokens: Tensor, xa: Tensor, xt_list: Optional[Sequence[
         M = B * t
         x = _empty(M, d, dt, dev)
         nv.embed(tok32, t, None, 0, p.tok_emb, p.pos_emb, x, n_pos=t)
-        xn, q, att = _empty(M, d, dt, dev), _empty(M, d, dt, dev), _empty(M, d, dt, dev)
-        qkv, hbuf = _empty(M, 3 * d, dt, dev), _empty(M, 4 * d, dt, dev)
-        kv_a = _empty(B * Ta, 2 * d, dt, dev)
+        ws = _BlockScratch(M, d, dt, dev)
         for bp in p.blocks:
-            if gated:
-                acc = x if len(feats) <= 1 else x.clone()
-                for i, f in enumerate(feats):
-                    Tx = f.shape[0] // B
-                    nv.layernorm(x, bp.x_ln[i].w, bp.x_ln[i].b, xn)
-                    nv.linear(xn, bp.x_attn[i].q_w, q, bias=bp.x_attn[i].q_b)
-                    kv_x = _empty(B * Tx, 2 * d, dt, dev)
-                    nv.linear(f, bp.x_attn[i].kv_w, kv_x, bias=bp.x_attn[i].kv_b)
-                    nv.attention(q, kv_x[:, :d], kv_x[:, d:], att, B, t, Tx, H, causal=False)
-                    nv.linear(att, bp.x_attn[i].o_w, acc, bias=bp.x_attn[i].o_b, residual=acc, gate=bp.x_gate[i])
-                x = acc
-                _mlp_inplace(x, xn, hbuf, bp.ff_ln, bp.ff, gate=bp.ff_gate)
-            nv.layernorm(x, bp.attn_ln.w, bp.attn_ln.b, xn)
-            nv.linear(xn, bp.attn.qkv_w, qkv, bias=bp.attn.qkv_b)
-            nv.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], att, B, t, t, H, causal=True)
-            nv.linear(att, bp.attn.o_w, x, bias=bp.attn.o_b, residual=x)
-            nv.layernorm(x, bp.cross_ln.w, bp.cross_ln.b, xn)
-            nv.linear(xn, bp.cross.q_w, q, bias=bp.cross.q_b)
-            nv.linear(xa2, bp.cross.kv_w, kv_a, bias=bp.cross.kv_b)
-            nv.attention(q, kv_a[:, :d], kv_a[:, d:], att, B, t, Ta, H, causal=False)
-            nv.linear(att, bp.cross.o_w, x, bias=bp.cross.o_b, residual=x)
-            _mlp_inplace(x, xn, hbuf, bp.mlp_ln, bp.mlp)
+            x = _block_forward(bp, ws, x, B, t, H, xa2, Ta, feats, causal=True)
+        xn = ws.xn
         nv.layernorm(x, p.ln.w, p.ln.b, xn)
         logits = torch.empty((M, p.n_vocab), dtype=torch.float32, device=dev)
         nv.linear(xn, p.tok_emb_t, logits)
@@ -569,13 +618,9 @@ class DecodeSession:
         self.load(xa, feats)
 
     def _check_feats(self, feats) -> List[Tensor]:
-        if self.gated and feats is None:
-            raise TypeError("object of type 'NoneType' has no len(): a gated x-attn model needs its feature input "
-                            "(pass x_v= to decode())")
-        feats = list(feats) if (self.gated and feats is not None) else []
-        if self.gated and len(feats) > len(self.p.blocks[0].x_attn):
-            raise ValueError(f"Got {len(feats)} translations but only support up to {len(self.p.blocks[0].x_attn)}")
-        return feats
+        if not self.gated:
+            return []
+        return validate_features(feats, self.B, self.dev, len(self.p.blocks[0].x_attn))
 
     def shape_key(self):
         return (self.dt, self.dev, self.B, self.G, self.T_cap, self.Ta, tuple(self.Tx), id(self.p))
@@ -847,7 +892,9 @@ class SplitSession:
         self.n_split = n_split
 
     def _check_feats(self, feats):
-        return self.subs[0]._check_feats(feats)
+        if not self.gated:
+            return []
+        return validate_features(feats, self.B, self.dev, len(self.p.blocks[0].x_attn))
 
     def shape_key(self):
         return (self.dt, self.dev, self.B, self.G, self.T_cap, self.Ta, tuple(self.Tx), id(self.p), self.n_split)
@@ -923,6 +970,8 @@ def get_session(dec, xa: Tensor, feats: Optional[Sequence[Tensor]], n_group: int
     dt = _engine_dtype(xa.dtype)
     p = decoder_pack(dec, dt)
     n_split = max(1, min(n_split, xa.shape[0]))
+    if len(p.blocks) > 0 and len(p.blocks[0].x_attn) > 0:  # refuse mismatched features before anything is sized by them
+        feats = validate_features(feats, xa.shape[0], xa.device, len(p.blocks[0].x_attn))
     if os.environ.get("WF_NO_GRAPH", "0") == "1":
         n_split = 1  # per-kernel profiling mode: one eager stream
     old = _SESSION_CACHE.get(dec)
@@ -995,3 +1044,188 @@ def standalone_mha(mha, x: Tensor, xa: Optional[Tensor], causal: bool) -> Tensor
         out = _empty(B * t, d, dt, x.device)
         nv.linear(att, mp.o_w, out, bias=mp.o_b)
     return out.view(B, t, d).to(x.dtype)
+
+
+@torch.no_grad()
+def standalone_conv1d(conv, x: Tensor) -> Tensor:
+    """Conv1d.forward (reference model.py:44-50) for the stem's geometry (kernel 3, padding 1, stride 1 | 2, no
+    dilation / groups) as im2col + GEMM; x (batch, C_in, T) -> (batch, C_out, T_out), no activation."""
+    nv.require_cuda(x)
+    if (conv.kernel_size != (3,) or conv.padding != (1,) or conv.stride not in ((1,), (2,)) or conv.dilation != (1,)
+            or conv.groups != 1 or conv.padding_mode != "zeros"):
+        raise nv.WfError(f"Conv1d geometry {conv} is not the Whisper stem's (kernel 3, padding 1, stride 1|2)")
+    if x.dim() != 3 or x.shape[1] != conv.in_channels:
+        raise ValueError(f"expected (batch, {conv.in_channels}, T), got {tuple(x.shape)}")
+    dt = _engine_dtype(x.dtype)
+    with torch.cuda.device(x.device):
+        xin = _to_dtype(x, dt).contiguous()
+        B, C, T = xin.shape
+        stride = conv.stride[0]
+        T_out = (T - 1) // stride + 1
+        cols = _empty(B * T_out, 3 * C, dt, x.device)
+        nv.im2col_k3(xin, C * T, T, 1, B, C, T, stride, cols)
+        out = _empty(B * T_out, conv.out_channels, dt, x.device)
+        nv.linear(cols, _pack_w(conv.weight, dt), out, bias=None if conv.bias is None else _f32(conv.bias))
+    return out.view(B, T_out, conv.out_channels).permute(0, 2, 1).to(x.dtype)
+
+
+@torch.no_grad()
+def standalone_gated_xattn(sub, x: Tensor, xt: Tensor) -> Tensor:
+    """GatedXAttnSubBlock.forward (reference model.py:121-134): tanh(attn_gate) * MHA(LN(x), xt) - the delta only."""
+    nv.require_cuda(x, xt)
+    dt = _engine_dtype(x.dtype)
+    B, t, d = x.shape
+    if xt.dim() != 3 or xt.shape[0] != B or xt.shape[2] != d:
+        raise ValueError(f"xt must be ({B}, T_x, {d}), got {tuple(xt.shape)}")
+    with torch.cuda.device(x.device):
+        mp, ln = _pack_mha(sub.attn, dt), _pack_ln(sub.attn_ln)
+        Tx = xt.shape[1]
+        x2 = _to_dtype(x, dt).reshape(B * t, d).contiguous()
+        f2 = _to_dtype(xt, dt).reshape(B * Tx, d).contiguous()
+        xn, q, att = torch.empty_like(x2), torch.empty_like(x2), torch.empty_like(x2)
+        kv = _empty(B * Tx, 2 * d, dt, x.device)
+        nv.layernorm(x2, ln.w, ln.b, xn)
+        nv.linear(xn, mp.q_w, q, bias=mp.q_b)
+        nv.linear(f2, mp.kv_w, kv, bias=mp.kv_b)
+        nv.attention(q, kv[:, :d], kv[:, d:], att, B, t, Tx, sub.attn.n_head, causal=False)
+        out = torch.empty_like(x2)
+        nv.linear(att, mp.o_w, out, bias=mp.o_b, gate=_f32(sub.attn_gate))
+    return out.view(B, t, d).to(x.dtype)
+
+
+@torch.no_grad()
+def standalone_block(blk, x: Tensor, xa: Optional[Tensor], causal: bool, xt_list: Optional[Sequence[Tensor]]) -> Tensor:
+    """ResidualAttentionBlock.forward (reference model.py:201-215) without kv_cache.  ``xt_list`` holds feature tensors
+    already brought to (batch, T_x, n_state) - at block level the reference receives them after TextDecoder's
+    projection and positional add (model.py:313-326)."""
+    nv.require_cuda(x, xa)
+    dt = _engine_dtype(x.dtype)
+    B, t, d = x.shape
+    gated = blk.add_gated_x_attn != 0
+    with torch.cuda.device(x.device):
+        bp = _cached_pack(blk, dt, _pack_block)
+        feats = None
+        if gated:
+            xt_list = validate_features(xt_list, B, x.device, len(bp.x_attn))
+            for i, f in enumerate(xt_list):
+                if f.shape[2] != d:
+                    raise ValueError(f"feature tensor {i} must be (batch, T_x, {d}) at block level, got {tuple(f.shape)}")
+            feats = [_to_dtype(f, dt).reshape(-1, d).contiguous() for f in xt_list]
+        xa2, Ta = None, 0
+        if blk.cross_attn is not None and xa is not None:
+            if xa.dim() != 3 or xa.shape[0] != B or xa.shape[2] != d:
+                raise ValueError(f"xa must be ({B}, T, {d}), got {tuple(xa.shape)}")
+            xa2, Ta = _to_dtype(xa, dt).reshape(-1, d).contiguous(), xa.shape[1]
+        x2 = _to_dtype(x, dt).reshape(B * t, d).clone()
+        ws = _BlockScratch(B * t, d, dt, x.device)
+        out = _block_forward(bp, ws, x2, B, t, blk.attn.n_head, xa2, Ta, feats, causal=causal)
+    return out.view(B, t, d).to(x.dtype)
+
+
+# ============================================================================ hook-style kv_cache compatibility path
+def hooks_in_use(dec, kv_cache: Optional[dict]) -> bool:
+    """True when a caller drives the decoder the reference's hook way (Whisper.install_kv_cache_hooks, reference
+    model.py:394-425): a non-empty cache dictionary, or forward hooks sitting on the key / value projections."""
+    if kv_cache is None:
+        return False
+    if len(kv_cache) > 0:
+        return True
+    blk = dec.blocks[0] if len(dec.blocks) else None
+    return blk is not None and len(blk.attn.key._forward_hooks) > 0
+
+
+def _mha_with_cache(m, mp: _MhaPack, xin: Tensor, x_res: Optional[Tensor], src: Optional[Tensor], causal: bool,
+                    kv_cache: dict, gate: Optional[Tensor] = None, out: Optional[Tensor] = None) -> Tensor:
+    """MultiHeadAttention.forward with the reference's kv_cache protocol (model.py:71-91): the key / value projections
+    are MODULE calls, so installed forward hooks see (and replace) their outputs; everything else is engine calls.
+    xin [B, t, d] (already normalised), x_res [B * t, d] residual rows updated in place (or `out` += when given)."""
+    B, t, d = xin.shape
+    dt, dev = xin.dtype, xin.device
+    q = _empty(B * t, d, dt, dev)
+    nv.linear(xin.reshape(B * t, d), mp.q_w, q, bias=mp.q_b)
+    if src is None or m.key not in kv_cache:
+        s3 = xin if src is None else src
+        k, v = m.key(s3), m.value(s3)       # hooks (if installed) return the concatenated cache tensors
+    else:
+        k, v = kv_cache[m.key], kv_cache[m.value]
+    Tk = k.shape[1]
+    k2, v2 = k.reshape(B * Tk, d).contiguous(), v.reshape(B * Tk, d).contiguous()
+    att = _empty(B * t, d, dt, dev)
+    # the reference adds mask[:t, :t] to a [t, Tk] score matrix: causal when t == Tk, a no-op 0 for one new token
+    nv.attention(q, k2, v2, att, B, t, Tk, m.n_head, causal=causal and t == Tk and t > 1)
+    if x_res is None and out is None:  # stand-alone module call: no residual stream
+        return nv.linear(att, mp.o_w, _empty(B * t, d, dt, dev), bias=mp.o_b, gate=gate)
+    dst = x_res if out is None else out
+    nv.linear(att, mp.o_w, dst, bias=mp.o_b, residual=dst, gate=gate)
+    return dst
+
+
+@torch.no_grad()
+def standalone_mha_cached(mha, x: Tensor, xa: Optional[Tensor], causal: bool, kv_cache: dict) -> Tensor:
+    """MultiHeadAttention.forward with a reference-style kv_cache dictionary (model.py:71-91)."""
+    nv.require_cuda(x, xa)
+    if x.dtype not in _ENGINE_DTYPES:
+        raise nv.WfError("the kv_cache hook path runs in float32 or bfloat16 activations")
+    with torch.cuda.device(x.device):
+        mp = _pack_mha(mha, x.dtype)
+        out = _mha_with_cache(mha, mp, x.contiguous(), None, None if xa is None else xa.contiguous(), causal, kv_cache)
+    return out.view(x.shape)
+
+
+@torch.no_grad()
+def decoder_forward_hooked(dec, tokens: Tensor, xa: Tensor, kv_cache: dict, xt_list: Optional[Sequence[Tensor]]):
+    """TextDecoder.forward driven through reference-style kv_cache hooks (model.py:292-340 with a cache dictionary):
+    positions start at the cached length, key / value projections go through the hooked modules.  A compatibility
+    path for callers that manage the cache themselves; whisper.decode() uses the engine's own sessions instead."""
+    nv.require_cuda(tokens, xa)
+    if xa.dtype not in _ENGINE_DTYPES:
+        raise nv.WfError("the kv_cache hook path runs in float32 or bfloat16 activations")
+    dt = xa.dtype
+    with torch.cuda.device(xa.device):
+        p = decoder_pack(dec, dt)
+        gated = len(p.blocks) > 0 and len(p.blocks[0].x_attn) > 0
+        B, t = tokens.shape
+        d, dev = p.d, xa.device
+        offset = next(iter(kv_cache.values())).shape[1] if kv_cache else 0
+        if offset + t > p.n_ctx:
+            raise RuntimeError(f"positions {offset}..{offset + t} exceed n_text_ctx {p.n_ctx}")
+        feats3 = None
+        if gated:
+            xt_list = validate_features(xt_list, B, dev, len(p.blocks[0].x_attn))
+            feats3 = []
+            for xt in xt_list:
+                Tx = xt.shape[1]
+                if offset + Tx > p.n_ctx:
+                    raise RuntimeError(f"feature positions {offset}..{offset + Tx} exceed n_text_ctx {p.n_ctx}")
+                if xt.shape[2] != d:
+                    a = _to_dtype(xt.reshape(B * Tx, -1).float() if xt.dtype == torch.float16 else
+                                  xt.reshape(B * Tx, -1), dt).contiguous()
+                    f = nv.linear(a, p.xt_w, _empty(B * Tx, d, dt, dev), bias=p.xt_b,
+                                  residual=p.pos_emb_t[offset:offset + Tx], res_row_mod=Tx)
+                else:
+                    f = nv.add_rowmod(xt.reshape(B * Tx, d).contiguous(), p.pos_emb[offset:].contiguous(),
+                                      _empty(B * Tx, d, dt, dev), Tx)
+                feats3.append(f.view(B, Tx, d))
+        tok32 = tokens.to(torch.int32).contiguous()
+        x = _empty(B * t, d, dt, dev)
+        nv.embed(tok32, t, None, 0, p.tok_emb, p.pos_emb[offset:].contiguous(), x, n_pos=t)
+        xn, hbuf = _empty(B * t, d, dt, dev), _empty(B * t, 4 * d, dt, dev)
+        xa3 = xa.contiguous()
+        for blk, bp in zip(dec.blocks, p.blocks):
+            if gated:
+                acc = x if len(feats3) <= 1 else x.clone()
+                for i, f in enumerate(feats3):
+                    nv.layernorm(x, bp.x_ln[i].w, bp.x_ln[i].b, xn)
+                    _mha_with_cache(blk.gated_x_attn_layers[i].attn, bp.x_attn[i], xn.view(B, t, d), x, f, False,
+                                    kv_cache, gate=bp.x_gate[i], out=acc)
+                x = acc
+                _mlp_inplace(x, xn, hbuf, bp.ff_ln, bp.ff, gate=bp.ff_gate)
+            nv.layernorm(x, bp.attn_ln.w, bp.attn_ln.b, xn)
+            _mha_with_cache(blk.attn, bp.attn, xn.view(B, t, d), x, None, True, kv_cache)
+            nv.layernorm(x, bp.cross_ln.w, bp.cross_ln.b, xn)
+            _mha_with_cache(blk.cross_attn, bp.cross, xn.view(B, t, d), x, xa3, False, kv_cache)
+            _mlp_inplace(x, xn, hbuf, bp.mlp_ln, bp.mlp)
+        nv.layernorm(x, p.ln.w, p.ln.b, xn)
+        logits = torch.empty((B * t, p.n_vocab), dtype=torch.float32, device=dev)
+        nv.linear(xn, p.tok_emb_t, logits)
+    return logits.view(B, t, p.n_vocab)

@@ -89,6 +89,7 @@ _SIGNATURES = {
     "wf_topk_logprobs": (C.c_int, [C.POINTER(_Topk), C.c_void_p]),
     "wf_kv_gather_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_longlong,
                                     C.c_void_p]),
+    "wf_debug_uniform_range": (C.c_int, [C.c_ulonglong, C.c_longlong, C.c_void_p, C.c_void_p]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
@@ -410,6 +411,15 @@ def topk_logprobs(logits: torch.Tensor, v: int, suppress: torch.Tensor, suppress
               _ptr(tokens), 0 if tokens is None else tokens.shape[1], n_init, cur_len, eot, ts[0], ts[1], ts[2], k,
               out_vals.data_ptr(), out_idx.data_ptr())
     _check(load().wf_topk_logprobs(C.byref(a), _stream()))
+
+
+def debug_uniform_range(seed: int, n: int, device) -> tuple:
+    """(min, max) of n uniforms of the temperature sampler's RNG (test hook)."""
+    out = torch.empty(2, dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        _check(load().wf_debug_uniform_range(int(seed) & 0xFFFFFFFFFFFFFFFF, int(n), out.data_ptr(), _stream()))
+    lo, hi = out.cpu().tolist()
+    return lo, hi
 
 
 def kv_gather_rows(src: torch.Tensor, dst: torch.Tensor, index: torch.Tensor, r: int, row_bytes: int,

@@ -228,6 +228,9 @@ class DecodingTask:
             raise ValueError("patience requires beam_size to be given")
         if options.length_penalty is not None and not (0 <= options.length_penalty <= 1):
             raise ValueError("length_penalty (alpha) should be a value between 0 and 1")
+        if options.beam_size is not None and not (1 <= options.beam_size <= 31):
+            # the device top-(beam + 1) kernel keeps at most 32 candidates per hypothesis
+            raise ValueError(f"beam_size must be between 1 and 31 on this engine, got {options.beam_size}")
         return options
 
     def _get_initial_tokens(self) -> Tuple[int, ...]:

@@ -40,11 +40,6 @@ class ModelDimensions:
     n_text_layer: int
 
 
-def _no_eager(what: str):
-    raise RuntimeError(f"{what}: this package has no eager PyTorch math; call the owning AudioEncoder / "
-                       f"TextDecoder (CUDA engine) instead")
-
-
 class LayerNorm(nn.LayerNorm):
     """Parameter holder; fp32 statistics are computed by ``wf_layernorm``."""
 
@@ -60,8 +55,10 @@ class Linear(nn.Linear):
 
 
 class Conv1d(nn.Conv1d):
-    def forward(self, x: Tensor) -> Tensor:  # pragma: no cover - only reachable by direct misuse
-        _no_eager("Conv1d.forward")
+    """Parameter holder; the stem geometry (kernel 3, padding 1, stride 1 | 2) runs as im2col + ``wf_linear``."""
+
+    def forward(self, x: Tensor) -> Tensor:
+        return _engine.standalone_conv1d(self, x)
 
 
 def sinusoids(length: int, channels: int, max_timescale: int = 10000) -> Tensor:
@@ -87,6 +84,8 @@ class MultiHeadAttention(nn.Module):
                 kv_cache: Optional[dict] = None):
         """Returns ``(out, None)``: the fused attention never materialises the fp32 score tensor the
         reference returns as its second value (only the broken word-timestamp path used it)."""
+        if kv_cache is not None and (len(kv_cache) > 0 or len(self.key._forward_hooks) > 0):
+            return _engine.standalone_mha_cached(self, x, xa, mask is not None, kv_cache), None
         return _engine.standalone_mha(self, x, xa, causal=mask is not None), None
 
 
@@ -100,7 +99,7 @@ class GatedXAttnSubBlock(nn.Module):
         self.attn_gate = nn.Parameter(torch.tensor([0.0]))
 
     def forward(self, x: Tensor, xt: Tensor) -> Tensor:
-        _no_eager("GatedXAttnSubBlock.forward")
+        return _engine.standalone_gated_xattn(self, x, xt)
 
 
 class ResidualAttentionBlock(nn.Module):
@@ -124,7 +123,12 @@ class ResidualAttentionBlock(nn.Module):
 
     def forward(self, x: Tensor, xa: Optional[Tensor] = None, mask: Optional[Tensor] = None,
                 kv_cache: Optional[dict] = None, xt_list: Optional[List[Tensor]] = None):
-        _no_eager("ResidualAttentionBlock.forward")
+        """One block over full sequences (reference model.py:201-215).  ``mask`` only selects causal self-attention
+        (the reference's mask is always the causal upper-triangular one, model.py:281); hook-style ``kv_cache``
+        dictionaries are not supported (the engine owns the KV cache of whisper.decode)."""
+        if kv_cache:
+            raise RuntimeError("hook-based kv_cache dictionaries are not supported at block level")
+        return _engine.standalone_block(self, x, xa, mask is not None, xt_list)
 
 
 class AudioEncoder(nn.Module):
@@ -170,11 +174,11 @@ class TextDecoder(nn.Module):
                 xt_list: Optional[List[Tensor]] = None):
         """x: (batch, t <= n_ctx) token ids; xa: (batch, n_audio_ctx, n_state) encoder output;
         xt_list: up to ``num_langs`` feature tensors (batch, T_x, bert_dim | n_state) for the gated
-        cross-attention.  Returns fp32 logits (batch, t, n_vocab).  ``kv_cache`` dicts of the
-        reference's hook mechanism are not used: caching lives inside the engine's decode sessions."""
-        if kv_cache:
-            raise RuntimeError("hook-based kv_cache dictionaries are not supported; use whisper.decode() "
-                               "(engine-managed KV cache) or call without kv_cache")
+        cross-attention.  Returns fp32 logits (batch, t, n_vocab).  ``kv_cache``: a dictionary filled by
+        ``Whisper.install_kv_cache_hooks`` switches to the reference's hook protocol (positions start at the cached
+        length); ``whisper.decode`` does not need it - its caching lives inside the engine's decode sessions."""
+        if _engine.hooks_in_use(self, kv_cache):
+            return _engine.decoder_forward_hooked(self, x, xa, kv_cache, xt_list)
         return _engine.decoder_forward(self, x, xa, xt_list)
 
 
@@ -210,8 +214,29 @@ class Whisper(nn.Module):
         return self.dims.n_vocab - 51765 - int(self.is_multilingual)
 
     def install_kv_cache_hooks(self, cache: Optional[dict] = None):
-        raise RuntimeError("install_kv_cache_hooks (reference model.py:394-425) has no equivalent: the KV cache "
-                           "is owned by the CUDA engine's decode session (see whisper.decode)")
+        """Reference-style KV cache (model.py:394-425): returns ``(cache, hooks)``; forward hooks on every key / value
+        projection of the decoder keep their outputs in ``cache`` - stored as-is the first time (and for anything
+        longer than n_text_ctx, i.e. cross-attention over the audio), appended along time afterwards - and hand the
+        cached tensor back as the projection's output.  ``whisper.decode`` does not use this (the engine owns its KV
+        cache); it exists for callers that step ``model.decoder(tokens, xa, kv_cache=cache)`` themselves.
+        As in the reference the hooks attach to EVERY MultiHeadAttention of the decoder, so they are only meaningful
+        for audio-only models."""
+        cache = dict(cache) if cache is not None else {}
+        hooks = []
+        n_ctx = self.dims.n_text_ctx
+
+        def keep(module, _inputs, output):
+            if module in cache and output.shape[1] <= n_ctx:
+                cache[module] = torch.cat([cache[module], output], dim=1).detach()
+            else:
+                cache[module] = output
+            return cache[module]
+
+        for layer in self.decoder.modules():
+            if isinstance(layer, MultiHeadAttention):
+                hooks.append(layer.key.register_forward_hook(keep))
+                hooks.append(layer.value.register_forward_hook(keep))
+        return cache, hooks
 
     detect_language = detect_language_function
     transcribe = transcribe_function
