@@ -154,6 +154,17 @@ int wf_latent_query(const void* q, long long ldq, const void* wkT, void* qp, int
 int wf_latent_attention(const void* qp, const void* src, void* ctx, int B, int T, int H, wf_stream_t stream);
 int wf_latent_value(const void* ctx, const void* wv, long long ldw, const float* bv, void* o, long long ldo, int R,
                     int H, wf_stream_t stream);
+/* Split form for full batches (more clips than SM pairs): the attention kernel is persistent, its 2-CTA clusters take
+ * equal ranges of the B x ceil(T / 64) tile sequence, and a clip cut at a range border is left as TWO contexts, each
+ * normalised by its own row sum: ctx [2][B, H, d] (parts part_stride elements apart), ml [2][B][32] float pairs
+ * (reference maximum in log2 units, row sum; row sum 0 = part absent).  wf_latent_value_split projects both parts and
+ * blends them with the softmax weights of the two segments (the projection is linear in the context).
+ * wf_latent_split_supported(H) = 1 when the one-pass kernel serves n_state = 64 H (a multiple of 256, >= 512). */
+int wf_latent_split_supported(int H);
+int wf_latent_attention_split(const void* qp, const void* src, void* ctx, long long part_stride, float* ml, int B, int T,
+                              int H, wf_stream_t stream);
+int wf_latent_value_split(const void* ctx, long long part_stride, const float* ml, const void* wv, long long ldw,
+                          const float* bv, void* o, long long ldo, int R, int H, wf_stream_t stream);
 
 /* ---- sampling: whisper/decoding.py:427-442 (SuppressBlank/SuppressTokens), :276-302 (GreedyDecoder),
  *      :697-701 (no_speech_prob), loop bookkeeping of :688-718 ------------------------------------ */

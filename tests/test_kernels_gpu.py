@@ -639,6 +639,55 @@ def test_latent_cross_attention_matches_kv_attention(nv, H, B, T):
     assert rel_l2(out, _latent_reference(q, src, wk, wv, bv, H)) < 1.5e-2
 
 
+@pytest.mark.parametrize("H,B,T", [(20, 128, 1500), (20, 128, 750), (16, 100, 333), (20, 75, 64), (12, 80, 130),
+                                   (20, 5, 200)])
+def test_latent_split_form_matches_single_part(nv, H, B, T):
+    """Full batches run the persistent pair kernel: clusters take equal tile ranges, a clip cut at a range border is
+    left as two separately normalised contexts + (maximum, row sum) per head, and latent_value blends them.  The blend
+    must equal attention over projected K / V, every clip must have a first part, and a second part exists exactly
+    where the partition of B * ceil(T / 64) tiles over the SM pairs cuts a clip."""
+    from helpers import rel_l2
+    if not nv.latent_split_supported(H):
+        pytest.skip("no pair kernel for this width")
+    d = 64 * H
+    bf = torch.bfloat16
+    q = _randn(B, d, dtype=bf, seed=21)
+    src = _randn(B, T, d, dtype=bf, seed=22)
+    wk = _randn(d, d, dtype=bf, seed=23, scale=2.0 / math.sqrt(d))
+    wv = _randn(d, d, dtype=bf, seed=24, scale=1.0 / math.sqrt(d))
+    bv = _randn(d, seed=25, scale=0.1)
+    qp = torch.empty(B, H, d, dtype=bf, device="cuda")
+    ctx = torch.zeros(2, B, H, d, dtype=bf, device="cuda")
+    ml = torch.full((2, B, 32, 2), float("nan"), device="cuda")
+    out = torch.full((B, d), float("nan"), dtype=bf, device="cuda")
+    nv.latent_query(q, wk.t().contiguous(), qp, H)
+    nv.latent_attention(qp, src, ctx, H, ml=ml)
+    nv.latent_value(ctx, wv, bv, out, H, ml=ml)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all()
+    l = ml[..., 1][:, :, :H]
+    assert torch.isfinite(l).all() and (l[0] > 0).all(), "every clip has a first part"
+    # where the second part exists: a clip is cut iff a cluster range border falls strictly inside it
+    n_tiles = (T + 63) // 64
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    clusters = sms // 2 if B > sms // 2 else B
+    borders = {B * n_tiles * c // clusters for c in range(1, clusters)}
+    cut = torch.tensor([any(b * n_tiles < g < (b + 1) * n_tiles for g in borders) for b in range(B)], device="cuda")
+    assert torch.equal((l[1] > 0).all(dim=1), cut) and torch.equal((l[1] > 0).any(dim=1), cut)
+    for lo in range(0, B, 16):
+        ref = _latent_reference(q[lo:lo + 16], src[lo:lo + 16], wk, wv, bv, H)
+        assert rel_l2(out[lo:lo + 16], ref) < 1.5e-2
+    # against the single-part form of the same kernel family (same rounding points up to the blend)
+    ctx1 = torch.empty(B, H, d, dtype=bf, device="cuda")
+    out1 = torch.empty(B, d, dtype=bf, device="cuda")
+    nv.latent_attention(qp, src, ctx1, H)
+    nv.latent_value(ctx1, wv, bv, out1, H)
+    torch.cuda.synchronize()
+    assert rel_l2(out, out1) < 6e-3
+    whole = ~cut
+    assert torch.equal(ctx[0][whole], ctx1[whole]), "uncut clips: same tiles in the same order, bit for bit"
+
+
 def test_latent_cross_attention_headline_size(nv):
     """BASELINE config 4 shapes (128 clips x 1500 encoder rows, 20 heads): the latent path against attention over
     projected K / V, and two properties that do not need a reference: the result does not depend on which clips share

@@ -346,7 +346,7 @@ def test_absorbed_projection_identity_against_oracle_mha():
 
 
 def test_latent_path_gate(monkeypatch):
-    """whisper/_engine.py:latent_cross_enabled - greedy rows only, head_dim 64, at most 32 heads, default from 112 rows."""
+    """whisper/_engine.py:latent_cross_enabled - greedy rows only, head_dim 64, at most 24 heads, default from 112 rows."""
     from whisper._engine import latent_cross_enabled as on
     monkeypatch.delenv("WF_LATENT", raising=False)
     assert on(128, 1, 20, 1280) and on(112, 1, 16, 1024) and not on(111, 1, 20, 1280)

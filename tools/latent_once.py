@@ -11,8 +11,10 @@ B, H, T = int(os.environ.get("B", 128)), int(os.environ.get("H", 20)), int(os.en
 d = 64 * H
 src = torch.randn(B, T, d, device="cuda").bfloat16()
 qp = (torch.randn(B, H, d, device="cuda") * 0.05).bfloat16()
-ctx = torch.empty(B, H, d, device="cuda", dtype=torch.bfloat16)
+split = os.environ.get("SPLIT", "1") == "1" and nv.latent_split_supported(H)
+ctx = torch.zeros(2 if split else 1, B, H, d, device="cuda", dtype=torch.bfloat16)
+ml = torch.zeros(2, B, 32, 2, device="cuda") if split else None
 for _ in range(3):
-    nv.latent_attention(qp, src, ctx, H)
+    nv.latent_attention(qp, src, ctx if split else ctx[0], H, ml=ml)
 torch.cuda.synchronize()
 print("ok", float(ctx.float().abs().mean()))

@@ -242,9 +242,18 @@ def latent():
         nv.latent_query(q, wk_t, qp, H)
         t_q = graph_timeit(lambda i: nv.latent_query(q, wk_t, qp, H), 1)
         t_a = graph_timeit(lambda i: nv.latent_attention(qp, srcs[i], ctx, H), n_rot, reps=16)
+        t_s = None
+        if nv.latent_split_supported(H):
+            ctx2 = torch.zeros(2, B, H, d, device="cuda", dtype=torch.bfloat16)
+            ml = torch.zeros(2, B, 32, 2, device="cuda")
+            nv.latent_attention(qp, srcs[0], ctx2, H, ml=ml)
+            t_s = graph_timeit(lambda i: nv.latent_attention(qp, srcs[i], ctx2, H, ml=ml), n_rot, reps=16)
+            t_v2 = graph_timeit(lambda i: nv.latent_value(ctx2, wv, bv, out, H, ml=ml), 1)
         t_v = graph_timeit(lambda i: nv.latent_value(ctx, wv, bv, out, H), 1)
+        split = "" if t_s is None else (f" | split form: attention {t_s:.1f} us = {B * T * d * 2 / t_s / 1e3:.0f} GB/s, "
+                                        f"value {t_v2:.2f} us")
         print(f"B={B} H={H} T={T}: query {t_q:.2f} us | attention {t_a:.1f} us = {B * T * d * 2 / t_a / 1e3:.0f} GB/s "
-              f"| value {t_v:.2f} us", flush=True)
+              f"| value {t_v:.2f} us{split}", flush=True)
 
 
 if __name__ == "__main__":

@@ -172,12 +172,24 @@ int wf_latent_query(const void* q, long long ldq, const void* wkT, void* qp, int
 }
 int wf_latent_attention(const void* qp, const void* src, void* ctx, int B, int T, int H, wf_stream_t stream) {
   WF_REQUIRE(qp && src && ctx, "wf_latent_attention: null buffer");
-  return latent_attention(qp, src, ctx, B, T, H, S(stream));
+  return latent_attention(qp, src, ctx, 0, nullptr, B, T, H, S(stream));
 }
 int wf_latent_value(const void* ctx, const void* wv, long long ldw, const float* bv, void* o, long long ldo, int R,
                     int H, wf_stream_t stream) {
   WF_REQUIRE(ctx && wv && o && R > 0 && H > 0, "wf_latent_value: null buffer / empty problem");
-  return latent_value(ctx, wv, ldw, bv, o, ldo, R, H, S(stream));
+  return latent_value(ctx, 0, nullptr, wv, ldw, bv, o, ldo, R, H, S(stream));
+}
+int wf_latent_split_supported(int H) { return H > 0 && latent_pair_supported(H) ? 1 : 0; }
+int wf_latent_attention_split(const void* qp, const void* src, void* ctx, long long part_stride, float* ml, int B, int T,
+                              int H, wf_stream_t stream) {
+  WF_REQUIRE(qp && src && ctx && ml && part_stride >= static_cast<long long>(B) * H * H * 64,
+             "wf_latent_attention_split: null buffer / parts overlap");
+  return latent_attention(qp, src, ctx, part_stride, ml, B, T, H, S(stream));
+}
+int wf_latent_value_split(const void* ctx, long long part_stride, const float* ml, const void* wv, long long ldw,
+                          const float* bv, void* o, long long ldo, int R, int H, wf_stream_t stream) {
+  WF_REQUIRE(ctx && ml && wv && o && R > 0 && H > 0, "wf_latent_value_split: null buffer / empty problem");
+  return latent_value(ctx, part_stride, ml, wv, ldw, bv, o, ldo, R, H, S(stream));
 }
 
 int wf_sample_greedy(const wf_sample_t* a, wf_stream_t stream) {

@@ -69,9 +69,16 @@ int attention_full_tc(const void* q, long long ldq, const void* k, long long ldk
 
 // latent.cu (one-token cross-attention over the source rows: absorbed K / V projections, bf16)
 int latent_query(const void* q, long long ldq, const void* wkT, void* qp, int R, int H, cudaStream_t stream);
-int latent_attention(const void* qp, const void* src, void* ctx, int B, int T, int H, cudaStream_t stream);
-int latent_value(const void* ctx, const void* wv, long long ldw, const float* bv, void* o, long long ldo, int R, int H,
-                 cudaStream_t stream);
+// ml == nullptr: ctx [B, H, d].  ml != nullptr (split form, needs latent_pair_supported(H)): ctx [2][B, H, d] with
+// the parts `part_stride` elements apart and ml [2][B][32] pairs (reference maximum in log2 units, row sum).
+int latent_attention(const void* qp, const void* src, void* ctx, long long part_stride, float* ml, int B, int T, int H,
+                     cudaStream_t stream);
+int latent_value(const void* ctx, long long part_stride, const float* ml, const void* wv, long long ldw, const float* bv,
+                 void* o, long long ldo, int R, int H, cudaStream_t stream);
+// latent_pair.cu (one-pass latent_attention on 2-CTA clusters; WF_ERR_UNSUPPORTED when the shape does not fit)
+bool latent_pair_supported(int H);
+int latent_attention_pair(const void* qp, const void* src, void* ctx, float* ml, long long part_stride, int B, int T,
+                          int H, cudaStream_t stream);
 
 // decode.cu
 int attention_decode(int dtype, const void* q, long long ldq, const void* kc, const void* vc, long long ld_kv,

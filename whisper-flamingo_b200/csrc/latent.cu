@@ -56,9 +56,15 @@ static constexpr int LA_PT = (LA_KT / 64) * LA_PATOM;   // P^T operand of a tile
 static constexpr int LA_MISC = 3072;                // floats: m_ref[32] alpha[32] 1/l[32] red[4][32] | flags | barriers
 static constexpr int LA_MAX_A = 16, LA_MAX_B = 6;
 static constexpr int LA_SMEM_LIMIT = 227 * 1024;
-static constexpr int LA_TMEM_COLS = 512;            // S^T (2 x 32) | C^T (d / 128 accumulators x 32)
-static constexpr int LA_TMEM_C = 2 * LA_NH;
-static constexpr int LA_THREADS = 256;
+#ifndef LA_ISSUERS
+#define LA_ISSUERS 2       // MMA-issuing threads per pass.  A narrow tcgen05.mma occupies the tensor front end for 40 clk but
+#endif                     // costs its issuing thread 53 clk, and a thread that waits for a chunk issues nothing: with two
+                           // threads per pass (own accumulators) one waits while the other issues
+static constexpr int LA_NI = LA_ISSUERS;
+static_assert(LA_NI == 1 || LA_NI == 2, "one or two issuing threads per pass");
+static constexpr int LA_TMEM_COLS = 512;            // S^T (2 buffers x LA_NI x 32) | C^T (d / 128 accumulators x 32)
+static constexpr int LA_TMEM_C = 2 * LA_NI * LA_NH;
+static constexpr int LA_THREADS = 256 + (LA_NI - 1) * 64;   // warps 8, 9: second issuer of pass A / pass B
 #ifndef LA_PF
 #define LA_PF 0        // chunks prefetched into L2 ahead of pass A (measured: 6 -> 133 us, 12 -> 141 us, 24 -> 178 us vs 124)
 #endif
@@ -158,7 +164,7 @@ latent_attn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     prog[0] = 0;
     prog[1] = 0;
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 128); mbar_init(&p_ready[i], 128); mbar_init(&c_done[i], 1);
+      mbar_init(&s_full[i], LA_NI); mbar_init(&s_free[i], 128); mbar_init(&p_ready[i], 128); mbar_init(&c_done[i], LA_NI);
     }
     mbar_fence_init();
   }
@@ -262,14 +268,14 @@ latent_attn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         prog[1] = (j * NS + a + 1) * 2;
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ------------------------------------------------------------------ MMA issuer, pass A
+  } else if ((warp == 1 || (LA_NI == 2 && warp == 8)) && lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer(s), pass A
     // S^T[128 keys x 32 heads] = chunk (A, K-major) x q'^T (B, K-major; rows >= HP of an atom alias the next atom and
-    // only produce head columns nobody reads), K = d in 16-column steps
+    // only produce head columns nobody reads), K = d in 16-column steps.  Issuer `me` takes the chunks with index
+    // = me (mod LA_NI) into its own accumulator (the softmax adds them).
     constexpr uint32_t idesc_s = umma_idesc_bf16(LA_KT, LA_NH);
     const uint32_t ra = smem_u32(ring_a), qa = smem_u32(qs);
-    int slot = 0;
-    uint32_t phase = 0;
+    const int me = warp == 1 ? 0 : 1;
 #if !LA_STREAM_Q
     mbar_wait(q_full, 0);
 #endif
@@ -285,36 +291,38 @@ latent_attn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 #endif
       if (j >= 2) mbar_wait(&s_free[j & 1], ((j >> 1) - 1) & 1);
       LA_T(ts);
-      for (int c = 0; c < 2 * NS; ++c) {
-        mbar_wait(&full_a[slot], phase);
+      const uint32_t acc = tmem_base + ((j & 1) * LA_NI + me) * LA_NH;
+      for (int c = me; c < 2 * NS; c += LA_NI) {
+        const int g = j * 2 * NS + c;          // chunk counter of the ring
+        const int slot = g % NA;
+        mbar_wait(&full_a[slot], (g / NA) & 1);
         LA_T(tw);
         tc_fence_after();
         const uint64_t a_desc = umma_desc_kmajor_sw128(ra + slot * slot_a);
         const uint64_t b_desc = umma_desc_kmajor_sw128(LA_STREAM_Q ? ra + slot * slot_a + LA_CHUNK : qa + c * q_atom);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_f16(tmem_base + (j & 1) * LA_NH, a_desc + 2 * k, b_desc + 2 * k, idesc_s, (c | k) != 0);
+          umma_f16(acc, a_desc + 2 * k, b_desc + 2 * k, idesc_s, (c >= LA_NI || k > 0) ? 1u : 0u);
         LA_T(tm);
         umma_commit(&empty_a[slot]);
         LA_T(tcm);
-        if (++slot == NA) { slot = 0; phase ^= 1; }
       }
       umma_commit(&s_full[j & 1]);
     }
 #ifdef LA_TIMING
     if (blockIdx.x == 0)
-      printf("issuer A per chunk: wait full %lld | 4 MMAs %lld | commit %lld ; per tile: wait s_free %lld ; total/tile %lld\n",
-             tw / (n_tiles * 2 * NS), tm / (n_tiles * 2 * NS), tcm / (n_tiles * 2 * NS), ts / n_tiles,
-             (clock64() - tt0) / n_tiles);
+      printf("issuer A%d per chunk: wait full %lld | 4 MMAs %lld | commit %lld ; per tile: wait s_free %lld ; total/tile %lld\n",
+             me, tw / (n_tiles * 2 * NS / LA_NI), tm / (n_tiles * 2 * NS / LA_NI), tcm / (n_tiles * 2 * NS / LA_NI),
+             ts / n_tiles, (clock64() - tt0) / n_tiles);
 #endif
-  } else if (warp == 3 && lane == 0) {
-    // ------------------------------------------------------------------ MMA issuer, pass B
+  } else if ((warp == 3 || (LA_NI == 2 && warp == 9)) && lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer(s), pass B
     // C^T[128 columns x 32 heads] (+)= stage^T (A, MN-major: rows = keys, two 64-column atoms 16 KB apart) x P^T (B,
-    // K-major, two atoms of 64 keys), K = 128 keys in 16-key steps
+    // K-major, two atoms of 64 keys), K = 128 keys in 16-key steps.  Issuer `me` takes the stages with ring counter
+    // = me (mod LA_NI); every stage has its own accumulator.
     constexpr uint32_t idesc_c = la_idesc_a_mn(128, LA_NH);
     const uint32_t rb = smem_u32(ring_b), pa = smem_u32(pt);
-    int slot = 0;
-    uint32_t phase = 0;
+    const int me = warp == 3 ? 0 : 1;
 #ifdef LA_TIMING
     long long tw = 0, tm = 0, tcm = 0, ts = 0, tt0 = clock64();
 #endif
@@ -324,9 +332,13 @@ latent_attn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 #endif
       mbar_wait(&p_ready[j & 1], (j >> 1) & 1);
       LA_T(ts);
+      tc_fence_after();
       const uint32_t pb = pa + (j & 1) * LA_PT;
       for (int a = 0; a < NS; ++a) {
-        mbar_wait(&full_b[slot], phase);
+        const int g = j * NS + a;              // stage counter of the ring
+        if (LA_NI == 2 && (g & 1) != me) continue;
+        const int slot = g % NB;
+        mbar_wait(&full_b[slot], (g / NB) & 1);
         LA_T(tw);
         tc_fence_after();
         const uint32_t st = rb + slot * LA_STAGE_B;
@@ -337,16 +349,16 @@ latent_attn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         LA_T(tm);
         umma_commit(&empty_b[slot]);
         LA_T(tcm);
-        if (++slot == NB) { slot = 0; phase ^= 1; }
       }
       umma_commit(&c_done[j & 1]);
     }
 #ifdef LA_TIMING
     if (blockIdx.x == 0)
-      printf("issuer B per stage: wait full %lld | 8 MMAs %lld | commit %lld ; per tile: wait p_ready %lld ; total/tile %lld\n",
-             tw / (n_tiles * NS), tm / (n_tiles * NS), tcm / (n_tiles * NS), ts / n_tiles, (clock64() - tt0) / n_tiles);
+      printf("issuer B%d per stage: wait full %lld | 8 MMAs %lld | commit %lld ; per tile: wait p_ready %lld ; total/tile %lld\n",
+             me, tw / (n_tiles * NS / LA_NI), tm / (n_tiles * NS / LA_NI), tcm / (n_tiles * NS / LA_NI), ts / n_tiles,
+             (clock64() - tt0) / n_tiles);
 #endif
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 8) {
     // ------------------------------------------------------------------ softmax (thread = key = TMEM lane of S^T)
     const int wq = warp - 4;
     const int tid = threadIdx.x - 128;
@@ -370,8 +382,16 @@ latent_attn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       mbar_wait(&s_full[buf], ph);
       tc_fence_after();
       uint32_t sv[32];
-      tmem_ld_32x32(lane_base + buf * LA_NH, sv);
-      tmem_ld_wait();
+      tmem_ld_32x32(lane_base + buf * LA_NI * LA_NH, sv);
+      if (LA_NI == 2) {    // the two issuers of pass A dealt the chunks to two accumulators
+        uint32_t sv2[32];
+        tmem_ld_32x32(lane_base + (buf * LA_NI + 1) * LA_NH, sv2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int h = 0; h < LA_NH; ++h) sv[h] = __float_as_uint(__uint_as_float(sv[h]) + __uint_as_float(sv2[h]));
+      } else {
+        tmem_ld_wait();
+      }
       tc_fence_before();
       mbar_arrive(&s_free[buf]);
       const bool valid = lane_on && j * LA_KT + key < T;
@@ -466,10 +486,24 @@ latent_attn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   }
 }
 
-int latent_attention(const void* qp, const void* src, void* ctx, int B, int T, int H, cudaStream_t stream) {
+int latent_attention(const void* qp, const void* src, void* ctx, long long part_stride, float* ml, int B, int T, int H,
+                     cudaStream_t stream) {
   const int d = H * 64;
-  WF_REQUIRE(B > 0 && T > 0 && H > 0 && H <= LA_NH && d % 128 == 0,
-             "latent attention: needs head_dim 64, an even number of heads and at most 32 of them (got %d heads)", H);
+  WF_REQUIRE(B > 0 && T > 0 && H > 0 && H <= LA_NH && d % 128 == 0 && LA_TMEM_C + (d / 128) * LA_NH <= LA_TMEM_COLS,
+             "latent attention: needs head_dim 64, an even number of heads and at most %d of them (got %d heads)",
+             2 * (LA_TMEM_COLS - LA_TMEM_C) / LA_NH, H);
+  // default: the one-pass pair kernel (latent_pair.cu: 2-CTA clusters, tiles resident in shared memory);
+  // WF_LATENT_PASS=2 keeps this file's two-pass kernel (A/B measurements; also the fallback when d % 256 != 0)
+  static int passes = -1;
+  if (passes < 0) {
+    const char* e = getenv("WF_LATENT_PASS");
+    passes = e ? atoi(e) : 1;
+  }
+  if (passes != 2) {
+    const int rc1 = latent_attention_pair(qp, src, ctx, ml, part_stride, B, T, H, stream);
+    if (rc1 != WF_ERR_UNSUPPORTED) return rc1;
+  }
+  WF_REQUIRE(ml == nullptr, "latent attention: the split form needs the pair kernel (wf_latent_split_supported)");
   const int hp = (H + 7) / 8 * 8, ns = d / 128;
   const int q_atom = hp * 128;
   const int fixed = 1024 + (LA_STREAM_Q ? 0 : 2 * ns * q_atom) + 2 * LA_PT + LA_MISC;
@@ -478,11 +512,14 @@ int latent_attention(const void* qp, const void* src, void* ctx, int B, int T, i
 #ifdef LA_NB_FORCE
   int nb = LA_NB_FORCE;
 #else
-  int nb = (LA_KT == 128 ? (n >= 12 ? 3 : 2) : 4);
+  int nb = (LA_KT == 128 ? (n >= 12 ? (LA_NI == 2 ? 4 : 3) : 2) : 4);
 #endif
   if (nb > LA_MAX_B) nb = LA_MAX_B;
   int na = (LA_SMEM_LIMIT - fixed - nb * LA_STAGE_B) / slot_a;
   if (na > LA_MAX_A) na = LA_MAX_A;
+  // Two issuers per pass deal the ring slots by parity: a slot must always be consumed by the same thread (an mbarrier
+  // wait is only valid at most one phase ahead, and TMA boxes complete out of order), so both rings are even.
+  if (LA_NI == 2) { na &= ~1; nb &= ~1; }
   WF_REQUIRE(na >= 2, "latent attention: shared memory too small for the rings (%d chunks)", n);
   const int smem = fixed + na * slot_a + nb * LA_STAGE_B;
   CUtensorMap mx, mq;
@@ -577,11 +614,20 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// SPLIT: ctx holds two partial contexts per (row, head) `part_stride` elements apart, each normalised by its own row
+// sum, with ml[(part * R + row) * 32 + head] = (reference maximum in log2 units, row sum; 0 = part absent) - what the
+// persistent pair kernel (latent_pair.cu) leaves when a clip is cut at a cluster border.  The projection is linear in
+// the context: both parts are projected and blended with the softmax weights of their segments.
+template <bool SPLIT>
 __global__ void __launch_bounds__(128)
-latent_value_kernel(const __nv_bfloat16* __restrict__ ctx, const __nv_bfloat16* __restrict__ wv, long long ldw,
-                    const float* __restrict__ bv, __nv_bfloat16* __restrict__ o, long long ldo, int R, int H, int d) {
-  __shared__ __align__(16) __nv_bfloat16 As[LV_STAGES * LV_A];
-  __shared__ __align__(16) __nv_bfloat16 Bs[LV_STAGES * LV_B];
+latent_value_kernel(const __nv_bfloat16* __restrict__ ctx, long long part_stride, const float2* __restrict__ ml,
+                    const __nv_bfloat16* __restrict__ wv, long long ldw, const float* __restrict__ bv,
+                    __nv_bfloat16* __restrict__ o, long long ldo, int R, int H, int d) {
+  constexpr int NP = SPLIT ? 2 : 1;
+  constexpr int NST = SPLIT ? 3 : LV_STAGES;   // static shared memory stays under 48 KB with two A tiles per stage
+  __shared__ __align__(16) __nv_bfloat16 As[NP * NST * LV_A];
+  __shared__ __align__(16) __nv_bfloat16 Bs[NST * LV_B];
+  __shared__ float wgt[2][16];
   const int h = blockIdx.x, m0 = blockIdx.y * 16;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_chunks = d / 64;
@@ -595,63 +641,125 @@ latent_value_kernel(const __nv_bfloat16* __restrict__ ctx, const __nv_bfloat16* 
       cp_async_16(&Bs[st * LV_B + row * LQ_LD + c8], b_base + row * ldw + kc * 64 + c8, true);
     }
   };
-  auto load_a = [&](int kc, int st) {
+  auto load_a = [&](int kc, int st, int part) {
     const int row = threadIdx.x >> 3, c8 = (threadIdx.x & 7) * 8;
     const bool ok = m0 + row < R;
-    cp_async_16(&As[st * LV_A + row * LQ_LD + c8], a_base + (ok ? static_cast<long long>(row) * H * d : 0) + kc * 64 + c8,
-                ok);
+    cp_async_16(&As[(part * NST + st) * LV_A + row * LQ_LD + c8],
+                a_base + part * part_stride + (ok ? static_cast<long long>(row) * H * d : 0) + kc * 64 + c8, ok);
   };
   // the weights do not depend on the previous kernel: request them before the dependency wait
-  for (int s = 0; s < LV_STAGES - 1; ++s)
+  for (int s = 0; s < NST - 1; ++s)
     if (s < n_chunks) load_b(s, s);
   pdl_wait();
-  for (int s = 0; s < LV_STAGES - 1; ++s) {
-    if (s < n_chunks) load_a(s, s);
+  bool second = false;
+  if (SPLIT) {
+    // blend weights of the two parts of every row: w_p = l_p 2^(m_p - max) / sum
+    bool mine = false;
+    if (threadIdx.x < 16) {
+      const int row = m0 + threadIdx.x;
+      float w0 = 1.f, w1 = 0.f;
+      if (row < R) {
+        const float2 p0 = ml[static_cast<long long>(row) * 32 + h];
+        const float2 p1 = ml[(static_cast<long long>(R) + row) * 32 + h];
+        if (p1.y > 0.f) {
+          const float mx = fmaxf(p0.x, p1.x);
+          const float e0 = p0.y * ex2_approx(p0.x - mx), e1 = p1.y * ex2_approx(p1.x - mx);
+          const float inv = 1.0f / (e0 + e1);
+          w0 = e0 * inv;
+          w1 = e1 * inv;
+          mine = true;
+        }
+      }
+      wgt[0][threadIdx.x] = w0;
+      wgt[1][threadIdx.x] = w1;
+    }
+    second = __syncthreads_or(mine ? 1 : 0) != 0;
+  }
+  for (int s = 0; s < NST - 1; ++s) {
+    if (s < n_chunks) {
+      load_a(s, s, 0);
+      if (SPLIT && second) load_a(s, s, 1);
+    }
     cp_async_commit();     // group s = {A(s)} (+ all early B loads in group 0)
   }
-  float c[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  float c[NP][2][4];
+#pragma unroll
+  for (int p = 0; p < NP; ++p)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) c[p][nt][e] = 0.f;
   for (int kc = 0; kc < n_chunks; ++kc) {
-    cp_async_wait<LV_STAGES - 2>();
+    cp_async_wait<NST - 2>();
     __syncthreads();
-    const int nx = kc + LV_STAGES - 1;
-    if (nx < n_chunks) { load_b(nx, nx % LV_STAGES); load_a(nx, nx % LV_STAGES); }
+    const int nx = kc + NST - 1;
+    if (nx < n_chunks) {
+      load_b(nx, nx % NST);
+      load_a(nx, nx % NST, 0);
+      if (SPLIT && second) load_a(nx, nx % NST, 1);
+    }
     cp_async_commit();
-    const int st = kc % LV_STAGES;
+    const int st = kc % NST;
 #pragma unroll
     for (int kp = 0; kp < 2; ++kp) {
-      uint32_t a0[4], a1[4];
-      ldmatrix_x4(a0, &As[st * LV_A + (lane & 15) * LQ_LD + kp * 32 + (lane >> 4) * 8]);
-      ldmatrix_x4(a1, &As[st * LV_A + (lane & 15) * LQ_LD + kp * 32 + 16 + (lane >> 4) * 8]);
+      uint32_t bf[2][4];
 #pragma unroll
-      for (int nt = 0; nt < 2; ++nt) {
-        uint32_t bf[4];
-        ldmatrix_x4(bf, &Bs[st * LV_B + ((warp * 2 + nt) * 8 + (lane & 7)) * LQ_LD + kp * 32 + (lane >> 3) * 8]);
-        mma_bf16_16816(c[nt], a0, bf[0], bf[1]);
-        mma_bf16_16816(c[nt], a1, bf[2], bf[3]);
+      for (int nt = 0; nt < 2; ++nt)
+        ldmatrix_x4(bf[nt], &Bs[st * LV_B + ((warp * 2 + nt) * 8 + (lane & 7)) * LQ_LD + kp * 32 + (lane >> 3) * 8]);
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        if (p == 1 && !second) continue;
+        uint32_t a0[4], a1[4];
+        const __nv_bfloat16* ap = &As[(p * NST + st) * LV_A];
+        ldmatrix_x4(a0, ap + (lane & 15) * LQ_LD + kp * 32 + (lane >> 4) * 8);
+        ldmatrix_x4(a1, ap + (lane & 15) * LQ_LD + kp * 32 + 16 + (lane >> 4) * 8);
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          mma_bf16_16816(c[p][nt], a0, bf[nt][0], bf[nt][1]);
+          mma_bf16_16816(c[p][nt], a1, bf[nt][2], bf[nt][3]);
+        }
       }
     }
   }
   const int g = lane >> 2, t = lane & 3;
+  float wa0 = 1.f, wb0 = 1.f, wa1 = 0.f, wb1 = 0.f;     // weights of rows g (a) and g + 8 (b), parts 0 / 1
+  if (SPLIT && second) { wa0 = wgt[0][g]; wb0 = wgt[0][g + 8]; wa1 = wgt[1][g]; wb1 = wgt[1][g + 8]; }
 #pragma unroll
   for (int nt = 0; nt < 2; ++nt) {
     const int col = h * 64 + (warp * 2 + nt) * 8 + 2 * t;
     const float b0 = bv ? bv[col] : 0.f, b1 = bv ? bv[col + 1] : 0.f;
-    if (m0 + g < R) *reinterpret_cast<uint32_t*>(o + (m0 + g) * ldo + col) = pack_bf16(c[nt][0] + b0, c[nt][1] + b1);
-    if (m0 + g + 8 < R)
-      *reinterpret_cast<uint32_t*>(o + (m0 + g + 8) * ldo + col) = pack_bf16(c[nt][2] + b0, c[nt][3] + b1);
+    float v0 = c[0][nt][0], v1 = c[0][nt][1], v2 = c[0][nt][2], v3 = c[0][nt][3];
+    if (SPLIT && second) {
+      v0 = wa0 * v0 + wa1 * c[NP - 1][nt][0];
+      v1 = wa0 * v1 + wa1 * c[NP - 1][nt][1];
+      v2 = wb0 * v2 + wb1 * c[NP - 1][nt][2];
+      v3 = wb0 * v3 + wb1 * c[NP - 1][nt][3];
+    }
+    if (m0 + g < R) *reinterpret_cast<uint32_t*>(o + (m0 + g) * ldo + col) = pack_bf16(v0 + b0, v1 + b1);
+    if (m0 + g + 8 < R) *reinterpret_cast<uint32_t*>(o + (m0 + g + 8) * ldo + col) = pack_bf16(v2 + b0, v3 + b1);
   }
 }
 
-int latent_value(const void* ctx, const void* wv, long long ldw, const float* bv, void* o, long long ldo, int R, int H,
-                 cudaStream_t stream) {
+int latent_value(const void* ctx, long long part_stride, const float* ml, const void* wv, long long ldw, const float* bv,
+                 void* o, long long ldo, int R, int H, cudaStream_t stream) {
   const int d = H * 64;
   WF_REQUIRE(ldw % 8 == 0 && ldo % 2 == 0 && (reinterpret_cast<uintptr_t>(ctx) & 15) == 0 &&
-                 (reinterpret_cast<uintptr_t>(wv) & 15) == 0 && (reinterpret_cast<uintptr_t>(o) & 3) == 0,
+                 (reinterpret_cast<uintptr_t>(wv) & 15) == 0 && (reinterpret_cast<uintptr_t>(o) & 3) == 0 &&
+                 part_stride % 8 == 0,
              "latent value: operands must be 16-byte aligned");
+  WF_REQUIRE(H <= 32, "latent value: at most 32 heads");
   dim3 grid(H, (R + 15) / 16);
-  WF_CHECK_CUDA(launch_pdl(0, latent_value_kernel, grid, dim3(128), 0, stream,
-                           reinterpret_cast<const __nv_bfloat16*>(ctx), reinterpret_cast<const __nv_bfloat16*>(wv), ldw,
-                           bv, reinterpret_cast<__nv_bfloat16*>(o), ldo, R, H, d));
+  if (ml != nullptr) {
+    WF_CHECK_CUDA(launch_pdl(0, latent_value_kernel<true>, grid, dim3(128), 0, stream,
+                             reinterpret_cast<const __nv_bfloat16*>(ctx), part_stride,
+                             reinterpret_cast<const float2*>(ml), reinterpret_cast<const __nv_bfloat16*>(wv), ldw, bv,
+                             reinterpret_cast<__nv_bfloat16*>(o), ldo, R, H, d));
+  } else {
+    WF_CHECK_CUDA(launch_pdl(0, latent_value_kernel<false>, grid, dim3(128), 0, stream,
+                             reinterpret_cast<const __nv_bfloat16*>(ctx), 0LL, static_cast<const float2*>(nullptr),
+                             reinterpret_cast<const __nv_bfloat16*>(wv), ldw, bv, reinterpret_cast<__nv_bfloat16*>(o),
+                             ldo, R, H, d));
+  }
   count_launch();
   return WF_OK;
 }

@@ -257,6 +257,7 @@ class _BlockFold:
     cross_q: Optional[_LnLinear]
     mlp1: _LnLinear
     cross_wk_t: Optional[Tensor] = None   # [d, d] = key.weight^T of the cross-attention (latent path, built on demand)
+    x_wk_t: Optional[List[Tensor]] = None  # the same for every gated x-attention sub-block
 
 
 def _fold_block(blk, bp: _BlockPack, dt) -> _BlockFold:
@@ -278,7 +279,7 @@ def latent_cross_enabled(rows: int, n_group: int, n_head: int, d: int) -> bool:
     HBM: it wins once the batch fills the GPU (measured on B200, large-v2: 138 vs 164 us per layer at 128 clips,
     slower at 64).  WF_LATENT=1 / 0 forces it on / off."""
     env = os.environ.get("WF_LATENT", "")
-    ok = n_group == 1 and n_head <= 32 and d == 64 * n_head and d % 128 == 0
+    ok = n_group == 1 and n_head <= 24 and d == 64 * n_head and d % 128 == 0
     if env in ("0", "1"):
         return ok and env == "1"
     return ok and rows >= 112
@@ -576,18 +577,31 @@ class DecodeSession:
         L = len(p.blocks)
         # ---- per-clip K/V caches (head-major) and step buffers; contents are (re)filled by load()
         self.latent = self.fold is not None and latent_cross_enabled(R, G, H, d)
+        # the gated x-attention takes the same route (its source rows = the prepared features, shared by all layers):
+        # no x-attn K/V arena and no per-layer K/V projection pass at load().  WF_LATENT_X=0 keeps the cached kernel.
+        self.latent_x = self.latent and self.gated and os.environ.get("WF_LATENT_X", "1") != "0"
         if self.latent:
             # no cross-attention K/V arena at all: every layer attends over the same bf16 encoder rows
             self.cross_kv = []
             self.xa_src = torch.empty((B, Ta, d), dtype=dt, device=dev)
             self.qp = torch.empty((R, H, d), dtype=dt, device=dev)
-            self.ctx = torch.empty((R, H, d), dtype=dt, device=dev)
+            # full batches run the persistent one-pass kernel, which leaves a clip cut at a cluster border as two
+            # partial contexts + their softmax statistics (csrc/latent_pair.cu); latent_value blends them
+            self.split = nv.latent_split_supported(H)
+            self.ctx = torch.zeros((2 if self.split else 1, R, H, d), dtype=dt, device=dev)
+            self.ctx_ml = torch.zeros((2, R, 32, 2), dtype=torch.float32, device=dev) if self.split else None
             for bp, bf in zip(p.blocks, self.fold):
                 if bf.cross_wk_t is None:
                     bf.cross_wk_t = bp.cross.qkv_w[d:2 * d].t().contiguous()
+                if self.latent_x and bf.x_wk_t is None:
+                    bf.x_wk_t = [xp.qkv_w[d:2 * d].t().contiguous() for xp in bp.x_attn]
         else:
             self.cross_kv = [torch.empty((B, 2 * H, Ta, 64), dtype=dt, device=dev) for _ in range(L)]
-        self.x_kv = [[torch.empty((B, 2 * H, tx, 64), dtype=dt, device=dev) for tx in self.Tx] for _ in range(L)]
+        if self.latent_x:
+            self.x_kv = [[] for _ in range(L)]
+            self.x_src = [torch.empty((B, tx, d), dtype=dt, device=dev) for tx in self.Tx]
+        else:
+            self.x_kv = [[torch.empty((B, 2 * H, tx, 64), dtype=dt, device=dev) for tx in self.Tx] for _ in range(L)]
         self.self_kv = [torch.zeros((R, 2 * H, t_cap, 64), dtype=dt, device=dev) for _ in range(L)]
         self.gemm_ws = torch.zeros(4096 + 8 * 1024 * 1024, dtype=torch.uint8, device=dev)  # split-K counters + partials
         self.x = _empty(R, d, dt, dev)
@@ -633,13 +647,19 @@ class DecodeSession:
         fprep = [prepare_features(p, f, dt) for f in feats]
         if self.latent:
             self.xa_src.view(-1, p.d).copy_(xa2)
+        if self.latent_x:
+            for i, f in enumerate(fprep):
+                self.x_src[i].view(-1, p.d).copy_(f)
+        if self.latent and self.latent_x:
+            return
         for l, bp in enumerate(p.blocks):
             if not self.latent:
                 nv.linear(xa2, bp.cross.kv_w, self.cross_kv[l].view(-1, 64), bias=bp.cross.kv_b,
                           head_major=(2 * H, self.Ta, self.Ta))
-            for i, f in enumerate(fprep):
-                nv.linear(f, bp.x_attn[i].kv_w, self.x_kv[l][i].view(-1, 64), bias=bp.x_attn[i].kv_b,
-                          head_major=(2 * H, self.Tx[i], self.Tx[i]))
+            if not self.latent_x:
+                for i, f in enumerate(fprep):
+                    nv.linear(f, bp.x_attn[i].kv_w, self.x_kv[l][i].view(-1, 64), bias=bp.x_attn[i].kv_b,
+                              head_major=(2 * H, self.Tx[i], self.Tx[i]))
 
     # -- one decoder pass for the token at position state[0]; logits of that position land in self.logits
     def _forward_token(self):
@@ -700,18 +720,33 @@ class DecodeSession:
         def lnlin(f: _LnLinear, out, **kw):
             nv.linear(x, f.w, out, bias=f.bias, ln_colsum=f.colsum, ln_eps=f.eps, **kw)
 
+        d = p.d
+
+        def latent_attend(src, wk_t, mp: _MhaPack):
+            # q' = Wk_h^T q_h -> softmax(src q' / 8)^T src -> Wv_h c_h + bv_h: the step streams src once for all heads
+            nv.latent_query(q, wk_t, self.qp, H)
+            if self.split:
+                nv.latent_attention(self.qp, src, self.ctx, H, ml=self.ctx_ml)
+                nv.latent_value(self.ctx, mp.qkv_w[2 * d:], mp.qkv_b[2 * d:], att, H, ml=self.ctx_ml)
+            else:
+                nv.latent_attention(self.qp, src, self.ctx[0], H)
+                nv.latent_value(self.ctx[0], mp.qkv_w[2 * d:], mp.qkv_b[2 * d:], att, H)
+
         for l, (bp, bf) in enumerate(zip(p.blocks, self.fold)):
             if self.gated:
-                multi = len(self.x_kv[l]) > 1
+                multi = len(self.Tx) > 1
                 acc = x
                 if multi:
                     self.acc.copy_(x)
                     acc = self.acc
-                for i, kvx in enumerate(self.x_kv[l]):
-                    Tx = self.Tx[i]
+                for i, Tx in enumerate(self.Tx):
                     lnlin(bf.x_q[i], q)
-                    nv.attention_decode(q, kvx, kvx[:, H:], 64, 2 * H * Tx * 64, Tx * 64, att, G, H, None, 0, Tx,
-                                        self.ws)
+                    if self.latent_x:
+                        latent_attend(self.x_src[i], bf.x_wk_t[i], bp.x_attn[i])
+                    else:
+                        kvx = self.x_kv[l][i]
+                        nv.attention_decode(q, kvx, kvx[:, H:], 64, 2 * H * Tx * 64, Tx * 64, att, G, H, None, 0, Tx,
+                                            self.ws)
                     nv.linear(att, bp.x_attn[i].o_w, acc, bias=bp.x_attn[i].o_b, residual=acc, gate=bp.x_gate[i])
                 if multi:
                     x.copy_(acc)
@@ -726,11 +761,7 @@ class DecodeSession:
             nv.linear(att, bp.attn.o_w, x, bias=bp.attn.o_b, residual=x)
             lnlin(bf.cross_q, q)
             if self.latent:
-                # q' = Wk_h^T q_h -> softmax(xa q' / 8)^T xa -> Wv_h c_h + bv_h: the step streams xa once for all heads
-                d = p.d
-                nv.latent_query(q, bf.cross_wk_t, self.qp, H)
-                nv.latent_attention(self.qp, self.xa_src, self.ctx, H)
-                nv.latent_value(self.ctx, bp.cross.qkv_w[2 * d:], bp.cross.qkv_b[2 * d:], att, H)
+                latent_attend(self.xa_src, bf.cross_wk_t, bp.cross)
             else:
                 ckv = self.cross_kv[l]
                 nv.attention_decode(q, ckv, ckv[:, H:], 64, 2 * H * self.Ta * 64, self.Ta * 64, att, G, H, None, 0,
@@ -981,8 +1012,9 @@ def get_session(dec, xa: Tensor, feats: Optional[Sequence[Tensor]], n_group: int
         key = (dt, xa.device, xa.shape[0], n_group, t_cap, xa.shape[1], tx, id(p))
         if n_split > 1:
             key = key + (n_split,)
-        same_path = (not isinstance(old, DecodeSession) or old.latent ==
-                     (old.fold is not None and latent_cross_enabled(old.R, old.G, p.n_head, p.d)))
+        same_path = (not isinstance(old, DecodeSession) or (
+            old.latent == (old.fold is not None and latent_cross_enabled(old.R, old.G, p.n_head, p.d)) and
+            old.latent_x == (old.latent and old.gated and os.environ.get("WF_LATENT_X", "1") != "0")))
         if old.shape_key() == key and (not old.gated or n_feats == len(old.Tx)) and same_path:
             old.load(xa, old._check_feats(feats))
             return old

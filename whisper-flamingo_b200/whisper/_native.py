@@ -84,6 +84,11 @@ _SIGNATURES = {
     "wf_latent_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "wf_latent_value": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_longlong,
                                   C.c_int, C.c_int, C.c_void_p]),
+    "wf_latent_split_supported": (C.c_int, [C.c_int]),
+    "wf_latent_attention_split": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_int,
+                                           C.c_int, C.c_void_p]),
+    "wf_latent_value_split": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p,
+                                       C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
     "wf_sample_greedy": (C.c_int, [C.POINTER(_Sample), C.c_void_p]),
     "wf_step_advance": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "wf_topk_logprobs": (C.c_int, [C.POINTER(_Topk), C.c_void_p]),
@@ -362,26 +367,49 @@ def latent_query(q: torch.Tensor, wk_t: torch.Tensor, qp: torch.Tensor, h: int) 
     return qp
 
 
-def latent_attention(qp: torch.Tensor, src: torch.Tensor, ctx: torch.Tensor, h: int) -> torch.Tensor:
-    """ctx[b, h, :] = softmax(src[b] qp[b, h, :] / 8)^T src[b]; src [B, T, d] contiguous bf16, qp / ctx [B, H, d]."""
+def latent_split_supported(h: int) -> bool:
+    """True when the one-pass pair kernel (csrc/latent_pair.cu) serves n_state = 64 h: the split form below exists."""
+    return bool(load().wf_latent_split_supported(int(h)))
+
+
+def latent_attention(qp: torch.Tensor, src: torch.Tensor, ctx: torch.Tensor, h: int,
+                     ml: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """ctx[b, h, :] = softmax(src[b] qp[b, h, :] / 8)^T src[b]; src [B, T, d] contiguous bf16, qp / ctx [B, H, d].
+    With ``ml`` (fp32 [2, B, 32, 2]) the split form: ctx is [2, B, H, d], two separately normalised partial contexts per
+    clip (the persistent kernel cuts a clip where a cluster's tile range ends) and ml their (reference maximum in log2
+    units, row sum) per head; ``latent_value(..., ml=ml)`` blends them."""
     b, t, d = src.shape
     assert src.dtype == qp.dtype == ctx.dtype == torch.bfloat16 and d == 64 * h
-    assert src.is_contiguous() and qp.is_contiguous() and ctx.is_contiguous() and qp.numel() == ctx.numel() == b * d * h
+    assert src.is_contiguous() and qp.is_contiguous() and ctx.is_contiguous() and qp.numel() == b * d * h
     # algorithmic bytes: every source row once for all heads
     with _Prof("latent_attention", bytes=2 * b * t * d):
-        _check(load().wf_latent_attention(qp.data_ptr(), src.data_ptr(), ctx.data_ptr(), b, t, h, _stream()))
+        if ml is None:
+            assert ctx.numel() == b * d * h
+            _check(load().wf_latent_attention(qp.data_ptr(), src.data_ptr(), ctx.data_ptr(), b, t, h, _stream()))
+        else:
+            assert ctx.numel() == 2 * b * d * h and ml.dtype == torch.float32 and ml.is_contiguous()
+            assert ml.numel() == 2 * b * 32 * 2
+            _check(load().wf_latent_attention_split(qp.data_ptr(), src.data_ptr(), ctx.data_ptr(), b * d * h,
+                                                    ml.data_ptr(), b, t, h, _stream()))
     return ctx
 
 
 def latent_value(ctx: torch.Tensor, wv: torch.Tensor, bv: Optional[torch.Tensor], out: torch.Tensor,
-                 h: int) -> torch.Tensor:
-    """out[r, 64h:64h+64] = Wv_h ctx[r, h, :] + bv_h; wv = value.weight ([d, d] rows, bf16), bv fp32 [d] or None."""
+                 h: int, ml: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[r, 64h:64h+64] = Wv_h ctx[r, h, :] + bv_h; wv = value.weight ([d, d] rows, bf16), bv fp32 [d] or None.
+    With ``ml``: ctx [2, R, H, d] / ml [2, R, 32, 2] as left by ``latent_attention(..., ml=ml)``."""
     r, d = out.shape[0], h * 64
-    assert ctx.dtype == wv.dtype == out.dtype == torch.bfloat16 and ctx.is_contiguous() and ctx.numel() == r * h * d
+    assert ctx.dtype == wv.dtype == out.dtype == torch.bfloat16 and ctx.is_contiguous()
     assert bv is None or bv.dtype == torch.float32
     with _Prof("latent_value", bytes=2 * (d * d + r * d + r * h * d)):
-        _check(load().wf_latent_value(ctx.data_ptr(), wv.data_ptr(), _row_stride(wv), _ptr(bv), out.data_ptr(),
-                                      _row_stride(out), r, h, _stream()))
+        if ml is None:
+            assert ctx.numel() == r * h * d
+            _check(load().wf_latent_value(ctx.data_ptr(), wv.data_ptr(), _row_stride(wv), _ptr(bv), out.data_ptr(),
+                                          _row_stride(out), r, h, _stream()))
+        else:
+            assert ctx.numel() == 2 * r * h * d and ml.dtype == torch.float32 and ml.numel() == 2 * r * 32 * 2
+            _check(load().wf_latent_value_split(ctx.data_ptr(), r * h * d, ml.data_ptr(), wv.data_ptr(), _row_stride(wv),
+                                                _ptr(bv), out.data_ptr(), _row_stride(out), r, h, _stream()))
     return out
 
 
