@@ -550,15 +550,26 @@ latent_query_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const __
   __shared__ __align__(16) __nv_bfloat16 Bs[128 * LQ_LD];
   const int n0 = blockIdx.x * 128, h = blockIdx.y, m0 = blockIdx.z * 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // (no early launch of the dependents here: measured, the 148 attention CTAs then take the SMs the second wave of
+  // this kernel's 200 CTAs needs and the pair costs 6 us more)
+  // the weight tile does not depend on the previous kernel: its HBM round trip runs under the dependency wait
+  uint4 w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int v = threadIdx.x + i * 256;
+    const int row = v >> 3, c8 = (v & 7) * 8;
+    w[i] = make_uint4(0, 0, 0, 0);
+    if (n0 + row < d) w[i] = *reinterpret_cast<const uint4*>(wkT + static_cast<long long>(n0 + row) * d + h * 64 + c8);
+  }
   pdl_wait();
-  for (int v = threadIdx.x; v < 128 * 8; v += 256) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int v = threadIdx.x + i * 256;
     const int row = v >> 3, c8 = (v & 7) * 8;
     uint4 a = make_uint4(0, 0, 0, 0);
     if (m0 + row < R) a = *reinterpret_cast<const uint4*>(q + (m0 + row) * ldq + h * 64 + c8);
     *reinterpret_cast<uint4*>(&As[row * LQ_LD + c8]) = a;
-    uint4 w = make_uint4(0, 0, 0, 0);
-    if (n0 + row < d) w = *reinterpret_cast<const uint4*>(wkT + static_cast<long long>(n0 + row) * d + h * 64 + c8);
-    *reinterpret_cast<uint4*>(&Bs[row * LQ_LD + c8]) = w;
+    *reinterpret_cast<uint4*>(&Bs[row * LQ_LD + c8]) = w[i];
   }
   __syncthreads();
   uint32_t af[4][4];
