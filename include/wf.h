@@ -209,6 +209,42 @@ typedef struct {
   int* out_idx;    /* [R, k] */
 } wf_topk_t;
 int wf_topk_logprobs(const wf_topk_t* args, wf_stream_t stream);
+/* One beam-search step on the device: whisper/decoding.py:337-386 (BeamSearchDecoder.update) + :173-180
+ * (rearrange_kv_cache, as a per-position row table) for ALL audios of the batch, graph-replayable - the position, the
+ * prompt length and the SOT index are read from `state`, nothing happens while the prompt is fed (except
+ * no_speech_prob at the SOT position), and state[3] counts the audios that hold max_candidates finished sequences
+ * (wf_step_advance(state, n_audio) then raises state[2]).  Top-(G + 1) of log_softmax(filtered logits) per hypothesis,
+ * candidate merge per audio in descending cumulative log-probability with the reference's dictionary semantics
+ * (identical hypotheses - equal hyp_id - collapse), EOT continuations -> finished lists, the first G others -> the next
+ * hypotheses: tokens / row_table rows permuted and extended in place, sum_logprobs updated. */
+typedef struct {
+  const float* logits; /* [R, ld] */
+  long long ld;
+  int R, V, G;         /* R = n_audio * G */
+  const uint8_t* suppress;
+  const uint8_t* suppress_first;
+  int* tokens;     /* [R, T_cap] */
+  int* tokens_tmp; /* [R, T_cap] scratch */
+  int T_cap;
+  int* state;
+  int eot, no_speech; /* no_speech: id or -1 */
+  int timestamp_begin, no_timestamps, max_initial_ts;
+  int max_candidates;     /* round(beam_size * patience), 1 .. 32 */
+  float* sum_logprobs;    /* [R] */
+  float* sum_scratch;     /* [R] */
+  float* no_speech_prob;  /* [R] */
+  int* hyp_id;            /* [R]: equal ids <=> equal token sequences; start with the audio index */
+  int* row_table;         /* [R, table_ld] or NULL */
+  int* table_tmp;         /* [R, table_ld] scratch (NULL with row_table) */
+  int table_ld;
+  float* top_vals;        /* [R, G + 1] scratch */
+  int* top_idx;           /* [R, G + 1] scratch */
+  int* fin_tokens;        /* [n_audio, max_candidates, T_cap] */
+  float* fin_score;       /* [n_audio, max_candidates] */
+  int* fin_len;           /* [n_audio, max_candidates] */
+  int* n_fin;             /* [n_audio], zeroed by the caller before the first step */
+} wf_beam_t;
+int wf_beam_step(const wf_beam_t* args, wf_stream_t stream);
 /* dst row r = src row src_index[r] (first used_bytes of row_bytes): decoding.py:173-180 (rearrange_kv_cache) */
 int wf_kv_gather_rows(const void* src, void* dst, const int* src_index, int R, long long row_bytes,
                       long long used_bytes, wf_stream_t stream);

@@ -147,6 +147,34 @@ def test_beam_search_fp32_identical_and_batched(a_model, mel2):
     assert both[1].tokens == whisper.decode(a_model, mel2[1], opt).tokens
 
 
+@pytest.mark.parametrize("opts", [dict(beam_size=5), dict(beam_size=3, patience=2.0), dict(beam_size=4, patience=0.5),
+                                  dict(beam_size=2, without_timestamps=False), dict(beam_size=7, length_penalty=0.6)])
+def test_device_beam_search_equals_host_bookkeeping(av_model, opts, monkeypatch):
+    """The beam-search step on the device (top-(G + 1), candidate merge with the reference's dictionary semantics,
+    finished lists, history / cache-table permutation, completion flag: csrc/decode.cu beam_update_kernel) against the
+    round-1 host bookkeeping (_BeamBook, pinned to the reference by the golden beam tokens): same candidates in the
+    same order, so the same tokens, log-probabilities and no_speech_prob - over a batch, with patience above and
+    below one, timestamp rules and a length penalty; EOT is reachable, so hypotheses do finish."""
+    import whisper
+    from whisper import _engine
+    mel = torch.stack([whisper.log_mel_spectrogram(p.cuda()) for p in _pcm(3)])
+    feat = _feat(3).cuda()
+    kw = dict(language="en", without_timestamps=True, sample_len=10, fp16=False)
+    kw.update(opts)
+    opt = whisper.DecodingOptions(**kw)
+    _engine.clear_sessions()
+    dev = whisper.decode(av_model, mel, opt, x_v=feat)
+    monkeypatch.setenv("WF_BEAM_HOST", "1")
+    _engine.clear_sessions()
+    host = whisper.decode(av_model, mel, opt, x_v=feat)
+    for d, h in zip(dev, host):
+        assert d.tokens == h.tokens
+        assert abs(d.avg_logprob - h.avg_logprob) < 1e-6 and abs(d.no_speech_prob - h.no_speech_prob) < 1e-7
+    monkeypatch.delenv("WF_BEAM_HOST")
+    again = whisper.decode(av_model, mel, opt, x_v=feat)      # the captured beam graph is replayed
+    assert [r.tokens for r in again] == [r.tokens for r in dev]
+
+
 def test_kv_cached_decode_equals_oracle_no_cache_loop_av(av_model, mel2):
     """The cached engine against the oracle's full-recompute loop on a case that is NOT in the golden file."""
     import whisper
@@ -173,6 +201,55 @@ def test_bf16_greedy_decode_runs_and_agrees_mostly(av_model, mel2):
     assert all(r.tokens[0] == g[0] for r, g in zip(res, gold["tokens"])) and min(agree) >= 0.5, agree
     for r, lp in zip(res, gold["avg_logprob"]):
         assert abs(r.avg_logprob - lp) < 0.15
+
+
+@pytest.mark.parametrize("condition", [False, True])
+def test_transcribe_batch_equals_one_recording_at_a_time(a_model, condition):
+    """SURVEY 8f rank 1, the B200 part: the current window of many recordings is decoded as one batch per round.
+    Every recording must come out exactly as ``transcribe`` returns it alone (fp32 engine: same tokens, same seeks,
+    same segment times) - with and without conditioning on the previous text (windows are grouped by prompt length),
+    for recordings of different lengths (the batch shrinks as they end)."""
+    import whisper
+    from whisper._synthetic import synthetic_pcm
+    secs = (75, 31, 52, 8)
+    pcms = [synthetic_pcm(1, n_samples=s * 16000, seed=100 + i)[0].numpy() for i, s in enumerate(secs)]
+    kw = dict(temperature=0.0, compression_ratio_threshold=None, logprob_threshold=None, no_speech_threshold=None,
+              language="en", fp16=False, sample_len=12, verbose=None, condition_on_previous_text=condition)
+    alone = [whisper.transcribe(a_model, p, **kw) for p in pcms]
+    together = whisper.transcribe_batch(a_model, pcms, **kw)
+    assert len(together) == len(alone)
+    for got, want in zip(together, alone):
+        assert got["text"] == want["text"] and got["language"] == want["language"]
+        assert len(got["segments"]) == len(want["segments"]) > 0
+        for s, g in zip(got["segments"], want["segments"]):
+            assert (s["id"], s["seek"], s["tokens"]) == (g["id"], g["seek"], g["tokens"])
+            assert s["start"] == g["start"] and s["end"] == g["end"]
+            assert abs(s["avg_logprob"] - g["avg_logprob"]) < 1e-5
+
+
+def test_transcribe_reuses_sessions_across_windows(a_model):
+    """The token capacity of a decode session is bucketed (64) and a few sessions are kept per decoder: the windows of a
+    recording - whose prompt grows and shrinks - must not build a new session (K/V arena + CUDA graph) each."""
+    import whisper
+    from whisper import _engine
+    from whisper._synthetic import synthetic_pcm
+    pcm = synthetic_pcm(1, n_samples=150 * 16000, seed=7)[0].numpy()
+    built = []
+    orig = _engine.DecodeSession.__init__
+
+    def counting(self, *a, **k):
+        built.append(1)
+        return orig(self, *a, **k)
+
+    _engine.clear_sessions()
+    _engine.DecodeSession.__init__ = counting
+    try:
+        out = whisper.transcribe(a_model, pcm, temperature=0.0, compression_ratio_threshold=None, logprob_threshold=None,
+                                 no_speech_threshold=None, language="en", fp16=False, sample_len=12, verbose=None)
+    finally:
+        _engine.DecodeSession.__init__ = orig
+    assert len({s["seek"] for s in out["segments"]}) >= 4, "several windows were decoded"
+    assert len(built) <= 2, f"{len(built)} sessions built for one recording"
 
 
 def test_transcribe_long_form_matches_reference_golden(a_model):
@@ -337,7 +414,7 @@ def test_bf16_greedy_decode_latent_cross_attention(av_model, mel2, monkeypatch):
     base = whisper.decode(av_model, mel2, opt, x_v=feat)
     monkeypatch.setenv("WF_LATENT", "1")
     res = whisper.decode(av_model, mel2, opt, x_v=feat)
-    sess = _engine._SESSION_CACHE.get(av_model.decoder)
+    sess = _engine.last_session(av_model.decoder)
     assert sess is not None and sess.latent
     agree = [sum(a == b for a, b in zip(r.tokens, g)) / len(g) for r, g in zip(res, gold["tokens"])]
     assert all(r.tokens[0] == g[0] for r, g in zip(res, gold["tokens"])) and min(agree) >= 0.5, agree

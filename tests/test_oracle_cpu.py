@@ -356,3 +356,46 @@ def test_latent_path_gate(monkeypatch):
     assert on(2, 1, 6, 384) and not on(2, 5, 6, 384)
     monkeypatch.setenv("WF_LATENT", "0")
     assert not on(128, 1, 20, 1280)
+
+
+# ----------------------------------------------------------------------------- load_audio (reference audio.py:26-63)
+def test_load_audio_reads_wave_files_without_ffmpeg(tmp_path, monkeypatch):
+    """Hosts without ffmpeg (this image) read RIFF/WAVE natively: 16-bit PCM at 16 kHz is exactly what the reference's
+    ffmpeg command would emit (int16 / 32768); other rates go through the windowed-sinc resampler, checked against the
+    analytic signal; stereo is down-mixed; a non-WAVE file is refused with the reference's error type."""
+    import struct
+    import whisper
+    from whisper.audio import load_audio
+    import shutil
+    if shutil.which("ffmpeg"):
+        monkeypatch.setenv("PATH", "")           # exercise the fall-back everywhere
+
+    def write_wav(path, x, rate, channels=1, bits=16):
+        if bits == 16:
+            data = (np.clip(x, -1, 1) * 32767).astype("<i2").tobytes()
+        else:
+            data = x.astype("<f4").tobytes()
+        fmt = struct.pack("<HHIIHH", 1 if bits == 16 else 3, channels, rate, rate * channels * bits // 8,
+                          channels * bits // 8, bits)
+        with open(path, "wb") as fh:
+            fh.write(b"RIFF" + struct.pack("<I", 36 + len(data)) + b"WAVE" + b"fmt " + struct.pack("<I", 16) + fmt)
+            fh.write(b"LIST" + struct.pack("<I", 4) + b"abcd")            # an extra chunk to skip
+            fh.write(b"data" + struct.pack("<I", len(data)) + data)
+
+    t = np.arange(16000) / 16000.0
+    x = 0.5 * np.sin(2 * np.pi * 440 * t)
+    write_wav(tmp_path / "a.wav", x, 16000)
+    got = load_audio(str(tmp_path / "a.wav"))
+    assert got.dtype == np.float32 and got.shape == (16000,)
+    assert np.array_equal(got, (x * 32767).astype("<i2").astype(np.float32) / 32768.0)
+    # 44.1 kHz stereo float -> 16 kHz mono
+    t2 = np.arange(44100) / 44100.0
+    st = np.stack([0.5 * np.sin(2 * np.pi * 440 * t2), 0.5 * np.sin(2 * np.pi * 440 * t2)], axis=1).reshape(-1)
+    write_wav(tmp_path / "b.wav", st, 44100, channels=2, bits=32)
+    got = load_audio(str(tmp_path / "b.wav"))
+    assert got.shape == (16000,)
+    assert np.abs(got[200:-200] - x[200:-200]).max() < 2e-3
+    assert whisper.load_audio is load_audio
+    (tmp_path / "c.bin").write_bytes(b"not audio at all")
+    with pytest.raises(RuntimeError, match="Failed to load audio"):
+        load_audio(str(tmp_path / "c.bin"))

@@ -78,7 +78,7 @@ def test_medium_beam5_more_than_128_rows_fp32_tokens_identical_to_oracle(medium_
     opt = whisper.DecodingOptions(language="en", without_timestamps=True, sample_len=5, beam_size=5, fp16=False)
     _engine.clear_sessions()
     res = whisper.decode(model, mel, opt, x_v=feat.cuda())
-    sess = _engine._SESSION_CACHE.get(model.decoder)
+    sess = _engine.last_session(model.decoder)
     assert sess.R == 130 and sess.fold is None and sess.row_table is not None
     spec = _spec(DecodingTask(model, opt), opt, 768)
     sd, od = oracle_sd(model), om.Dims(**MEDIUM2)

@@ -217,6 +217,23 @@ int wf_topk_logprobs(const wf_topk_t* a, wf_stream_t stream) {
   t.max_initial_ts = a->max_initial_ts; t.k = a->k; t.out_vals = a->out_vals; t.out_idx = a->out_idx;
   return topk_logprobs(t, S(stream));
 }
+int wf_beam_step(const wf_beam_t* a, wf_stream_t stream) {
+  WF_REQUIRE(a != nullptr, "wf_beam_step: null args");
+  WF_REQUIRE(a->logits && a->suppress && a->top_vals && a->top_idx && a->state, "wf_beam_step: null buffer");
+  TopkArgs t;
+  t.logits = a->logits; t.ld = a->ld; t.R = a->R; t.V = a->V; t.suppress = a->suppress;
+  t.suppress_first = a->suppress_first; t.tokens = a->tokens; t.T_cap = a->T_cap; t.n_init = 0; t.cur_len = 0;
+  t.eot = a->eot; t.timestamp_begin = a->timestamp_begin; t.no_timestamps = a->no_timestamps;
+  t.max_initial_ts = a->max_initial_ts; t.k = a->G + 1; t.out_vals = a->top_vals; t.out_idx = a->top_idx;
+  t.state = a->state; t.no_speech_prob = a->no_speech_prob; t.no_speech = a->no_speech;
+  BeamArgs b;
+  b.R = a->R; b.G = a->G; b.max_candidates = a->max_candidates; b.eot = a->eot; b.vals = a->top_vals; b.idx = a->top_idx;
+  b.tokens = a->tokens; b.tokens_tmp = a->tokens_tmp; b.T_cap = a->T_cap; b.row_table = a->row_table;
+  b.table_tmp = a->table_tmp; b.table_ld = a->table_ld; b.sum_logprobs = a->sum_logprobs;
+  b.sum_logprobs_out = a->sum_scratch; b.hyp_id = a->hyp_id; b.state = a->state; b.fin_tokens = a->fin_tokens;
+  b.fin_score = a->fin_score; b.fin_len = a->fin_len; b.n_fin = a->n_fin;
+  return beam_step(t, b, S(stream));
+}
 int wf_kv_gather_rows(const void* src, void* dst, const int* src_index, int R, long long row_bytes,
                       long long used_bytes, wf_stream_t stream) {
   WF_REQUIRE(src && dst && src_index, "wf_kv_gather_rows: null buffer");

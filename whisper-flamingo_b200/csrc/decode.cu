@@ -1132,6 +1132,10 @@ __global__ void step_advance_kernel(int* state, int R) {
   pdl_trigger();
   pdl_wait();
   const int t = state[0], n_init = state[1];
+  if (state[2] != 0) {   // finished: steps replayed before the host has polled the flag change nothing
+    state[3] = 0;
+    return;
+  }
   if (t + 1 >= n_init && state[3] == R) state[2] = 1;
   state[3] = 0;
   state[0] = t + 1;
@@ -1149,6 +1153,25 @@ __global__ void __launch_bounds__(256) topk_logprobs_kernel(TopkArgs a) {
   __shared__ int picked[32];
   const int r = blockIdx.x;
   const float* lg = a.logits + r * a.ld;
+  if (a.state != nullptr) {
+    // graph-replayable form: the position lives in device memory (state[0] = position of the token fed this step)
+    if (a.state[2] != 0) return;   // search finished (the host polls the flag every few steps)
+    const int t = a.state[0], sot_index = a.state[4];
+    a.n_init = a.state[1];
+    a.cur_len = t + 1;
+    if (a.no_speech_prob != nullptr && a.no_speech >= 0 && t == sot_index) {
+      // no_speech_prob = softmax(raw logits at the SOT position)[no_speech]   (decoding.py:697-701)
+      ArgMax am{-INFINITY, 0x7fffffff};
+      for (int i = threadIdx.x; i < a.V; i += blockDim.x) am = better(am, ArgMax{lg[i], i});
+      am = block_argmax(am, sh_am);
+      float se = 0.f;
+      for (int i = threadIdx.x; i < a.V; i += blockDim.x) se += expf(lg[i] - am.v);
+      se = block_sum(se, sh_f);
+      if (threadIdx.x == 0) a.no_speech_prob[r] = expf(lg[a.no_speech] - am.v) / se;
+      __syncthreads();
+    }
+    if (t + 1 < a.n_init) return;  // still feeding the forced initial tokens
+  }
   RowMask m;
   if (a.tokens) {
     m = make_row_mask(a.tokens + static_cast<long long>(r) * a.T_cap, a.n_init, a.cur_len, a.V, a.eot,
@@ -1185,6 +1208,165 @@ int topk_logprobs(const TopkArgs& a, cudaStream_t stream) {
   WF_REQUIRE(a.R > 0 && a.V > 0 && a.k > 0 && a.k <= 32, "topk: bad arguments (k=%d)", a.k);
   WF_REQUIRE(a.logits && a.suppress && a.out_vals && a.out_idx, "topk: null buffer");
   topk_logprobs_kernel<<<a.R, 256, 0, stream>>>(a);
+  WF_CHECK_LAUNCH();
+  return WF_OK;
+}
+
+// One step of BeamSearchDecoder.update (decoding.py:337-386) on the device, one CTA per audio.
+// Candidates = the top-(G + 1) continuations of each of the G hypotheses; identical hypotheses (all beams share the
+// prompt at the first step; `hyp_id` equal <=> token sequences equal) collapse into one dictionary entry that keeps the
+// position of its first insertion and the value of its last, as the reference's tuple-keyed dict does; entries are
+// visited by descending cumulative log-probability (stable), EOT continuations go to the finished list (at most
+// max_candidates per audio), the first G others become the next hypotheses.  The token histories and the per-position
+// row table of the self-attention cache (decoding.py:173-180 rearrange_kv_cache) are permuted through scratch rows.
+static constexpr int BEAM_MAX_CAND = 32 * 33;
+__global__ void __launch_bounds__(128) beam_update_kernel(BeamArgs a) {
+  __shared__ float c_score[BEAM_MAX_CAND];
+  __shared__ int c_tok[BEAM_MAX_CAND];
+  __shared__ short c_src[BEAM_MAX_CAND];      // hypothesis (0 .. G-1) the candidate extends
+  __shared__ short c_order[BEAM_MAX_CAND];    // candidate index by rank (alive entries only)
+  __shared__ int keep[32], fin_src[32], fin_slot[32];
+  __shared__ float fin_sc[32];
+  __shared__ int n_alive, n_keep, n_done;
+  const int au = blockIdx.x, G = a.G, k = G + 1, n = G * k;
+  const int t = a.state[0], n_init = a.state[1];
+  if (t + 1 < n_init || a.state[2] != 0) return;   // feeding the forced initial tokens / search finished
+  const int L = t + 1;                        // tokens per hypothesis so far
+  const int row0 = au * G;
+  if (threadIdx.x == 0) { n_alive = 0; n_keep = 0; n_done = 0; }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int j = i / k, r = row0 + j;
+    c_score[i] = a.sum_logprobs[r] + a.vals[r * k + (i - j * k)];    // fp32 add, as the reference
+    c_tok[i] = a.idx[r * k + (i - j * k)];
+    c_src[i] = static_cast<short>(j);
+  }
+  __syncthreads();
+  // dictionary semantics: an entry lives at its first insertion and carries the value of its last
+  float my_score[(BEAM_MAX_CAND + 127) / 128];
+  short my_src[(BEAM_MAX_CAND + 127) / 128];
+  bool my_alive[(BEAM_MAX_CAND + 127) / 128];
+#pragma unroll 1
+  for (int q = 0, i = threadIdx.x; i < n; i += blockDim.x, ++q) {
+    const int hid = a.hyp_id[row0 + c_src[i]], tok = c_tok[i];
+    bool first = true;
+    int last = i;
+    for (int i2 = 0; i2 < n; ++i2)
+      if (i2 != i && c_tok[i2] == tok && a.hyp_id[row0 + c_src[i2]] == hid) {
+        if (i2 < i) first = false;
+        if (i2 > last) last = i2;
+      }
+    my_alive[q] = first;
+    my_score[q] = c_score[last];
+    my_src[q] = c_src[last];
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int q = 0, i = threadIdx.x; i < n; i += blockDim.x, ++q) {
+    c_score[i] = my_alive[q] ? my_score[q] : NAN;     // NaN marks a collapsed duplicate
+    c_src[i] = my_src[q];
+  }
+  __syncthreads();
+  // rank among the live entries: descending score, ties by insertion order (Python's sort is stable)
+#pragma unroll 1
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = c_score[i];
+    if (v != v) continue;
+    int rank = 0;
+    for (int i2 = 0; i2 < n; ++i2) {
+      const float w = c_score[i2];
+      if (w != w) continue;
+      if (w > v || (w == v && i2 < i)) ++rank;
+    }
+    c_order[rank] = static_cast<short>(i);
+    atomicAdd(&n_alive, 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int kept = 0, nd = 0, nf = a.n_fin[au];
+    for (int p = 0; p < n_alive && kept < G; ++p) {
+      const int i = c_order[p];
+      if (c_tok[i] == a.eot) {
+        if (nd < 32) { fin_src[nd] = i; ++nd; }
+      } else {
+        keep[kept++] = i;
+      }
+    }
+    // finished sequences of this step in the order visited (= descending score), while there is room (:374-378)
+    int nrec = 0;
+    for (int q = 0; q < nd && nf < a.max_candidates; ++q) {
+      const int i = fin_src[q];
+      fin_slot[nrec] = nf;
+      fin_sc[nrec] = c_score[i];
+      fin_src[nrec] = row0 + c_src[i];
+      ++nrec;
+      ++nf;
+    }
+    a.n_fin[au] = nf;
+    n_keep = kept;
+    n_done = nrec;
+    if (nf >= a.max_candidates) atomicAdd(&a.state[3], 1);
+  }
+  __syncthreads();
+  const long long ld = a.T_cap;
+  // finished: tokens of the parent + EOT
+  for (int q = 0; q < n_done; ++q) {
+    int* dst = a.fin_tokens + (static_cast<long long>(au) * a.max_candidates + fin_slot[q]) * ld;
+    const int* src = a.tokens + static_cast<long long>(fin_src[q]) * ld;
+    for (int p = threadIdx.x; p < L; p += blockDim.x) dst[p] = src[p];
+    if (threadIdx.x == 0) {
+      dst[L] = a.eot;
+      a.fin_score[au * a.max_candidates + fin_slot[q]] = fin_sc[q];
+      a.fin_len[au * a.max_candidates + fin_slot[q]] = L + 1;
+    }
+  }
+  // next hypotheses: row s continues hypothesis c_src[keep[s]] with token c_tok[keep[s]] (through scratch rows: the
+  // sources are rows of this audio, which this CTA is about to overwrite)
+  for (int s2 = 0; s2 < n_keep; ++s2) {
+    const int i = keep[s2];
+    const int* src = a.tokens + static_cast<long long>(row0 + c_src[i]) * ld;
+    int* dst = a.tokens_tmp + static_cast<long long>(row0 + s2) * ld;
+    for (int p = threadIdx.x; p < L; p += blockDim.x) dst[p] = src[p];
+    if (a.row_table != nullptr) {
+      const int* ts = a.row_table + static_cast<long long>(row0 + c_src[i]) * a.table_ld;
+      int* td = a.table_tmp + static_cast<long long>(row0 + s2) * a.table_ld;
+      for (int p = threadIdx.x; p < L && p < a.table_ld; p += blockDim.x) td[p] = ts[p];
+    }
+  }
+  __syncthreads();
+  for (int s2 = 0; s2 < n_keep; ++s2) {
+    const int i = keep[s2];
+    const int* src = a.tokens_tmp + static_cast<long long>(row0 + s2) * ld;
+    int* dst = a.tokens + static_cast<long long>(row0 + s2) * ld;
+    for (int p = threadIdx.x; p < L; p += blockDim.x) dst[p] = src[p];
+    if (a.row_table != nullptr) {
+      const int* ts = a.table_tmp + static_cast<long long>(row0 + s2) * a.table_ld;
+      int* td = a.row_table + static_cast<long long>(row0 + s2) * a.table_ld;
+      for (int p = threadIdx.x; p < L && p < a.table_ld; p += blockDim.x) td[p] = ts[p];
+    }
+    if (threadIdx.x == 0) {
+      dst[L] = c_tok[i];
+      a.sum_logprobs_out[row0 + s2] = c_score[i];
+    }
+  }
+  __syncthreads();
+  for (int s2 = threadIdx.x; s2 < G; s2 += blockDim.x) {
+    if (s2 < n_keep) a.sum_logprobs[row0 + s2] = a.sum_logprobs_out[row0 + s2];
+    else a.sum_logprobs[row0 + s2] = -INFINITY;     // fewer than G live continuations: the row is dead
+    a.hyp_id[row0 + s2] = a.R + row0 + s2;           // from now on every hypothesis is a distinct sequence
+  }
+}
+
+int beam_step(const TopkArgs& tk, const BeamArgs& b, cudaStream_t stream) {
+  WF_REQUIRE(b.G >= 1 && b.G <= 31 && b.R > 0 && b.R % b.G == 0, "beam step: beam size must be 1 .. 31 (got %d)", b.G);
+  WF_REQUIRE(b.max_candidates >= 1 && b.max_candidates <= 32, "beam step: 1 .. 32 finished candidates per audio");
+  WF_REQUIRE(b.tokens && b.tokens_tmp && b.state && b.sum_logprobs && b.sum_logprobs_out && b.hyp_id && b.vals && b.idx &&
+                 b.fin_tokens && b.fin_score && b.fin_len && b.n_fin && (b.row_table == nullptr || b.table_tmp != nullptr),
+             "beam step: null buffer");
+  WF_REQUIRE(tk.state == b.state && tk.k == b.G + 1 && tk.out_vals == b.vals && tk.out_idx == b.idx,
+             "beam step: the top-k pass must feed the update");
+  int rc = topk_logprobs(tk, stream);
+  if (rc) return rc;
+  beam_update_kernel<<<b.R / b.G, 128, 0, stream>>>(b);
   WF_CHECK_LAUNCH();
   return WF_OK;
 }

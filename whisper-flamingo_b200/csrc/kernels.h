@@ -126,8 +126,35 @@ struct TopkArgs {
   int k;
   float* out_vals;    // [R, k] log-probabilities
   int* out_idx;       // [R, k]
+  // graph-replayable form (optional): position / n_init / sot_index from the device state, no_speech_prob recorded at
+  // the SOT position, nothing else done while the prompt is being fed
+  const int* state = nullptr;
+  float* no_speech_prob = nullptr;
+  int no_speech = -1;
 };
 int topk_logprobs(const TopkArgs& a, cudaStream_t stream);
+struct BeamArgs {
+  int R, G;                 // rows = audios * G
+  int max_candidates;       // round(beam_size * patience)
+  int eot;
+  const float* vals;        // [R, G + 1] top log-probabilities of this step (TopkArgs.out_vals)
+  const int* idx;           // [R, G + 1]
+  int* tokens;              // [R, T_cap] token histories, permuted and extended in place
+  int* tokens_tmp;          // [R, T_cap] scratch
+  int T_cap;
+  int* row_table;           // [R, table_ld] physical row of every cached self-attention position, or null
+  int* table_tmp;
+  int table_ld;
+  float* sum_logprobs;      // [R] cumulative log-probabilities
+  float* sum_logprobs_out;  // [R] scratch
+  int* hyp_id;              // [R] equal ids <=> equal token sequences (all beams of an audio start equal)
+  int* state;               // [0] position, [1] n_init, [3] += audios with max_candidates finished sequences
+  int* fin_tokens;          // [audios, max_candidates, T_cap]
+  float* fin_score;         // [audios, max_candidates]
+  int* fin_len;             // [audios, max_candidates]
+  int* n_fin;               // [audios]
+};
+int beam_step(const TopkArgs& tk, const BeamArgs& b, cudaStream_t stream);
 int kv_gather_rows(const void* src, void* dst, const int* src_index, int R, long long row_bytes, long long used_bytes,
                    cudaStream_t stream);
 // test hook: out_min_max[0..1] (device) = min / max of n draws of the sampling RNG's uniform

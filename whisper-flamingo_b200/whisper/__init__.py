@@ -17,7 +17,7 @@ import torch
 from .audio import load_audio, log_mel_spectrogram, pad_or_trim
 from .decoding import DecodingOptions, DecodingResult, decode, detect_language
 from .model import ModelDimensions, Whisper
-from .transcribe import transcribe
+from .transcribe import transcribe, transcribe_batch
 from .version import __version__
 
 # official checkpoint names (weights must already be on disk: this build never downloads)

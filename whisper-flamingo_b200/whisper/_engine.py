@@ -861,7 +861,80 @@ class DecodeSession:
                     break
         return launches
 
-    # -- beam search support (host-driven; see decoding.py) ---------------------------------------------
+    # -- beam search on the device ------------------------------------------------------------------------
+    def configure_beam(self, max_candidates: int):
+        """Buffers of the device-side beam search (after configure_greedy, which sets prompt / masks / state)."""
+        R, B, dev = self.R, self.B, self.dev
+        ld = self.tokens.shape[1]
+        if getattr(self, "_beam_cap", None) != (max_candidates, ld):
+            self._beam_cap = (max_candidates, ld)
+            self.tokens_tmp = torch.zeros_like(self.tokens)
+            self.table_tmp = torch.zeros_like(self.row_table) if self.row_table is not None else None
+            self.sum_tmp = torch.zeros(R, dtype=torch.float32, device=dev)
+            self.hyp_id = torch.zeros(R, dtype=torch.int32, device=dev)
+            self.top_vals = torch.empty((R, self.G + 1), dtype=torch.float32, device=dev)
+            self.top_idx = torch.empty((R, self.G + 1), dtype=torch.int32, device=dev)
+            self.fin_tokens = torch.zeros((B, max_candidates, ld), dtype=torch.int32, device=dev)
+            self.fin_score = torch.zeros((B, max_candidates), dtype=torch.float32, device=dev)
+            self.fin_len = torch.zeros((B, max_candidates), dtype=torch.int32, device=dev)
+            self.n_fin = torch.zeros(B, dtype=torch.int32, device=dev)
+            self._beam_graph = None
+        # all hypotheses of an audio start as the same sequence: equal ids
+        self.hyp_id.copy_(torch.arange(R, dtype=torch.int32, device=dev) // self.G)
+        self.n_fin.zero_()
+        key = (self._sampler[1] is not None,) + tuple(self._sampler[2:5]) + (max_candidates,)
+        if key != getattr(self, "_beam_key", None):
+            self._beam_key, self._beam_graph = key, None
+        self.max_candidates = max_candidates
+
+    def _beam_step(self):
+        """Decoder pass + top-(G + 1) + candidate merge + history / cache-table permutation + position advance."""
+        self._forward_token()
+        suppress, suppress_first, eot, no_speech, ts = self._sampler[:5]
+        nv.beam_step(self.logits, self.p.n_vocab, self.G, suppress, suppress_first, self.tokens, self.tokens_tmp,
+                     self.state, eot, no_speech, ts, self.max_candidates, self.sum_logprobs, self.sum_tmp,
+                     self.no_speech_prob, self.hyp_id, self.row_table, self.table_tmp, self.top_vals, self.top_idx,
+                     self.fin_tokens, self.fin_score, self.fin_len, self.n_fin)
+        nv.step_advance(self.state, self.B)
+
+    def run_beam(self, n_sample: int, n_ctx: int, check_every: int = 8) -> int:
+        """Feeds the prompt and runs up to n_sample beam-search steps (one replay of the captured step each); the host
+        only polls the completion flag (every audio has its finished candidates) every few steps."""
+        total = self.n_init - 1 + n_sample
+        assert self.n_init + n_sample <= self.tokens.shape[1]
+        if self.use_graph and self._beam_graph is None:
+            snap = [t.clone() for t in (self.state, self.tokens, self.sum_logprobs, self.no_speech_prob, self.hyp_id,
+                                        self.n_fin)] + ([self.row_table.clone()] if self.row_table is not None else [])
+            side = torch.cuda.Stream(device=self.dev)
+            side.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.stream(side):
+                self._beam_step()        # warm-up outside capture
+            torch.cuda.current_stream(self.dev).wait_stream(side)
+            for dst, src in zip((self.state, self.tokens, self.sum_logprobs, self.no_speech_prob, self.hyp_id, self.n_fin)
+                                + ((self.row_table,) if self.row_table is not None else ()), snap):
+                dst.copy_(src)
+            g = torch.cuda.CUDAGraph()
+            before = nv.kernel_launch_count()
+            with torch.cuda.graph(g):
+                self._beam_step()
+            self._beam_graph_kernels = nv.kernel_launch_count() - before
+            self._beam_graph = g
+        steps = 0
+        for i in range(total):
+            if self._beam_graph is not None:
+                self._beam_graph.replay()
+                nv.note_graph_replay(self._beam_graph_kernels)
+            else:
+                self._beam_step()
+            steps += 1
+            sampled = i - (self.n_init - 1) + 1
+            if sampled > 0 and self.n_init + sampled > n_ctx:
+                break                      # the reference stops once a hypothesis is longer than the text context
+            if sampled > 0 and sampled % check_every == 0 and i + 1 < total and self.all_done():
+                break
+        return steps
+
+    # -- beam search support, host-driven (kept for WF_BEAM_HOST=1 A/B runs; see decoding.py) --------------
     def forward_at(self, pos: int):
         """Single-position pass used by the beam-search driver: sets state[0] = pos, then replays the captured
         forward graph (or launches the kernels eagerly when graphs are off)."""
@@ -979,7 +1052,14 @@ class SplitSession:
         return toks, lps, nsp
 
 
-_SESSION_CACHE = weakref.WeakKeyDictionary()  # decoder module -> its last DecodeSession / SplitSession
+_SESSION_CACHE = weakref.WeakKeyDictionary()  # decoder module -> its most recent sessions (most recent first)
+
+
+def _session_cache_size() -> int:
+    """Sessions kept per decoder (WF_SESSION_CACHE, default 3).  The long-form driver alternates between a few shapes
+    (the batch shrinks as recordings end, fallback sub-batches, bucketed token capacities): each keeps its K/V arena,
+    step buffers and captured CUDA graph."""
+    return max(1, int(os.environ.get("WF_SESSION_CACHE", "3")))
 
 
 def default_split(n_rows: int, greedy: bool) -> int:
@@ -1005,9 +1085,13 @@ def get_session(dec, xa: Tensor, feats: Optional[Sequence[Tensor]], n_group: int
         feats = validate_features(feats, xa.shape[0], xa.device, len(p.blocks[0].x_attn))
     if os.environ.get("WF_NO_GRAPH", "0") == "1":
         n_split = 1  # per-kernel profiling mode: one eager stream
-    old = _SESSION_CACHE.get(dec)
     n_feats = 0 if feats is None else len(feats)
-    if old is not None and os.environ.get("WF_NO_SESSION_CACHE", "0") != "1":
+    cached = _SESSION_CACHE.get(dec) or []
+    no_cache = os.environ.get("WF_NO_SESSION_CACHE", "0") == "1"
+    if no_cache:
+        cached = []
+        _SESSION_CACHE.pop(dec, None)
+    for i, old in enumerate(cached):
         tx = tuple(f.shape[1] for f in feats) if (old.gated and feats is not None) else ()
         key = (dt, xa.device, xa.shape[0], n_group, t_cap, xa.shape[1], tx, id(p))
         if n_split > 1:
@@ -1016,16 +1100,26 @@ def get_session(dec, xa: Tensor, feats: Optional[Sequence[Tensor]], n_group: int
             old.latent == (old.fold is not None and latent_cross_enabled(old.R, old.G, p.n_head, p.d)) and
             old.latent_x == (old.latent and old.gated and os.environ.get("WF_LATENT_X", "1") != "0")))
         if old.shape_key() == key and (not old.gated or n_feats == len(old.Tx)) and same_path:
+            cached.insert(0, cached.pop(i))
             old.load(xa, old._check_feats(feats))
             return old
-    _SESSION_CACHE.pop(dec, None)
-    del old
+    # sessions of a repacked decoder (weights changed) can never match again: drop them, then make room
+    cached = [c for c in cached if c.p is p][: _session_cache_size() - 1]
+    _SESSION_CACHE[dec] = cached
     if n_split > 1:
         sess = SplitSession(dec, xa, feats, n_group, t_cap, n_split)
     else:
         sess = DecodeSession(dec, xa, feats, n_group, t_cap)
-    _SESSION_CACHE[dec] = sess
+    cached.insert(0, sess)
+    if no_cache:     # profiling sessions (eager, instrumented) must not be handed to a later product call
+        _SESSION_CACHE.pop(dec, None)
     return sess
+
+
+def last_session(dec):
+    """The most recently used cached session of a decoder (None when there is none) - test / tooling hook."""
+    cached = _SESSION_CACHE.get(dec)
+    return cached[0] if cached else None
 
 
 def clear_sessions() -> None:

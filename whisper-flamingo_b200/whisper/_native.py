@@ -50,6 +50,18 @@ class _Topk(C.Structure):
                 ("k", C.c_int), ("out_vals", C.c_void_p), ("out_idx", C.c_void_p)]
 
 
+class _Beam(C.Structure):
+    _fields_ = [("logits", C.c_void_p), ("ld", C.c_longlong), ("R", C.c_int), ("V", C.c_int), ("G", C.c_int),
+                ("suppress", C.c_void_p), ("suppress_first", C.c_void_p), ("tokens", C.c_void_p),
+                ("tokens_tmp", C.c_void_p), ("T_cap", C.c_int), ("state", C.c_void_p), ("eot", C.c_int),
+                ("no_speech", C.c_int), ("timestamp_begin", C.c_int), ("no_timestamps", C.c_int),
+                ("max_initial_ts", C.c_int), ("max_candidates", C.c_int), ("sum_logprobs", C.c_void_p),
+                ("sum_scratch", C.c_void_p), ("no_speech_prob", C.c_void_p), ("hyp_id", C.c_void_p),
+                ("row_table", C.c_void_p), ("table_tmp", C.c_void_p), ("table_ld", C.c_int),
+                ("top_vals", C.c_void_p), ("top_idx", C.c_void_p), ("fin_tokens", C.c_void_p),
+                ("fin_score", C.c_void_p), ("fin_len", C.c_void_p), ("n_fin", C.c_void_p)]
+
+
 _SIGNATURES = {
     "wf_version": (C.c_int, []),
     "wf_last_error": (C.c_char_p, []),
@@ -92,6 +104,7 @@ _SIGNATURES = {
     "wf_sample_greedy": (C.c_int, [C.POINTER(_Sample), C.c_void_p]),
     "wf_step_advance": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "wf_topk_logprobs": (C.c_int, [C.POINTER(_Topk), C.c_void_p]),
+    "wf_beam_step": (C.c_int, [C.POINTER(_Beam), C.c_void_p]),
     "wf_kv_gather_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_longlong,
                                     C.c_void_p]),
     "wf_debug_uniform_range": (C.c_int, [C.c_ulonglong, C.c_longlong, C.c_void_p, C.c_void_p]),
@@ -439,6 +452,24 @@ def topk_logprobs(logits: torch.Tensor, v: int, suppress: torch.Tensor, suppress
               _ptr(tokens), 0 if tokens is None else tokens.shape[1], n_init, cur_len, eot, ts[0], ts[1], ts[2], k,
               out_vals.data_ptr(), out_idx.data_ptr())
     _check(load().wf_topk_logprobs(C.byref(a), _stream()))
+
+
+def beam_step(logits: torch.Tensor, v: int, g: int, suppress: torch.Tensor, suppress_first: Optional[torch.Tensor],
+              tokens: torch.Tensor, tokens_tmp: torch.Tensor, state: torch.Tensor, eot: int, no_speech: int, ts,
+              max_candidates: int, sum_logprobs: torch.Tensor, sum_scratch: torch.Tensor, no_speech_prob: torch.Tensor,
+              hyp_id: torch.Tensor, row_table: Optional[torch.Tensor], table_tmp: Optional[torch.Tensor],
+              top_vals: torch.Tensor, top_idx: torch.Tensor, fin_tokens: torch.Tensor, fin_score: torch.Tensor,
+              fin_len: torch.Tensor, n_fin: torch.Tensor) -> None:
+    """One step of BeamSearchDecoder.update + rearrange_kv_cache for every audio of the batch, on the device."""
+    assert tokens.shape == tokens_tmp.shape and tokens.dtype == tokens_tmp.dtype == torch.int32
+    assert fin_tokens.shape[-1] == tokens.shape[1] and hyp_id.dtype == torch.int32
+    a = _Beam(logits.data_ptr(), _row_stride(logits), logits.shape[0], v, g, suppress.data_ptr(), _ptr(suppress_first),
+              tokens.data_ptr(), tokens_tmp.data_ptr(), tokens.shape[1], state.data_ptr(), eot, no_speech, ts[0], ts[1],
+              ts[2], max_candidates, sum_logprobs.data_ptr(), sum_scratch.data_ptr(), no_speech_prob.data_ptr(),
+              hyp_id.data_ptr(), _ptr(row_table), _ptr(table_tmp), 0 if row_table is None else row_table.shape[1],
+              top_vals.data_ptr(), top_idx.data_ptr(), fin_tokens.data_ptr(), fin_score.data_ptr(), fin_len.data_ptr(),
+              n_fin.data_ptr())
+    _check(load().wf_beam_step(C.byref(a), _stream()))
 
 
 def debug_uniform_range(seed: int, n: int, device) -> tuple:

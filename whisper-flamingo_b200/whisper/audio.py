@@ -4,7 +4,7 @@ Same public surface as reference ``whisper/audio.py`` (constants :13-23, ``pad_o
 ``mel_filters`` :92-108, ``log_mel_spectrogram`` :111-161); the computation runs in the fused
 CUDA kernel chain of ``csrc/logmel.cu`` behind ``wf_logmel_f32``.  There is no CPU path: CPU
 inputs are staged to the current CUDA device and the result is returned on the input's device.
-``load_audio`` (ffmpeg subprocess, :26-63) is outside the hot path and not provided.
+``load_audio`` (:26-63) runs ffmpeg like the reference and reads WAVE files natively where ffmpeg is missing.
 """
 from __future__ import annotations
 
@@ -32,9 +32,102 @@ FRAMES_PER_SECOND = exact_div(SAMPLE_RATE, HOP_LENGTH)  # 10ms per audio frame
 TOKENS_PER_SECOND = exact_div(SAMPLE_RATE, N_SAMPLES_PER_TOKEN)  # 20ms per audio token
 
 
+def _wav_pcm(file: str):
+    """(float32 mono waveform in [-1, 1), sample rate) of a RIFF/WAVE file with integer PCM (8 / 16 / 24 / 32 bit) or
+    IEEE float samples; None when the file is something else."""
+    import struct
+    with open(file, "rb") as fh:
+        head = fh.read(12)
+        if len(head) < 12 or head[:4] != b"RIFF" or head[8:12] != b"WAVE":
+            return None
+        fmt, data = None, None
+        while True:
+            ck = fh.read(8)
+            if len(ck) < 8:
+                break
+            tag, size = ck[:4], struct.unpack("<I", ck[4:])[0]
+            if tag == b"fmt ":
+                fmt = fh.read(size)
+            elif tag == b"data":
+                data = fh.read(size)
+            else:
+                fh.seek(size, 1)
+            if size & 1:
+                fh.seek(1, 1)
+            if fmt is not None and data is not None:
+                break
+    if fmt is None or data is None or len(fmt) < 16:
+        return None
+    code, channels, rate, _, _, bits = struct.unpack("<HHIIHH", fmt[:16])
+    if code == 0xFFFE and len(fmt) >= 26:      # WAVE_FORMAT_EXTENSIBLE: the real code opens the sub-format GUID
+        code = struct.unpack("<H", fmt[24:26])[0]
+    if code == 1 and bits == 8:
+        x = (np.frombuffer(data, np.uint8).astype(np.float32) - 128.0) / 128.0
+    elif code == 1 and bits == 16:
+        x = np.frombuffer(data[: len(data) // 2 * 2], "<i2").astype(np.float32) / 32768.0
+    elif code == 1 and bits == 24:
+        b = np.frombuffer(data[: len(data) // 3 * 3], np.uint8).reshape(-1, 3).astype(np.int32)
+        v = b[:, 0] | (b[:, 1] << 8) | (b[:, 2] << 16)
+        x = (v - ((v & 0x800000) << 1)).astype(np.float32) / 8388608.0
+    elif code == 1 and bits == 32:
+        x = np.frombuffer(data[: len(data) // 4 * 4], "<i4").astype(np.float32) / 2147483648.0
+    elif code == 3 and bits == 32:
+        x = np.frombuffer(data[: len(data) // 4 * 4], "<f4").astype(np.float32)
+    elif code == 3 and bits == 64:
+        x = np.frombuffer(data[: len(data) // 8 * 8], "<f8").astype(np.float32)
+    else:
+        return None
+    if channels > 1:
+        x = x[: len(x) // channels * channels].reshape(-1, channels).mean(axis=1, dtype=np.float32)
+    return x, int(rate)
+
+
+def _resample(x: np.ndarray, rate: int, sr: int) -> np.ndarray:
+    """Band-limited rate conversion by a Kaiser-windowed sinc (cut-off at 0.94 of the lower Nyquist, 32 zero
+    crossings): one interpolation per output sample, vectorised in blocks.  Not ffmpeg's resampler - only the
+    fall-back for hosts without ffmpeg."""
+    if rate == sr or len(x) == 0:
+        return x.astype(np.float32)
+    ratio = sr / rate
+    cutoff = 0.94 * min(1.0, ratio)
+    half = int(np.ceil(32 / cutoff))
+    n_out = int(np.floor(len(x) * ratio))
+    xp = np.concatenate([np.zeros(half, np.float32), x.astype(np.float32), np.zeros(half + 1, np.float32)])
+    taps = np.arange(-half, half + 1)
+    out = np.empty(n_out, np.float32)
+    for lo in range(0, n_out, 65536):
+        t = np.arange(lo, min(lo + 65536, n_out)) / ratio          # positions in input samples
+        base = np.floor(t).astype(np.int64)
+        frac = (t - base)[:, None]
+        arg = taps[None, :] - frac                                  # distance of every tap from the output instant
+        win = np.i0(8.6 * np.sqrt(np.clip(1.0 - (arg / (half + 1)) ** 2, 0.0, None))) / np.i0(8.6)
+        h = cutoff * np.sinc(cutoff * arg) * win
+        idx = base[:, None] + taps[None, :] + half
+        out[lo: lo + len(t)] = (xp[idx] * h).sum(axis=1)
+    return out
+
+
 def load_audio(file: str, sr: int = SAMPLE_RATE):
-    raise RuntimeError("load_audio (ffmpeg decode, reference audio.py:26-63) is outside the B200 hot path; "
-                       "pass a waveform array or tensor instead")
+    """Open an audio file as a mono float32 waveform at ``sr`` Hz (reference audio.py:26-63).
+
+    Like the reference this runs the ``ffmpeg`` CLI (any container / codec, down-mix, resample, 16-bit PCM -> float
+    / 32768).  Hosts without ffmpeg still read RIFF/WAVE files natively (PCM or float samples, any rate - resampled by
+    a windowed sinc, which is close to but not bit-identical with ffmpeg's)."""
+    from subprocess import CalledProcessError, run
+    cmd = ["ffmpeg", "-nostdin", "-threads", "0", "-i", file, "-f", "s16le", "-ac", "1", "-acodec", "pcm_s16le",
+           "-ar", str(sr), "-"]
+    try:
+        out = run(cmd, capture_output=True, check=True).stdout
+        return np.frombuffer(out, np.int16).flatten().astype(np.float32) / 32768.0
+    except CalledProcessError as e:
+        raise RuntimeError(f"Failed to load audio: {e.stderr.decode()}") from e
+    except FileNotFoundError:
+        pass  # no ffmpeg on this host
+    wav = _wav_pcm(file)
+    if wav is None:
+        raise RuntimeError(f"Failed to load audio: ffmpeg is not installed and {file!r} is not a PCM / float WAVE file")
+    x, rate = wav
+    return _resample(x, rate, sr)
 
 
 def pad_or_trim(array, length: int = N_SAMPLES, *, axis: int = -1):

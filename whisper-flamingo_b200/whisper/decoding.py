@@ -233,7 +233,9 @@ class DecodingTask:
             raise ValueError(f"beam_size must be between 1 and 31 on this engine, got {options.beam_size}")
         return options
 
-    def _get_initial_tokens(self) -> Tuple[int, ...]:
+    _UNSET = object()
+
+    def _get_initial_tokens(self, prompt=_UNSET) -> Tuple[int, ...]:
         tokens = list(self.sot_sequence)
         prefix = self.options.prefix
         if prefix:
@@ -241,7 +243,8 @@ class DecodingTask:
             if self.sample_len is not None:
                 ids = ids[-(self.n_ctx // 2 - self.sample_len):]
             tokens = tokens + ids
-        prompt = self.options.prompt
+        if prompt is DecodingTask._UNSET:
+            prompt = self.options.prompt
         if prompt:
             ids = self.tokenizer.encode(" " + prompt.strip()) if isinstance(prompt, str) else list(prompt)
             tokens = [self.tokenizer.sot_prev] + ids[-(self.n_ctx // 2 - 1):] + tokens
@@ -296,7 +299,10 @@ class DecodingTask:
 
     # ---- main entry (reference :720-798)
     @torch.no_grad()
-    def run(self, mel: Tensor, x_v=None, test_a: bool = False, test_v: bool = False) -> List[DecodingResult]:
+    def run(self, mel: Tensor, x_v=None, test_a: bool = False, test_v: bool = False,
+            prompts: Optional[Sequence[Sequence[int]]] = None) -> List[DecodingResult]:
+        """``prompts`` (extension, used by ``transcribe_batch``): one previous-text token list per clip instead of the
+        single ``options.prompt``; after the reference's truncation (:603) they must give rows of equal length."""
         nv.require_cuda(mel)
         tk = self.tokenizer
         n_audio = mel.shape[0]
@@ -307,6 +313,13 @@ class DecodingTask:
             audio_features = self._get_audio_features(mel)
             timing.mark("encoder")
             init_rows = [list(self.initial_tokens) for _ in range(n_audio)]
+            if prompts is not None:
+                if len(prompts) != n_audio:
+                    raise ValueError(f"{len(prompts)} prompts for {n_audio} clips")
+                init_rows = [list(self._get_initial_tokens(list(p))) for p in prompts]
+                if any(len(r) != self.sample_begin for r in init_rows):
+                    raise ValueError("per-clip prompts must give initial token rows of one length "
+                                     f"({sorted({len(r) for r in init_rows})} vs {self.sample_begin})")
             languages, language_probs = self._detect_language(audio_features, init_rows, feats)
             if self.options.task == "lang_id":
                 return [DecodingResult(audio_features=f, language=l, language_probs=p)
@@ -314,7 +327,10 @@ class DecodingTask:
             n_sample = min(self.sample_len, self.n_ctx + 1 - self.sample_begin)
             if n_sample <= 0:
                 raise ValueError("the prompt already fills the text context; nothing can be sampled")
+            # token capacity of the session in buckets of 64: the prompt of the long-form driver changes length with
+            # every window, and a session (K/V arena, step buffers, captured graph) is keyed by its capacity
             t_cap = self.sample_begin + n_sample
+            t_cap = min(-(-t_cap // 64) * 64, max(t_cap, self.n_ctx + 1))
             greedy = self.options.beam_size is None
             session = _engine.get_session(self.model.decoder, audio_features, feats, self.n_group, t_cap,
                                           _engine.default_split(n_audio * self.n_group, greedy))
@@ -370,6 +386,45 @@ class DecodingTask:
         return cand, cand_lp, nsp[::G]
 
     def _run_beam(self, session: "_engine.DecodeSession", n_sample: int, init_rows: List[List[int]]):
+        """BeamSearchDecoder (reference :305-408) with the whole step on the device: decoder pass, top-(G + 1), candidate
+        merge per audio, token-history and cache-table permutation are one replayed CUDA graph; the host polls the
+        completion flag every 8 steps and assembles the candidate lists once at the end (finalize, :388-408)."""
+        import os
+        if os.environ.get("WF_BEAM_HOST", "0") == "1":
+            return self._run_beam_host(session, n_sample, init_rows)
+        G, tk = self.n_group, self.tokenizer
+        max_candidates = round(G * (self.options.patience or 1.0))
+        assert max_candidates > 0, f"Invalid beam size ({G}) or patience ({self.options.patience})"
+        if max_candidates > 32:
+            raise ValueError(f"beam_size * patience = {max_candidates} finished candidates per audio; this engine keeps "
+                             f"at most 32")
+        session.configure_beam(max_candidates)
+        session.run_beam(n_sample, self.n_ctx)
+        # one device -> host read of the whole search state
+        L = int(session.state[0].item()) + 1          # tokens per live hypothesis
+        rows = session.tokens[:, :L].cpu().tolist()
+        sum_lp = session.sum_logprobs.cpu().numpy()
+        n_fin = session.n_fin.cpu().tolist()
+        fin_len = session.fin_len.cpu().tolist()
+        fin_score = session.fin_score.cpu().tolist()
+        fin_tok = session.fin_tokens.cpu()
+        cand, cand_lp = [], []
+        for a in range(session.B):
+            seqs = {tuple(fin_tok[a, m, : fin_len[a][m]].tolist()): fin_score[a][m] for m in range(n_fin[a])}
+            if len(seqs) < G:  # top up with the best live hypotheses (reference :393-400)
+                order = np.argsort(sum_lp[a * G:(a + 1) * G])[::-1]
+                for j in order:
+                    seqs[tuple(rows[a * G + j] + [tk.eot])] = float(sum_lp[a * G + j])
+                    if len(seqs) >= G:
+                        break
+            cand.append([list(q) for q in seqs])
+            cand_lp.append(list(seqs.values()))
+        nsp = session.no_speech_prob.cpu().tolist()[::G]
+        return cand, cand_lp, nsp
+
+    def _run_beam_host(self, session: "_engine.DecodeSession", n_sample: int, init_rows: List[List[int]]):
+        """Round-1 form: the decoder pass and the top-k on the device, the candidate merge in Python (two device -> host
+        syncs and three uploads per step).  WF_BEAM_HOST=1; kept as the A/B comparator of the device-side search."""
         G, tk, n_init = self.n_group, self.tokenizer, self.sample_begin
         R = session.R
         book = _BeamBook(G, tk.eot, self.options.patience, session.B)
@@ -412,7 +467,8 @@ class DecodingTask:
 
 @torch.no_grad()
 def decode(model: "Whisper", mel: Tensor, options: DecodingOptions = DecodingOptions(), x_v=None,
-           test_v: bool = False, test_a: bool = False, **kwargs) -> Union[DecodingResult, List[DecodingResult]]:
+           test_v: bool = False, test_a: bool = False, prompts: Optional[Sequence[Sequence[int]]] = None,
+           **kwargs) -> Union[DecodingResult, List[DecodingResult]]:
     """Decode 30-second segment(s) given as mel spectrogram(s) ``(n_mels, 3000)`` or ``(*, n_mels, 3000)``.
 
     ``x_v``: optional feature tensor ``(*, T_x, bert_dim)`` (or list of tensors) for a gated x-attn model.
@@ -425,5 +481,5 @@ def decode(model: "Whisper", mel: Tensor, options: DecodingOptions = DecodingOpt
             x_v = x_v.unsqueeze(0)
     if kwargs:
         options = replace(options, **kwargs)
-    result = DecodingTask(model, options).run(mel, x_v, test_a, test_v)
+    result = DecodingTask(model, options).run(mel, x_v, test_a, test_v, prompts=prompts)
     return result[0] if single else result
