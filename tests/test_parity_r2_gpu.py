@@ -94,11 +94,14 @@ def test_medium_beam5_more_than_128_rows_fp32_tokens_identical_to_oracle(medium_
     _engine.clear_sessions()
 
 
-def test_medium_beam5_more_than_128_rows_bf16_logits_and_decode(medium_case):
-    """bf16 engine on the same shape: R = 130 disables the fused-LayerNorm path, self-attention goes through
+@pytest.mark.parametrize("fused", [True, False])
+def test_medium_beam5_more_than_128_rows_bf16_logits_and_decode(medium_case, fused, monkeypatch):
+    """bf16 engine on the same shape, R = 130 rows = two row tiles: the decode GEMMs run row-tiled with the LayerNorms
+    inside (fused) or as the unfused 19-launch blocks (WF_NO_LN_FUSION=1); self-attention goes through
     wf_attention_decode_paged (row table), cross / x-attention through the shared-cache multi-query kernel (G = 5).
     Teacher-forced histories (identical for the 5 rows of a clip) with the row table SHUFFLED inside each clip - any
     row of the group holds the same K/V, so the logits must not move - against the fp32 oracle."""
+    monkeypatch.setenv("WF_NO_LN_FUSION", "0" if fused else "1")
     import whisper
     from whisper import _engine
     from whisper.decoding import DecodingTask
@@ -115,7 +118,7 @@ def test_medium_beam5_more_than_128_rows_bf16_logits_and_decode(medium_case):
     xa16 = model.encoder(mel.bfloat16())
     _engine.clear_sessions()
     sess = _engine.DecodeSession(model.decoder, xa16, [feat.cuda()], G, t + 1, use_graph=False)
-    assert sess.fold is None and sess.R == 130 and sess.row_table is not None
+    assert (sess.fold is not None) == fused and sess.R == 130 and sess.row_table is not None
     suppress = torch.zeros(51865, dtype=torch.uint8, device="cuda")
     sess.configure_greedy(task.initial_tokens, task.sot_index, suppress, None, tk.eot, tk.no_speech, (-1, -1, -1))
     sess.tokens[:, :t] = hist.repeat_interleave(G, 0).to("cuda", torch.int32)
@@ -126,7 +129,11 @@ def test_medium_beam5_more_than_128_rows_bf16_logits_and_decode(medium_case):
         sess._forward_token()
         whisper._native.step_advance(sess.state, sess.R)
     got = sess.logits[:, :51865].float().cpu().view(B, G, -1)
-    assert (got - got[:, :1]).abs().max().item() <= 1e-5 * got.abs().max().item() + 1e-6, "rows of a group differ"
+    # unfused: identical rows are computed identically.  Fused: the LayerNorm statistics inside the GEMM are summed in a
+    # row-dependent chunk order (bank-conflict-free reads of the swizzled tile), so equal rows agree to fp32 rounding of
+    # mean / rstd, i.e. to a bf16 ulp here and there - far below the bf16 tolerance against the oracle checked next
+    spread = (got - got[:, :1]).abs().max().item()
+    assert spread <= (2e-2 if fused else 1e-5) * got.abs().max().item() + 1e-6, f"rows of a group differ by {spread}"
     check = [0, 9, 25]
     xa32 = om.encoder_forward(sd, od, mel[check].cpu())
     ref = om.decoder_forward(sd, od, hist[check], xa32, xt_list=[feat[check]])[:, -1]

@@ -103,6 +103,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 
   const int rank = static_cast<int>(cluster_ctarank());
   const int n_blk = blockIdx.x / CS;
+  const int m0 = blockIdx.y * SK_BM;   // row tile: beam-search steps run up to a few hundred hypotheses
   const int rounds_total = (K + SK_KA * SK_BK - 1) / (SK_KA * SK_BK);
   const int per = (rounds_total + CS - 1) / CS;
   const int r0 = min(rounds_total, rank * per), r1 = min(rounds_total, r0 + per);
@@ -144,7 +145,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     for (int i = 0; i < npre; ++i) {
 #pragma unroll
       for (int a = 0; a < SK_KA; ++a)
-        tma_load_2d(a_atom(i, a), &map_a, &full_bar[i], ((r0 + i) * SK_KA + a) * SK_BK, 0);
+        tma_load_2d(a_atom(i, a), &map_a, &full_bar[i], ((r0 + i) * SK_KA + a) * SK_BK, m0);
     }
     int stage = npre == STAGES ? 0 : npre;
     uint32_t phase = npre == STAGES ? 1 : 0;
@@ -153,7 +154,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
 #pragma unroll
       for (int a = 0; a < SK_KA; ++a) {
-        tma_load_2d(a_atom(stage, a), &map_a, &full_bar[stage], ((r0 + r) * SK_KA + a) * SK_BK, 0);
+        tma_load_2d(a_atom(stage, a), &map_a, &full_bar[stage], ((r0 + r) * SK_KA + a) * SK_BK, m0);
         tma_load_2d(b_atom(stage, a), &map_b, &full_bar[stage], ((r0 + r) * SK_KA + a) * SK_BK, n_blk * BN);
       }
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -290,10 +291,11 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     if (CS == 1) {
       const int q = warp & 3;
       const int grp = (warp - 4) >> 2;
-      const int m = q * 32 + lane;
+      const int ml = q * 32 + lane;       // row inside the tile
+      const int m = m0 + ml;
       const long long res_row = ep.res_row_mod > 0 ? (m % ep.res_row_mod) : m;
       float mean = 0.f, rstd = 1.f;
-      if (ln) row_stats(m, mean, rstd);
+      if (ln) row_stats(ml, mean, rstd);
       const uint32_t tsrc = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
       for (int c = grp; c < BN / 32; c += 2) {
@@ -327,10 +329,10 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       constexpr int GPR = BN / 8;
       const uint32_t dump_local = smem_u32(dump);
       for (int it = et; it < rows_per * GPR; it += EPI_THREADS_SK) {
-        const int row = rank * rows_per + it / GPR;
+        const int row = rank * rows_per + it / GPR;     // row inside the tile
         const int col = (it % GPR) * 8;
         const int n0 = n_blk * BN + col;
-        if (row >= M || n0 >= N) continue;
+        if (m0 + row >= M || n0 >= N) continue;
         const uint32_t off = static_cast<uint32_t>((row * Cfg::DUMP_LD + col) * 4);
         float4 t[8][2];
 #pragma unroll
@@ -353,8 +355,8 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         }
         float mean = 0.f, rstd = 1.f;
         if (ln) row_stats(row, mean, rstd);
-        const long long res_row = ep.res_row_mod > 0 ? (row % ep.res_row_mod) : row;
-        finish_chunk<8>(v, ep, row, res_row, n0, N, gate, c_off, mean, rstd);
+        const long long res_row = ep.res_row_mod > 0 ? ((m0 + row) % ep.res_row_mod) : (m0 + row);
+        finish_chunk<8>(v, ep, m0 + row, res_row, n0, N, gate, c_off, mean, rstd);
       }
     }
   }
@@ -382,7 +384,7 @@ static int launch_skinny(const CUtensorMap& ma, const CUtensorMap& mb, int M, in
   }
   const int tiles = (N + BN - 1) / BN;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(tiles * cs);
+  cfg.gridDim = dim3(tiles * cs, (M + SK_BM - 1) / SK_BM);
   cfg.blockDim = dim3(SK_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
@@ -418,8 +420,13 @@ static int launch_skinny(const CUtensorMap& ma, const CUtensorMap& mb, int M, in
 //   * a cluster costs ~1.1 us for its two barriers plus the DSMEM reduction at ~20 B/clk per SM, so K is split (4-way)
 //     only when a CTA would otherwise walk >= 32 rounds:  N=1280, K=5120: 15.4 us (32, cs 1) -> 10.0 us (64, cs 4);
 //     N=K=1280: 5.94 us (32, cs 1) vs 5.98 us (32, cs 2).
+// M > 128 (beam search: B x G hypotheses): the same kernel over ceil(M / 128) row tiles, every tile a CTA (cluster) of
+// its own - the weights are read once from HBM and then from L2.  Up to 4 row tiles; above, the persistent large-tile
+// kernels of gemm_tc.cu / gemm_tc2.cu take over.
+static constexpr int SK_MAX_M_TILES = 4;
 bool skinny_plan(int M, int N, int K, int tile_hint, int* bn_out, int* cs_out) {
-  if (M > SK_BM) return false;
+  if (M > SK_BM * SK_MAX_M_TILES) return false;
+  const int m_tiles = (M + SK_BM - 1) / SK_BM;
   static int mode = -1, force_cs = -1;
   if (mode < 0) {
     const char* e = getenv("WF_SKINNY");  // 0: use the persistent kernel of gemm_tc.cu instead (A/B measurements)
@@ -439,7 +446,7 @@ bool skinny_plan(int M, int N, int K, int tile_hint, int* bn_out, int* cs_out) {
       const int bn = bns[i];
       if (tile_hint && bn != tile_hint) continue;
       const int tiles = (N + bn - 1) / bn;
-      if (tiles * cs > sms) continue;
+      if (tiles * cs * m_tiles > sms) continue;
       *bn_out = bn;
       *cs_out = cs;
       return true;

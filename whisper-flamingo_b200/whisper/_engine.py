@@ -568,8 +568,8 @@ class DecodeSession:
         self.T_cap = t_cap
         d, H = p.d, p.n_head
         self.gated = len(p.blocks) > 0 and len(p.blocks[0].x_attn) > 0
-        # bf16 and one 128-row tile: LayerNorms run inside the GEMMs and q | k,v is a single projection
-        self.fold = (decoder_fold(dec, p, dt) if (dt == torch.bfloat16 and R <= 128 and
+        # bf16 and at most four 128-row tiles: LayerNorms run inside the GEMMs and q | k,v is a single projection
+        self.fold = (decoder_fold(dec, p, dt) if (dt == torch.bfloat16 and R <= 512 and
                                                   os.environ.get("WF_NO_LN_FUSION", "0") != "1") else None)
         feats = self._check_feats(feats)
         self.Ta = Ta = xa.shape[1]
