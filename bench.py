@@ -250,11 +250,12 @@ def run_product(args):
         dist.destroy_process_group()
 
 
-# DRAM bytes (read + write) per launch of a kernel family from the committed `ncu --set full` captures under profiles/
-# (large-v2 AV, B=128, greedy): attention_decode alternates a cross-attention (988.0 MB) and an x-attention (499.2 MB)
-# launch with the K/V-cache path and is x-attention only (497.0 MB) with the latent path; latent_attention: 608.7 MB read
-# + 4.0 MB written against 491.5 MB of source rows - part of the second pass misses L2 (r01_ncu_full_latent_attn.txt)
-NCU_TRAFFIC = {"attention_decode": 497.0e6, "latent_attention": 612.7e6}
+# DRAM bytes (read + write) per launch of a kernel family, from the committed `ncu --set full` capture of this same
+# configuration (profiles/r02_ncu_full_latent_pair.txt: large-v2 AV, B=128, greedy): the cross-attention launch over 1500
+# encoder rows reads 498.5 MB + writes 5.6 MB against 491.5 MB of source rows, the x-attention launch over 750 feature
+# rows 252.8 + 5.5 MB against 245.8 MB - every source row crosses the HBM interface once (the round-1 two-pass kernel:
+# 612.7 MB).  Reported as `traffic` with `traffic_source: "profile"`: ncu cannot run inside the timed region.
+NCU_TRAFFIC = {"latent_attention_T1500": 504.1e6, "latent_attention_T750": 258.3e6}
 
 
 def launch_floor_ms(dev, n=256):
@@ -321,14 +322,14 @@ def profile_kernels(model, pcm_dev, feat_dev, opt, B, step_ms):
         ach, peak, unit = f["flops"] / (f["ms"] * 1e-3) / 1e12, pk["tc_sustained"], "TFLOP/s"
     else:
         ach, peak, unit = f["bytes"] / (f["ms"] * 1e-3) / 1e9, pk["hbm"], "GB/s"
-    # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/
-    # r01_ncu_full_attn_decode_hm.txt: 988.0 MB for a cross-attention launch, 499.2 MB for an x-attention launch; the
-    # family alternates the two, algorithmic 983.0 / 491.5 MB) - only for the configuration that was captured
+    # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture - only for the configuration
+    # that was captured
     traffic = None
     if B == 128 and not BEAM and len(model.decoder.blocks) == 32:
         traffic = NCU_TRAFFIC.get(top["kernel"])
     roof = {"kernel": top["kernel"], "bound": "tensor" if tensor_bound else "hbm", "achieved": round(ach, 1),
             "peak": peak, "unit": unit, "frac": round(ach / peak, 4), "traffic": traffic,
+            "traffic_source": None if traffic is None else "profile (profiles/r02_ncu_full_latent_pair.txt)",
             "algorithmic_per_launch": round((f["flops"] if tensor_bound else f["bytes"]) / f["launches"], 1),
             "avg_launch_ms": round(f["ms"] / f["launches"], 4), "peak_source": pk["source"],
             "share_of_step": top["share_above_launch_floor"], "launch_floor_us": round(floor_ms * 1e3, 2)}

@@ -395,7 +395,9 @@ def latent_attention(qp: torch.Tensor, src: torch.Tensor, ctx: torch.Tensor, h: 
     assert src.dtype == qp.dtype == ctx.dtype == torch.bfloat16 and d == 64 * h
     assert src.is_contiguous() and qp.is_contiguous() and ctx.is_contiguous() and qp.numel() == b * d * h
     # algorithmic bytes: every source row once for all heads
-    with _Prof("latent_attention", bytes=2 * b * t * d):
+    # (profiled per source length: the cross-attention over 1500 encoder rows and the x-attention over 750 feature rows
+    # are different launches of the same kernel)
+    with _Prof(f"latent_attention_T{t}", bytes=2 * b * t * d):
         if ml is None:
             assert ctx.numel() == b * d * h
             _check(load().wf_latent_attention(qp.data_ptr(), src.data_ptr(), ctx.data_ptr(), b, t, h, _stream()))
