@@ -44,9 +44,9 @@ struct TcEpilogue {
 };
 
 // gemm_skinny.cu
-bool skinny_plan(int M, int N, int K, int tile_hint, int* bn_out, int* cs_out);
+bool skinny_plan(int M, int N, int K, int tile_hint, int* bn_out, int* cs_out, int* bm_out);
 int linear_bf16_skinny(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K,
-                       const TcEpilogue& ep, int bn, int cs, cudaStream_t stream);
+                       const TcEpilogue& ep, int bm, int bn, int cs, cudaStream_t stream);
 
 // gemm_tc2.cu
 bool pair_gemm_usable(int M, int N, int K);

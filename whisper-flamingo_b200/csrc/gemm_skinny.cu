@@ -33,14 +33,17 @@ static constexpr int SK_THREADS = 384; // warp 0 TMA, warp 1 MMA, warp 2 TMEM al
 static constexpr int SK_UMMA_K = 16;
 static constexpr int EPI_THREADS_SK = 256;
 
-template <int BN, int STAGES>
+// BM = 128, or 64: half the rows per CTA on twice the CTAs.  Every CTA of a GEMM re-reads its BM rows of the activation
+// tile from L2 (~64 B/clk per SM, ~6300 B/clk chip-wide), which - not the weight stream - sets the main loop of these
+// kernels: (BM + BN) x K x 2 bytes per CTA.  N = K = 1280: 409 KB on 40 CTAs (128 x 32) -> 245 KB on 80 CTAs (64 x 32).
+template <int BM, int BN, int STAGES>
 struct SkCfg {
-  static constexpr int A_ATOM = SK_BM * SK_BK * 2;  // 16 KB
+  static constexpr int A_ATOM = BM * SK_BK * 2;  // 16 KB / 8 KB
   static constexpr int B_ATOM = BN * SK_BK * 2;
   static constexpr int STAGE_BYTES = SK_KA * (A_ATOM + B_ATOM);
   static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
   static constexpr int DUMP_LD = BN + 4;  // +16 B per row: 16-byte accesses of a quarter-warp hit distinct banks
-  static constexpr int DUMP_BYTES = SK_BM * DUMP_LD * 4;
+  static constexpr int DUMP_BYTES = BM * DUMP_LD * 4;
   static constexpr int STAT_BYTES = 2 * SK_BM * 2 * 4;  // [atom group][row]{sum, sumsq}
   static constexpr int BAR_BYTES = (2 * STAGES + 1) * 8 + 16;
   static constexpr int SMEM_BYTES = PIPE_BYTES + STAT_BYTES + BAR_BYTES + 1024;
@@ -82,11 +85,11 @@ __device__ __forceinline__ float2 ld_dsmem_f2(uint32_t addr) {
   return v;
 }
 
-template <int BN, int STAGES>
+template <int BM, int BN, int STAGES>
 __global__ void __launch_bounds__(SK_THREADS, 1)
 gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                    int M, int N, int K, TcEpilogue ep, int CS) {
-  using Cfg = SkCfg<BN, STAGES>;
+  using Cfg = SkCfg<BM, BN, STAGES>;
   extern __shared__ uint8_t sk_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sk_smem_raw) + 1023) & ~uintptr_t(1023));
   float* dump = reinterpret_cast<float*>(smem);                                   // aliases the pipeline stages
@@ -103,7 +106,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 
   const int rank = static_cast<int>(cluster_ctarank());
   const int n_blk = blockIdx.x / CS;
-  const int m0 = blockIdx.y * SK_BM;   // row tile: beam-search steps run up to a few hundred hypotheses
+  const int m0 = blockIdx.y * BM;   // row tile: beam-search steps run up to a few hundred hypotheses
   const int rounds_total = (K + SK_KA * SK_BK - 1) / (SK_KA * SK_BK);
   const int per = (rounds_total + CS - 1) / CS;
   const int r0 = min(rounds_total, rank * per), r1 = min(rounds_total, r0 + per);
@@ -164,7 +167,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     // into accumulator 0, warp 3 the odd rounds into accumulator 1 (the epilogue adds them).  One thread sustains
     // ~350 cycles per round + ~63 per MMA whatever the tile shape (M = 64 operands: same time), and the cost is per issuing
     // THREAD: a second stream brought N=K=1280 from 6.9 to 5.9 us and K=5120 from 20.0 to 15.4 us.
-    constexpr uint32_t idesc = umma_idesc_bf16(SK_BM, BN);
+    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
     constexpr int NI = Cfg::NI;
     const int me = warp - 1;
     const uint32_t tmem_d = tmem_base + me * BN;
@@ -192,7 +195,11 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     // ------------------------------------------------------------ epilogue warps, phase A
     const int q = warp & 3;            // TMEM lane quarter
     const int grp = (warp - 4) >> 2;   // 0 / 1: column half in the epilogue, swizzle atom in the LN statistics
-    const int rloc = q * 32 + lane;
+    const int rloc = q * 32 + lane;    // row of the staged A tile whose statistics this thread accumulates
+    // accumulator row of this thread: a 128-row accumulator keeps row r in lane r, a 64-row one keeps rows 16 q .. 16 q + 15
+    // in lanes 32 q .. 32 q + 15 (profiles/r01_probe_tmem_m64_layout.txt)
+    const int arow = BM == 128 ? rloc : q * 16 + (lane & 15);
+    const bool alive = BM == 128 || lane < 16;
     if (ln) {
       // row sums of the raw A operand from the staged tiles (row = 128 B = 8 chunks of 16 B, order irrelevant)
       float s1 = 0.f, s2 = 0.f;
@@ -202,7 +209,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         mbar_wait(&full_bar[stage], phase);
         const uint8_t* row = a_atom(stage, grp) + rloc * 128;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 8 && rloc < BM; ++j) {
           const uint4 u = *reinterpret_cast<const uint4*>(row + ((j + rloc) & 7) * 16);
           const float f[8] = {bf16lo(u.x), bf16hi(u.x), bf16lo(u.y), bf16hi(u.y),
                               bf16lo(u.z), bf16hi(u.z), bf16lo(u.w), bf16hi(u.w)};
@@ -247,10 +254,12 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 #pragma unroll
           for (int j = 0; j < 32; ++j) r[j] = 0u;
         }
-        float* drow = dump + rloc * Cfg::DUMP_LD + c * 32;
+        float* drow = dump + arow * Cfg::DUMP_LD + c * 32;
+        if (alive) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<uint4*>(drow + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<uint4*>(drow + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+        }
       }
     }
   }
@@ -291,7 +300,8 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     if (CS == 1) {
       const int q = warp & 3;
       const int grp = (warp - 4) >> 2;
-      const int ml = q * 32 + lane;       // row inside the tile
+      const int ml = BM == 128 ? q * 32 + lane : q * 16 + (lane & 15);       // row inside the tile
+      const bool alive = BM == 128 || lane < 16;
       const int m = m0 + ml;
       const long long res_row = ep.res_row_mod > 0 ? (m % ep.res_row_mod) : m;
       float mean = 0.f, rstd = 1.f;
@@ -313,7 +323,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           }
         }
         const int n0 = n_blk * BN + c * 32;
-        if (m < M && n0 < N) {
+        if (alive && m < M && n0 < N) {
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -325,7 +335,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       // warp reads 1 KB of CONTIGUOUS remote shared memory per partial tile (a row-per-thread mapping measured 8 GB/s
       // over DSMEM: 32 different 128-byte lines per request) and stores coalesced 16-byte pieces of output rows.
       const int et = (warp - 4) * 32 + lane;
-      const int rows_per = SK_BM / CS;
+      const int rows_per = BM / CS;
       constexpr int GPR = BN / 8;
       const uint32_t dump_local = smem_u32(dump);
       for (int it = et; it < rows_per * GPR; it += EPI_THREADS_SK) {
@@ -373,18 +383,18 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------ host
-template <int BN, int STAGES>
+template <int BM, int BN, int STAGES>
 static int launch_skinny(const CUtensorMap& ma, const CUtensorMap& mb, int M, int N, int K, const TcEpilogue& ep, int cs,
                          cudaStream_t stream) {
-  using Cfg = SkCfg<BN, STAGES>;
+  using Cfg = SkCfg<BM, BN, STAGES>;
   static PerDeviceOnce configured;  // function attributes are per device
   if (configured.first_use()) {
-    WF_CHECK_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    WF_CHECK_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<BM, BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::SMEM_BYTES));
   }
   const int tiles = (N + BN - 1) / BN;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(tiles * cs, (M + SK_BM - 1) / SK_BM);
+  cfg.gridDim = dim3(tiles * cs, (M + BM - 1) / BM);
   cfg.blockDim = dim3(SK_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
@@ -408,7 +418,7 @@ static int launch_skinny(const CUtensorMap& ma, const CUtensorMap& mb, int M, in
   }
   cfg.attrs = attr;
   cfg.numAttrs = n;
-  WF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_skinny_kernel<BN, STAGES>, ma, mb, M, N, K, ep, cs));
+  WF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_skinny_kernel<BM, BN, STAGES>, ma, mb, M, N, K, ep, cs));
   count_launch();
   return WF_OK;
 }
@@ -424,15 +434,17 @@ static int launch_skinny(const CUtensorMap& ma, const CUtensorMap& mb, int M, in
 // its own - the weights are read once from HBM and then from L2.  Up to 4 row tiles; above, the persistent large-tile
 // kernels of gemm_tc.cu / gemm_tc2.cu take over.
 static constexpr int SK_MAX_M_TILES = 4;
-bool skinny_plan(int M, int N, int K, int tile_hint, int* bn_out, int* cs_out) {
+bool skinny_plan(int M, int N, int K, int tile_hint, int* bn_out, int* cs_out, int* bm_out) {
   if (M > SK_BM * SK_MAX_M_TILES) return false;
   const int m_tiles = (M + SK_BM - 1) / SK_BM;
-  static int mode = -1, force_cs = -1;
+  static int mode = -1, force_cs = -1, force_bm = -1;
   if (mode < 0) {
     const char* e = getenv("WF_SKINNY");  // 0: use the persistent kernel of gemm_tc.cu instead (A/B measurements)
     mode = e ? atoi(e) : 1;
     const char* c = getenv("WF_SKINNY_CS");
     force_cs = c ? atoi(c) : 0;
+    const char* b = getenv("WF_SKINNY_BM");  // 64 / 128: force the row tile (A/B measurements)
+    force_bm = b ? atoi(b) : 0;
   }
   if (mode == 0) return false;
   const int sms = num_sms();
@@ -441,39 +453,70 @@ bool skinny_plan(int M, int N, int K, int tile_hint, int* bn_out, int* cs_out) {
   int cs = rounds >= 32 ? 4 : 1;
   if (force_cs) cs = force_cs;
   while (cs > 1 && cs > rounds) cs >>= 1;
+  bool found = false;
   for (;; cs >>= 1) {
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 4 && !found; ++i) {
       const int bn = bns[i];
       if (tile_hint && bn != tile_hint) continue;
       const int tiles = (N + bn - 1) / bn;
       if (tiles * cs * m_tiles > sms) continue;
       *bn_out = bn;
       *cs_out = cs;
-      return true;
+      *bm_out = SK_BM;
+      found = true;
     }
-    if (cs == 1) return false;
+    if (found || cs == 1) break;
   }
+  // 64-row tiles on twice the CTAs (no K split): taken when a CTA then pulls fewer bytes, (BM + BN) x K x 2
+  if (force_bm != 128 && (!found || *cs_out == 1)) {
+    const int m_tiles64 = (M + 63) / 64;
+    for (int i = 0; i < 3; ++i) {
+      const int bn = bns[i];
+      if (tile_hint && bn != tile_hint) continue;
+      const int tiles = (N + bn - 1) / bn;
+      if (tiles * m_tiles64 > sms) continue;
+      if (!found || M <= 64 || 64 + bn < SK_BM + *bn_out || force_bm == 64) {
+        *bn_out = bn;
+        *cs_out = 1;
+        *bm_out = 64;
+        found = true;
+      }
+      break;
+    }
+  }
+  return found;
 }
 
 int linear_bf16_skinny(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K,
-                       const TcEpilogue& ep, int bn, int cs, cudaStream_t stream) {
+                       const TcEpilogue& ep, int bm, int bn, int cs, cudaStream_t stream) {
   CUtensorMap ma, mb;
-  int rc = make_map_bf16(&ma, A, M, K, lda, SK_BM);
+  int rc = make_map_bf16(&ma, A, M, K, lda, bm);
   if (rc) return rc;
   rc = make_map_bf16(&mb, W, N, K, ldw, bn);
   if (rc) return rc;
+  if (bm == 64) {
+    WF_REQUIRE(cs == 1, "linear (skinny): 64-row tiles do not split K");
+    switch (bn) {
+      case 32: return launch_skinny<64, 32, 4>(ma, mb, M, N, K, ep, cs, stream);
+      case 64: return launch_skinny<64, 64, 4>(ma, mb, M, N, K, ep, cs, stream);
+      case 128: return launch_skinny<64, 128, 3>(ma, mb, M, N, K, ep, cs, stream);
+      default:
+        set_error("linear (skinny): unsupported tile 64 x %d", bn);
+        return WF_ERR_UNSUPPORTED;
+    }
+  }
   static int small = -1;  // WF_SKINNY_SMALL=1: <= 100 KB of shared memory per CTA, so that a GEMM CTA fits on an SM next to
   if (small < 0) {        // one K/V-streaming attention CTA of another sub-batch (SplitSession)
     const char* e = getenv("WF_SKINNY_SMALL");
     small = e ? atoi(e) : 0;
   }
-  if (small && bn == 32) return launch_skinny<32, 2>(ma, mb, M, N, K, ep, cs, stream);
-  if (small && bn == 64) return launch_skinny<64, 2>(ma, mb, M, N, K, ep, cs, stream);
+  if (small && bn == 32) return launch_skinny<128, 32, 2>(ma, mb, M, N, K, ep, cs, stream);
+  if (small && bn == 64) return launch_skinny<128, 64, 2>(ma, mb, M, N, K, ep, cs, stream);
   switch (bn) {
-    case 32: return launch_skinny<32, 4>(ma, mb, M, N, K, ep, cs, stream);
-    case 64: return launch_skinny<64, 4>(ma, mb, M, N, K, ep, cs, stream);
-    case 128: return launch_skinny<128, 3>(ma, mb, M, N, K, ep, cs, stream);
-    case 256: return launch_skinny<256, 2>(ma, mb, M, N, K, ep, cs, stream);
+    case 32: return launch_skinny<128, 32, 4>(ma, mb, M, N, K, ep, cs, stream);
+    case 64: return launch_skinny<128, 64, 4>(ma, mb, M, N, K, ep, cs, stream);
+    case 128: return launch_skinny<128, 128, 3>(ma, mb, M, N, K, ep, cs, stream);
+    case 256: return launch_skinny<128, 256, 2>(ma, mb, M, N, K, ep, cs, stream);
     default:
       set_error("linear (skinny): unsupported tile %d", bn);
       return WF_ERR_UNSUPPORTED;

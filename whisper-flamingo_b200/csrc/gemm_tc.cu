@@ -385,14 +385,14 @@ int linear_bf16_tc(const void* A, long long lda, const void* W, long long ldw, i
   ep.ln_colsum = e.ln_colsum; ep.ln_eps = e.ln_eps; ep.split_n = e.split_n; ep.C2 = e.C2;
   ep.stat_out = e.stat_out; ep.stat_in = e.stat_in; ep.stat_in_slots = e.stat_in_slots;
   {
-    int sbn = 0, scs = 1;  // decode step (one M tile): cluster split-K kernel
+    int sbn = 0, scs = 1, sbm = 128;  // decode step (a few row tiles): cluster split-K kernel
     // (row statistics travelling between GEMMs are a feature of the large-tile kernels: those calls stay there)
     const bool stats = e.stat_out != nullptr || e.stat_in != nullptr;
-    if (!(stats && M > 128) && skinny_plan(M, N, K, tile_hint, &sbn, &scs))
-      return linear_bf16_skinny(A, lda, W, ldw, M, N, K, ep, sbn, scs, stream);
+    if (!(stats && M > 128) && skinny_plan(M, N, K, tile_hint, &sbn, &scs, &sbm))
+      return linear_bf16_skinny(A, lda, W, ldw, M, N, K, ep, sbm, sbn, scs, stream);
     // a LayerNorm computed inside the GEMM exists in the skinny kernel only (the large-tile kernels take the row
     // statistics from the producing GEMM): more than one wave of 128-wide tiles rather than no plan
-    if (e.ln_colsum && !e.stat_in && M <= 512) return linear_bf16_skinny(A, lda, W, ldw, M, N, K, ep, 128, 1, stream);
+    if (e.ln_colsum && !e.stat_in && M <= 512) return linear_bf16_skinny(A, lda, W, ldw, M, N, K, ep, 128, 128, 1, stream);
   }
   WF_REQUIRE(!e.ln_colsum || (e.stat_in && e.stat_in_slots > 0),
              "linear: a fused LayerNorm over more than 128 rows needs the row statistics of the producing GEMM (M=%d)", M);

@@ -34,8 +34,11 @@
 // is reloaded (one L2 round trip) and the context accumulators alternate between two TMEM regions.
 // What bounds it (profiles/r02_latent_experiments.txt): a ring stage is occupied for (load latency under load ~2.4 us)
 // + (residency: scores of the whole tile, exchange + softmax, context MMAs ~2.3 us), so 160 KB of ring per SM turn
-// over at ~17 B/clk/SM = 4.8 TB/s.  Measured dead ends: pass A yielding the tensor pipe to pass B (118 us vs 102.5),
-// a tile-contiguous source layout (no change: DRAM page locality is not the limit), one issuer per pass (108 us).
+// over at ~17 B/clk/SM = 4.8 TB/s.  With the MMAs and the softmax removed the same ring streams the same bytes in
+// 75.0 us = 6.56 TB/s: the memory path is not the limit, the loop is.  Measured dead ends: pass A yielding the tensor
+// pipe to pass B (118 us vs 102.5), a tile-contiguous source layout (no change: DRAM page locality is not the limit),
+// one issuer per pass (108 us), L2 prefetch 1 .. 4 tiles ahead of the ring (105.9 .. 111.9 us; it slows even the bare
+// stream, 84 us).
 #include "common.cuh"
 #include "kernels.h"
 
