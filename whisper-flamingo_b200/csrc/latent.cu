@@ -611,11 +611,15 @@ int latent_query(const void* q, long long ldq, const void* wkT, void* qp, int R,
 
 // ---------------------------------------------------------------------------------------------------------------
 // o[row, 64 h + j] = sum_n c[row, h, n] * wv[64 h + j, n] + bv[64 h + j]
-// grid (H, ceil(R / 16)), 128 threads; K = d streamed in 64-column chunks through a 4-stage cp.async ring;
+// grid (H, ceil(R / 16)), 128 threads; K = d streamed in 128-column stages through a 3-stage cp.async ring;
 // warp w owns output columns 16 w .. 16 w + 15 of the head.
-static constexpr int LV_STAGES = 4;
-static constexpr int LV_A = 16 * LQ_LD;      // elements per A stage
-static constexpr int LV_B = 64 * LQ_LD;
+// K = d streamed in 128-column stages (64-column stages: twice the pipeline rounds, each a cp.async wait + block
+// barrier - measured 8.2 / 11.8 us per launch for the plain / split form at large-v2 width)
+static constexpr int LV_STAGES = 3;
+static constexpr int LV_KC = 128;            // columns per stage
+static constexpr int LV_LD = LV_KC + 8;      // smem row stride in elements (272 B: conflict-free ldmatrix)
+static constexpr int LV_A16 = 16 * LV_LD;     // elements per 16-row A tile and stage
+static constexpr int LV_B = 64 * LV_LD;
 
 __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc, bool pred) {
   const uint32_t sz = pred ? 16u : 0u;     // src-size 0: zero fill
@@ -629,34 +633,43 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // sum, with ml[(part * R + row) * 32 + head] = (reference maximum in log2 units, row sum; 0 = part absent) - what the
 // persistent pair kernel (latent_pair.cu) leaves when a clip is cut at a cluster border.  The projection is linear in
 // the context: both parts are projected and blended with the softmax weights of their segments.
-template <bool SPLIT>
+// LV_MT = 16-row MMA tiles per CTA: 16 rows while H x ceil(R / 16) CTAs fit the SMs at once, else 32 (128 rows x 20 heads
+// = 160 CTAs of 16 rows would put two CTAs on 12 of the SMs: 8.5 -> 7.3 us)
+template <bool SPLIT, int LV_MT>
 __global__ void __launch_bounds__(128)
 latent_value_kernel(const __nv_bfloat16* __restrict__ ctx, long long part_stride, const float2* __restrict__ ml,
                     const __nv_bfloat16* __restrict__ wv, long long ldw, const float* __restrict__ bv,
                     __nv_bfloat16* __restrict__ o, long long ldo, int R, int H, int d) {
   constexpr int NP = SPLIT ? 2 : 1;
-  constexpr int NST = SPLIT ? 3 : LV_STAGES;   // static shared memory stays under 48 KB with two A tiles per stage
-  __shared__ __align__(16) __nv_bfloat16 As[NP * NST * LV_A];
-  __shared__ __align__(16) __nv_bfloat16 Bs[NST * LV_B];
-  __shared__ float wgt[2][16];
-  const int h = blockIdx.x, m0 = blockIdx.y * 16;
+  constexpr int NST = LV_STAGES;
+  constexpr int LV_ROWS = 16 * LV_MT, LV_A = LV_MT * LV_A16;
+  extern __shared__ __align__(16) uint8_t lv_smem[];       // NST x (NP A tiles + one B tile): 65 KB, 78 KB in the split form
+  __nv_bfloat16* As = reinterpret_cast<__nv_bfloat16*>(lv_smem);
+  __nv_bfloat16* Bs = As + NP * NST * LV_A;
+  __shared__ float wgt[2][LV_ROWS];
+  const int h = blockIdx.x, m0 = blockIdx.y * LV_ROWS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_chunks = d / 64;
+  const int n_chunks = (d + LV_KC - 1) / LV_KC;
   const __nv_bfloat16* a_base = ctx + (static_cast<long long>(m0) * H + h) * d;       // row stride H * d
   const __nv_bfloat16* b_base = wv + static_cast<long long>(h) * 64 * ldw;
   auto load_b = [&](int kc, int st) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 8; ++i) {
       const int v = threadIdx.x + i * 128;
-      const int row = v >> 3, c8 = (v & 7) * 8;
-      cp_async_16(&Bs[st * LV_B + row * LQ_LD + c8], b_base + row * ldw + kc * 64 + c8, true);
+      const int row = v >> 4, c8 = (v & 15) * 8;
+      const bool ok = kc * LV_KC + c8 < d;      // the last stage of a width that is not a multiple of 128 is zero-filled
+      cp_async_16(&Bs[st * LV_B + row * LV_LD + c8], b_base + row * ldw + (ok ? kc * LV_KC + c8 : 0), ok);
     }
   };
   auto load_a = [&](int kc, int st, int part) {
-    const int row = threadIdx.x >> 3, c8 = (threadIdx.x & 7) * 8;
-    const bool ok = m0 + row < R;
-    cp_async_16(&As[(part * NST + st) * LV_A + row * LQ_LD + c8],
-                a_base + part * part_stride + (ok ? static_cast<long long>(row) * H * d : 0) + kc * 64 + c8, ok);
+#pragma unroll
+    for (int i = 0; i < 2 * LV_MT; ++i) {
+      const int v = threadIdx.x + i * 128;
+      const int row = v >> 4, c8 = (v & 15) * 8;
+      const bool ok = m0 + row < R && kc * LV_KC + c8 < d;
+      cp_async_16(&As[(part * NST + st) * LV_A + row * LV_LD + c8],
+                  a_base + part * part_stride + (ok ? static_cast<long long>(row) * H * d + kc * LV_KC + c8 : 0), ok);
+    }
   };
   // the weights do not depend on the previous kernel: request them before the dependency wait
   for (int s = 0; s < NST - 1; ++s)
@@ -666,7 +679,7 @@ latent_value_kernel(const __nv_bfloat16* __restrict__ ctx, long long part_stride
   if (SPLIT) {
     // blend weights of the two parts of every row: w_p = l_p 2^(m_p - max) / sum
     bool mine = false;
-    if (threadIdx.x < 16) {
+    if (threadIdx.x < LV_ROWS) {
       const int row = m0 + threadIdx.x;
       float w0 = 1.f, w1 = 0.f;
       if (row < R) {
@@ -693,13 +706,15 @@ latent_value_kernel(const __nv_bfloat16* __restrict__ ctx, long long part_stride
     }
     cp_async_commit();     // group s = {A(s)} (+ all early B loads in group 0)
   }
-  float c[NP][2][4];
+  float c[NP][LV_MT][2][4];
 #pragma unroll
   for (int p = 0; p < NP; ++p)
 #pragma unroll
-    for (int nt = 0; nt < 2; ++nt)
+    for (int mt = 0; mt < LV_MT; ++mt)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) c[p][nt][e] = 0.f;
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) c[p][mt][nt][e] = 0.f;
   for (int kc = 0; kc < n_chunks; ++kc) {
     cp_async_wait<NST - 2>();
     __syncthreads();
@@ -712,42 +727,49 @@ latent_value_kernel(const __nv_bfloat16* __restrict__ ctx, long long part_stride
     cp_async_commit();
     const int st = kc % NST;
 #pragma unroll
-    for (int kp = 0; kp < 2; ++kp) {
+    for (int kp = 0; kp < LV_KC / 32; ++kp) {
       uint32_t bf[2][4];
 #pragma unroll
       for (int nt = 0; nt < 2; ++nt)
-        ldmatrix_x4(bf[nt], &Bs[st * LV_B + ((warp * 2 + nt) * 8 + (lane & 7)) * LQ_LD + kp * 32 + (lane >> 3) * 8]);
+        ldmatrix_x4(bf[nt], &Bs[st * LV_B + ((warp * 2 + nt) * 8 + (lane & 7)) * LV_LD + kp * 32 + (lane >> 3) * 8]);
 #pragma unroll
       for (int p = 0; p < NP; ++p) {
         if (p == 1 && !second) continue;
-        uint32_t a0[4], a1[4];
-        const __nv_bfloat16* ap = &As[(p * NST + st) * LV_A];
-        ldmatrix_x4(a0, ap + (lane & 15) * LQ_LD + kp * 32 + (lane >> 4) * 8);
-        ldmatrix_x4(a1, ap + (lane & 15) * LQ_LD + kp * 32 + 16 + (lane >> 4) * 8);
 #pragma unroll
-        for (int nt = 0; nt < 2; ++nt) {
-          mma_bf16_16816(c[p][nt], a0, bf[nt][0], bf[nt][1]);
-          mma_bf16_16816(c[p][nt], a1, bf[nt][2], bf[nt][3]);
+        for (int mt = 0; mt < LV_MT; ++mt) {
+          uint32_t a0[4], a1[4];
+          const __nv_bfloat16* ap = &As[(p * NST + st) * LV_A + mt * 16 * LV_LD];
+          ldmatrix_x4(a0, ap + (lane & 15) * LV_LD + kp * 32 + (lane >> 4) * 8);
+          ldmatrix_x4(a1, ap + (lane & 15) * LV_LD + kp * 32 + 16 + (lane >> 4) * 8);
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt) {
+            mma_bf16_16816(c[p][mt][nt], a0, bf[nt][0], bf[nt][1]);
+            mma_bf16_16816(c[p][mt][nt], a1, bf[nt][2], bf[nt][3]);
+          }
         }
       }
     }
   }
   const int g = lane >> 2, t = lane & 3;
-  float wa0 = 1.f, wb0 = 1.f, wa1 = 0.f, wb1 = 0.f;     // weights of rows g (a) and g + 8 (b), parts 0 / 1
-  if (SPLIT && second) { wa0 = wgt[0][g]; wb0 = wgt[0][g + 8]; wa1 = wgt[1][g]; wb1 = wgt[1][g + 8]; }
 #pragma unroll
-  for (int nt = 0; nt < 2; ++nt) {
-    const int col = h * 64 + (warp * 2 + nt) * 8 + 2 * t;
-    const float b0 = bv ? bv[col] : 0.f, b1 = bv ? bv[col + 1] : 0.f;
-    float v0 = c[0][nt][0], v1 = c[0][nt][1], v2 = c[0][nt][2], v3 = c[0][nt][3];
-    if (SPLIT && second) {
-      v0 = wa0 * v0 + wa1 * c[NP - 1][nt][0];
-      v1 = wa0 * v1 + wa1 * c[NP - 1][nt][1];
-      v2 = wb0 * v2 + wb1 * c[NP - 1][nt][2];
-      v3 = wb0 * v3 + wb1 * c[NP - 1][nt][3];
+  for (int mt = 0; mt < LV_MT; ++mt) {
+    const int ra = mt * 16 + g, rb = ra + 8;                // rows of this thread inside the CTA's tile
+    float wa0 = 1.f, wb0 = 1.f, wa1 = 0.f, wb1 = 0.f;       // blend weights of rows ra / rb, parts 0 / 1
+    if (SPLIT && second) { wa0 = wgt[0][ra]; wb0 = wgt[0][rb]; wa1 = wgt[1][ra]; wb1 = wgt[1][rb]; }
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      const int col = h * 64 + (warp * 2 + nt) * 8 + 2 * t;
+      const float b0 = bv ? bv[col] : 0.f, b1 = bv ? bv[col + 1] : 0.f;
+      float v0 = c[0][mt][nt][0], v1 = c[0][mt][nt][1], v2 = c[0][mt][nt][2], v3 = c[0][mt][nt][3];
+      if (SPLIT && second) {
+        v0 = wa0 * v0 + wa1 * c[NP - 1][mt][nt][0];
+        v1 = wa0 * v1 + wa1 * c[NP - 1][mt][nt][1];
+        v2 = wb0 * v2 + wb1 * c[NP - 1][mt][nt][2];
+        v3 = wb0 * v3 + wb1 * c[NP - 1][mt][nt][3];
+      }
+      if (m0 + ra < R) *reinterpret_cast<uint32_t*>(o + (m0 + ra) * ldo + col) = pack_bf16(v0 + b0, v1 + b1);
+      if (m0 + rb < R) *reinterpret_cast<uint32_t*>(o + (m0 + rb) * ldo + col) = pack_bf16(v2 + b0, v3 + b1);
     }
-    if (m0 + g < R) *reinterpret_cast<uint32_t*>(o + (m0 + g) * ldo + col) = pack_bf16(v0 + b0, v1 + b1);
-    if (m0 + g + 8 < R) *reinterpret_cast<uint32_t*>(o + (m0 + g + 8) * ldo + col) = pack_bf16(v2 + b0, v3 + b1);
   }
 }
 
@@ -759,17 +781,33 @@ int latent_value(const void* ctx, long long part_stride, const float* ml, const 
                  part_stride % 8 == 0,
              "latent value: operands must be 16-byte aligned");
   WF_REQUIRE(H <= 32, "latent value: at most 32 heads");
-  dim3 grid(H, (R + 15) / 16);
+  const bool wide = H * ((R + 15) / 16) > num_sms();      // 32 rows per CTA
+  const int rows = wide ? 32 : 16;
+  dim3 grid(H, (R + rows - 1) / rows);
+  const size_t smem1 = static_cast<size_t>(LV_STAGES) * ((rows / 16) * LV_A16 + LV_B) * 2;
+  const size_t smem2 = smem1 + static_cast<size_t>(LV_STAGES) * (rows / 16) * LV_A16 * 2;
+  static PerDeviceOnce configured;  // function attributes are per device
+  if (configured.first_use()) {
+    const int big = static_cast<int>(static_cast<size_t>(LV_STAGES) * (4 * LV_A16 + LV_B) * 2);
+    WF_CHECK_CUDA(cudaFuncSetAttribute(latent_value_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    WF_CHECK_CUDA(cudaFuncSetAttribute(latent_value_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    WF_CHECK_CUDA(cudaFuncSetAttribute(latent_value_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    WF_CHECK_CUDA(cudaFuncSetAttribute(latent_value_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  }
+  const __nv_bfloat16* c16 = reinterpret_cast<const __nv_bfloat16*>(ctx);
+  const __nv_bfloat16* w16 = reinterpret_cast<const __nv_bfloat16*>(wv);
+  __nv_bfloat16* o16 = reinterpret_cast<__nv_bfloat16*>(o);
+  const float2* ml2 = reinterpret_cast<const float2*>(ml);
   if (ml != nullptr) {
-    WF_CHECK_CUDA(launch_pdl(0, latent_value_kernel<true>, grid, dim3(128), 0, stream,
-                             reinterpret_cast<const __nv_bfloat16*>(ctx), part_stride,
-                             reinterpret_cast<const float2*>(ml), reinterpret_cast<const __nv_bfloat16*>(wv), ldw, bv,
-                             reinterpret_cast<__nv_bfloat16*>(o), ldo, R, H, d));
+    if (wide) WF_CHECK_CUDA(launch_pdl(0, latent_value_kernel<true, 2>, grid, dim3(128), smem2, stream, c16, part_stride, ml2,
+                                       w16, ldw, bv, o16, ldo, R, H, d));
+    else WF_CHECK_CUDA(launch_pdl(0, latent_value_kernel<true, 1>, grid, dim3(128), smem2, stream, c16, part_stride, ml2, w16,
+                                  ldw, bv, o16, ldo, R, H, d));
   } else {
-    WF_CHECK_CUDA(launch_pdl(0, latent_value_kernel<false>, grid, dim3(128), 0, stream,
-                             reinterpret_cast<const __nv_bfloat16*>(ctx), 0LL, static_cast<const float2*>(nullptr),
-                             reinterpret_cast<const __nv_bfloat16*>(wv), ldw, bv, reinterpret_cast<__nv_bfloat16*>(o),
-                             ldo, R, H, d));
+    if (wide) WF_CHECK_CUDA(launch_pdl(0, latent_value_kernel<false, 2>, grid, dim3(128), smem1, stream, c16, 0LL, ml2, w16,
+                                       ldw, bv, o16, ldo, R, H, d));
+    else WF_CHECK_CUDA(launch_pdl(0, latent_value_kernel<false, 1>, grid, dim3(128), smem1, stream, c16, 0LL, ml2, w16, ldw,
+                                  bv, o16, ldo, R, H, d));
   }
   count_launch();
   return WF_OK;

@@ -587,7 +587,7 @@ class DecodeSession:
             self.qp = torch.empty((R, H, d), dtype=dt, device=dev)
             # full batches run the persistent one-pass kernel, which leaves a clip cut at a cluster border as two
             # partial contexts + their softmax statistics (csrc/latent_pair.cu); latent_value blends them
-            self.split = nv.latent_split_supported(H)
+            self.split = nv.latent_split_supported(H) and B > nv.device_sms() // 2
             self.ctx = torch.zeros((2 if self.split else 1, R, H, d), dtype=dt, device=dev)
             self.ctx_ml = torch.zeros((2, R, 32, 2), dtype=torch.float32, device=dev) if self.split else None
             for bp, bf in zip(p.blocks, self.fold):

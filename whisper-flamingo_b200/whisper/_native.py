@@ -380,6 +380,11 @@ def latent_query(q: torch.Tensor, wk_t: torch.Tensor, qp: torch.Tensor, h: int) 
     return qp
 
 
+def device_sms() -> int:
+    """Streaming multiprocessors of the current CUDA device."""
+    return int(load().wf_device_sms())
+
+
 def latent_split_supported(h: int) -> bool:
     """True when the one-pass pair kernel (csrc/latent_pair.cu) serves n_state = 64 h: the split form below exists."""
     return bool(load().wf_latent_split_supported(int(h)))
