@@ -276,7 +276,7 @@ def linear(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias: Optiona
                    _ptr(c_off_ptr), c_off_mul, hm[0], hm[1], hm[2], _ptr(ws),
                    0 if ws is None else ws.numel() * ws.element_size(), _ptr(ln_colsum), float(ln_eps), int(split_n),
                    _ptr(out2), _ptr(stat_out), _ptr(stat_in), 0 if stat_in is None else stat_in.shape[1])
-    fam = ("gemm_tc_bf16" if m > 256 else "gemm_tc_bf16_skinny") if dt == WF_BF16 else "gemm_f32"
+    fam = ("gemm_tc_bf16" if m > 512 else "gemm_tc_bf16_skinny") if dt == WF_BF16 else "gemm_f32"  # <= 4 row tiles: decode GEMM
     with _Prof(fam, flops=2 * m * n * k, bytes=(m * k + n * k) * a.element_size() + m * n * out.element_size()):
         _check(load().wf_linear(dt, a.data_ptr(), _row_stride(a), w.data_ptr(), _row_stride(w), m, n, k,
                                 C.byref(ep), tile_hint, _stream()))
