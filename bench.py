@@ -333,7 +333,60 @@ def profile_kernels(model, pcm_dev, feat_dev, opt, B, step_ms):
             "algorithmic_per_launch": round((f["flops"] if tensor_bound else f["bytes"]) / f["launches"], 1),
             "avg_launch_ms": round(f["ms"] / f["launches"], 4), "peak_source": pk["source"],
             "share_of_step": top["share_above_launch_floor"], "launch_floor_us": round(floor_ms * 1e3, 2)}
+    # An event pair around ONE eager launch of a 100-us kernel also holds ~10 us of launch latency (the GPU idles until
+    # the launch arrives: the same ~13 us the bracket around the 2.5-us step_advance kernel reads, `launch_floor_us`), and
+    # the kernel starts cold, without the early loads programmatic dependent launch gives it in the replayed graph of the
+    # timed region.  The dominant kernel is therefore timed again the way the timed region runs it - inside a CUDA graph -
+    # and THAT is `achieved`; the eager figure stays next to it.
+    in_graph = dominant_in_graph(model, top["kernel"], pk)
+    if in_graph:
+        roof["eager_bracketed"] = {"avg_launch_ms": roof["avg_launch_ms"], "achieved": roof["achieved"], "frac": roof["frac"]}
+        roof["avg_launch_ms"], roof["achieved"], roof["frac"] = in_graph["avg_launch_ms"], in_graph["achieved"], in_graph["frac"]
+        roof["how"] = in_graph["how"]
     return {"roofline": roof, "kernels": table, "profiled_step_ms": round(total, 2)}
+
+
+def dominant_in_graph(model, family, pk, reps=32):
+    """The dominant kernel as the timed region runs it: inside a CUDA graph (programmatic dependent launch lets its
+    first loads start under the previous kernel), 32 back-to-back launches on the decode session's own buffers
+    (491.5 MB of source rows per launch: larger than L2), bracketed by CUDA events.  The eager, per-launch-bracketed
+    figure above starts every launch cold.  Only for the latent attention families."""
+    from whisper import _engine, _native as nv
+    if not family.startswith("latent_attention_T"):
+        return None
+    sess = _engine.last_session(model.decoder)
+    if sess is None or not getattr(sess, "latent", False):
+        return None
+    t = int(family.rsplit("T", 1)[1])
+    src = sess.xa_src if sess.xa_src.shape[1] == t else next((x for x in getattr(sess, "x_src", []) if x.shape[1] == t), None)
+    if src is None:
+        return None
+    H = sess.p.n_head
+    ctx = sess.ctx if sess.split else sess.ctx[0]
+
+    def launch():
+        nv.latent_attention(sess.qp, src, ctx, H, ml=sess.ctx_ml if sess.split else None)
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        launch()
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(reps):
+            launch()
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    ach = src.numel() * 2 / (ms * 1e-3) / 1e9
+    return {"avg_launch_ms": round(ms, 4), "achieved": round(ach, 1), "frac": round(ach / pk["hbm"], 4), "launches": reps,
+            "how": "CUDA graph of back-to-back launches on the session's buffers, CUDA events around the replay"}
 
 
 # ----------------------------------------------------------------------------- reference arm / CPU baseline

@@ -1086,11 +1086,12 @@ def get_session(dec, xa: Tensor, feats: Optional[Sequence[Tensor]], n_group: int
     if os.environ.get("WF_NO_GRAPH", "0") == "1":
         n_split = 1  # per-kernel profiling mode: one eager stream
     n_feats = 0 if feats is None else len(feats)
-    cached = _SESSION_CACHE.get(dec) or []
     no_cache = os.environ.get("WF_NO_SESSION_CACHE", "0") == "1"
-    if no_cache:
-        cached = []
-        _SESSION_CACHE.pop(dec, None)
+    if no_cache:  # profiling sessions (eager, instrumented) neither use nor disturb the cached product sessions
+        if n_split > 1:
+            return SplitSession(dec, xa, feats, n_group, t_cap, n_split)
+        return DecodeSession(dec, xa, feats, n_group, t_cap)
+    cached = _SESSION_CACHE.get(dec) or []
     for i, old in enumerate(cached):
         tx = tuple(f.shape[1] for f in feats) if (old.gated and feats is not None) else ()
         key = (dt, xa.device, xa.shape[0], n_group, t_cap, xa.shape[1], tx, id(p))
@@ -1111,8 +1112,6 @@ def get_session(dec, xa: Tensor, feats: Optional[Sequence[Tensor]], n_group: int
     else:
         sess = DecodeSession(dec, xa, feats, n_group, t_cap)
     cached.insert(0, sess)
-    if no_cache:     # profiling sessions (eager, instrumented) must not be handed to a later product call
-        _SESSION_CACHE.pop(dec, None)
     return sess
 
 
