@@ -173,6 +173,96 @@ attn_decode_kernel(const T* __restrict__ q, long long ldq, const T* __restrict__
   }
 }
 
+// ---- growing self-attention cache (decode step: one query per hypothesis, a few dozen to a few hundred keys whose
+// number lives in device memory): one WARP per (hypothesis, head).  The block-per-item kernel above spends its time in
+// block barriers and launches 2560 CTAs of 128 threads for 128 x 20 items (1.08 waves of 148 x 16 resident CTAs: the
+// tail wave doubles it); here an item's K and V rows are read in fully coalesced 512-byte pieces (8 lanes x 16 B per
+// key, 4 keys per instruction), 32 keys per round with an online softmax, everything in registers and shuffles.
+//   lane = (key group kg = lane / 8, dim group dg = lane % 8);  score of key 4 i + kg after round i lives in the 8 lanes
+//   of group kg - lane (kg, dg) keeps the one of round i == dg, so each lane ends a round holding one key's score.
+static constexpr int SW_WARPS = 8;
+__global__ void __launch_bounds__(SW_WARPS * 32)
+attn_decode_warp_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const __nv_bfloat16* __restrict__ kc,
+                        const __nv_bfloat16* __restrict__ vc, long long ld_kv, long long kv_batch_stride,
+                        long long kv_head_stride, __nv_bfloat16* __restrict__ o, long long ldo, int H, int items,
+                        const int* __restrict__ len_ptr, int len_add, int len_const, const int* __restrict__ row_table,
+                        int table_ld) {
+  pdl_trigger();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int item = blockIdx.x * SW_WARPS + (threadIdx.x >> 5);
+  if (item >= items) return;
+  const int row = item / H, h = item - row * H;
+  const int len = len_ptr ? (*len_ptr + len_add) : len_const;
+  const int kg = lane >> 3, dg = lane & 7;
+  float qv[8];
+  ld8(q + static_cast<long long>(row) * ldq + h * HD + dg * 8, qv);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) qv[j] *= 0.125f;
+  const int* tbl = row_table ? row_table + static_cast<long long>(row) * table_ld : nullptr;
+  const long long own = static_cast<long long>(row) * kv_batch_stride + h * kv_head_stride + dg * 8;
+  const long long hoff = static_cast<long long>(h) * kv_head_stride + dg * 8;
+  float m_run = -INFINITY, l_run = 0.f, acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int base = 0; base < len; base += 32) {
+    // physical cache entry of key base + lane (beam search re-orders hypotheses through this table)
+    const int my_entry = (tbl && base + lane < len) ? __ldg(tbl + base + lane) : row;
+    long long koff[8];
+    float s_mine = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int key = base + 4 * i + kg;
+      const int entry = tbl ? __shfl_sync(0xffffffffu, my_entry, 4 * i + kg) : row;
+      koff[i] = (tbl ? static_cast<long long>(entry) * kv_batch_stride + hoff : own) + static_cast<long long>(key) * ld_kv;
+      float part = 0.f;
+      if (key < len) {
+        float kv[8];
+        ld8(kc + koff[i], kv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) part = fmaf(qv[j], kv[j], part);
+      }
+      part += __shfl_xor_sync(0xffffffffu, part, 1);
+      part += __shfl_xor_sync(0xffffffffu, part, 2);
+      part += __shfl_xor_sync(0xffffffffu, part, 4);
+      if (i == dg && key < len) s_mine = part;
+    }
+    // online softmax over the 32 keys of the round (lane (kg, dg) holds key base + 4 dg + kg)
+    const float m_new = fmaxf(m_run, warp_max(s_mine));
+    const float corr = __expf(m_run - m_new);      // 0 on the first round
+    const float p_mine = __expf(s_mine - m_new);   // 0 for keys beyond the length
+    l_run = l_run * corr + warp_sum(p_mine);
+    m_run = m_new;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] *= corr;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int key = base + 4 * i + kg;
+      const float p = __shfl_sync(0xffffffffu, p_mine, (kg << 3) | i);
+      if (key < len) {
+        float vv[8];
+        ld8(vc + koff[i], vv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(p, vv[j], acc[j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 8);
+    acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
+  }
+  if (kg == 0) {
+    const float inv = 1.0f / l_run;
+    uint4 u;
+    u.x = pack_bf16(acc[0] * inv, acc[1] * inv);
+    u.y = pack_bf16(acc[2] * inv, acc[3] * inv);
+    u.z = pack_bf16(acc[4] * inv, acc[5] * inv);
+    u.w = pack_bf16(acc[6] * inv, acc[7] * inv);
+    *reinterpret_cast<uint4*>(o + static_cast<long long>(row) * ldo + h * HD + dg * 8) = u;
+  }
+}
+
 // ---- head-major bf16 variant: the K (V) rows of one (audio, head) are contiguous 128-byte lines, so a tile of
 // 128 keys is one contiguous 16 KB block.  Tiles are staged in shared memory by 1-D bulk copies (cp.async.bulk,
 // mbarrier completion) three stages ahead of the math: the memory system always has 2 CTAs x 3 x 32 KB = 192 KB in
@@ -766,6 +856,26 @@ static int launch_decode_attn(const T* q, long long ldq, const T* kc, const T* v
     WF_REQUIRE(ws && ws_bytes >= static_cast<long long>(R) * H * n_splits * PART * (long long)sizeof(float),
                "attention_decode: workspace too small (need %lld bytes)",
                static_cast<long long>(R) * H * n_splits * PART * (long long)sizeof(float));
+  if constexpr (sizeof(T) == 2 && NQ == 1) {
+    // the growing self-attention cache of a decode step: warp-per-item kernel (WF_DECODE_WARP=0: the block-per-item one)
+    static int warp_kernel = -1;
+    if (warp_kernel < 0) {
+      const char* e = getenv("WF_DECODE_WARP");
+      warp_kernel = e ? atoi(e) : 1;
+    }
+    if (warp_kernel && len_ptr != nullptr && len_max <= 512 && q_group == 1 && ld_kv % 8 == 0 && ldq % 8 == 0 &&
+        ldo % 8 == 0 && kv_batch_stride % 8 == 0 && kv_head_stride % 8 == 0 &&
+        ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(kc) | reinterpret_cast<uintptr_t>(vc) |
+          reinterpret_cast<uintptr_t>(o)) & 15) == 0) {
+      const int items = R * H;
+      WF_CHECK_CUDA(launch_pdl(2, attn_decode_warp_kernel, dim3((items + SW_WARPS - 1) / SW_WARPS), dim3(SW_WARPS * 32), 0,
+                               stream, (const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)kc, (const __nv_bfloat16*)vc,
+                               ld_kv, kv_batch_stride, kv_head_stride, (__nv_bfloat16*)o, ldo, H, items, len_ptr, len_add,
+                               len_max, row_table, table_ld));
+      count_launch();
+      return WF_OK;
+    }
+  }
   if constexpr (sizeof(T) == 2) if (!row_table) {
     // head-major cache + long key range: bulk-copy pipelined kernel, one CTA streams a whole (audio, head) item
     // (measured: 5.8 TB/s unsplit vs 4.0 TB/s when the item is cut into 12 one-tile CTAs - the pipeline needs depth)
