@@ -4,9 +4,10 @@
 //
 // One CTA per (batch, head, 256-query tile) = two 128-query warpgroups A and B sharing every K/V tile:
 //   warp 0 lane 0 : TMA producer  - Q_A, Q_B once, then K/V tiles of 128 keys through a 3-stage ring
-//   warp 1 lane 0 : MMA issuer    - S_w(j) = Q_w K(j)^T (128x128x64, fp32 in TMEM), O_w += P_w(j) V(j)
-//                                   (A = P_w from shared memory, B = V as an MN-major operand), interleaved so that
-//                                   the tensor pipe works for one warpgroup while the other does its exponentials
+//   warp 1 lane 0 : MMA issuer    - S_w(j) = Q_w K(j)^T (128x128x64, fp32 in TMEM) as soon as S_w(j-1) has been read
+//   warp 3 lane 0 : MMA issuer    - O_w += P_w(j) V(j) (A = P_w from tensor memory, B = V as an MN-major operand) as
+//                                   soon as P_w(j) exists; the tensor pipe works for one warpgroup while the other does
+//                                   its exponentials
 //   warp 2        : TMEM allocator (S_A | S_B | O_A | O_B = 384 -> 512 columns)
 //   warps 4..11   : softmax warpgroups: one thread owns one query row = one TMEM lane, so row max / row sum need
 //                   no shuffles; exp2 with the 1/sqrt(64) scale folded in; P written as bf16 into a 128B-swizzled
@@ -26,6 +27,9 @@ static constexpr int FT_D = 64;       // head dim
 // (TMA fill + K and V operand reads of two warpgroups + Q) instead of 256 KB - at 128 B/clk the smem-P version spent as
 // long on shared-memory traffic (2048 clk) as on its exponentials.  The freed 64 KB become two more K/V stages.
 static constexpr bool FT_P_IN_TMEM = true;
+#ifndef FT_LAG
+#define FT_LAG 400    // clk between the first score tiles of the two warpgroups (0: 2670 us, 400: 2332, 800: 2347, 1200: 2372)
+#endif
 static constexpr int FT_STAGES = FT_P_IN_TMEM ? 5 : 3;
 static constexpr int FT_TILE = FT_N * FT_D * 2;             // 16 KB: one K (or V, or Q, or half-P) tile
 static constexpr int FT_OFF_KV = FT_WG * FT_TILE;           // after Q_A, Q_B
@@ -91,7 +95,6 @@ fa_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
   } else if (warp == 1 && lane == 0) {
     // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc_s = umma_idesc_bf16(FT_M, FT_N);        // S = Q K^T : both K-major
-    constexpr uint32_t idesc_o = umma_idesc_bf16(FT_M, FT_D, 1);     // O += P V  : B (= V) MN-major
     auto issue_s = [&](int w, int j) {   // S_w(j) = Q_w K(j)^T  (kv_full(j) already observed by the caller)
       const int st = j % FT_STAGES;
       const uint64_t q_desc = umma_desc_kmajor_sw128(smem_u32(smem + w * FT_TILE));
@@ -101,54 +104,82 @@ fa_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
         umma_f16(tmem_base + w * FT_N, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k > 0);
       umma_commit(&s_full[w]);
     };
-    auto issue_pv = [&](int w, int j) {  // O_w += P_w(j) V(j)
+    // Two issuing threads: this one only computes scores, warp 3 only accumulates P V.  With one thread walking
+    // S_A(j+1), PV_A(j), S_B(j+1), PV_B(j) in order, the scores of a warpgroup were issued only after the OTHER
+    // warpgroup's probabilities had arrived: each warpgroup idled ~750-850 of its ~3700 clk per tile waiting for S.
+    mbar_wait(q_full, 0);
+#ifdef FT_TIMING
+    long long ti_kv = 0, ti_sf = 0, ti_is = 0, tli = clock64();
+#define FT_TI(acc_) do { const long long n_ = clock64(); acc_ += n_ - tli; tli = n_; } while (0)
+#else
+#define FT_TI(acc_)
+#endif
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(&kv_full[j % FT_STAGES], (j / FT_STAGES) & 1);
+      FT_TI(ti_kv);
+      for (int w = 0; w < FT_WG; ++w) {
+        if (j > 0) mbar_wait(&s_free[w], (j - 1) & 1);   // the warpgroup has pulled S_w(j-1) out of TMEM
+        FT_TI(ti_sf);
+#if FT_LAG > 0
+        if (j == 0 && w == 1) {
+          // start warpgroup B half a period behind A: both spend half of a tile on the MUFU pipe, which they share
+          mbar_wait(&s_free[0], 0);
+          const long long t0 = clock64();
+          while (clock64() - t0 < FT_LAG) {}
+        }
+#endif
+        tc_fence_after();
+        issue_s(w, j);
+        FT_TI(ti_is);
+      }
+    }
+#ifdef FT_TIMING
+    if (blockIdx.x == 1 && blockIdx.y == 3 && blockIdx.z == 5)
+      printf("fa S issuer per tile: wait K/V %lld | wait s_free %lld | issue %lld\n", ti_kv / n_tiles, ti_sf / n_tiles, ti_is / n_tiles);
+#endif
+  } else if (warp == 3 && lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer, O += P V
+    constexpr uint32_t idesc_o = umma_idesc_bf16(FT_M, FT_D, 1);     // B (= V) MN-major
+#ifdef FT_TIMING
+    long long tpv_w = 0, tpv_i = 0;
+#endif
+    for (int j = 0; j < n_tiles; ++j) {
       const int st = j % FT_STAGES;
       const uint32_t v_addr = smem_u32(smem + FT_OFF_KV + st * 2 * FT_TILE + FT_TILE);
-      const uint32_t p_addr = smem_u32(smem + FT_OFF_P + (FT_P_IN_TMEM ? 0 : w * 2 * FT_TILE));
-      (void)p_addr;
+      for (int w = 0; w < FT_WG; ++w) {
+#ifdef FT_TIMING
+        const long long tp0 = clock64();
+#endif
+        mbar_wait(&p_full[w], j & 1);
+#ifdef FT_TIMING
+        const long long tp1 = clock64();
+        tpv_w += tp1 - tp0;
+#endif
+        tc_fence_after();
 #pragma unroll
-      for (int kk = 0; kk < FT_N / 16; ++kk) {
-        // B: V rows 16 kk .. 16 kk + 15 (two 1024-B groups)
-        const uint64_t b_desc = umma_desc_mnmajor_sw128(v_addr + kk * 2048);
-        if constexpr (FT_P_IN_TMEM) {
-          // A: 16 keys = 8 TMEM cells of this warpgroup's P region
-          umma_f16_ts(tmem_base + FT_COL_O + w * FT_D, tmem_base + FT_COL_P + w * (FT_N / 2) + kk * 8, b_desc, idesc_o,
-                      (j > 0 || kk > 0) ? 1u : 0u);
-        } else {
-          // A: P half (kk / 4) of 64 keys, 16 keys (32 B) per step
-          const uint64_t a_desc = umma_desc_kmajor_sw128(p_addr + (kk >> 2) * FT_TILE) + 2 * (kk & 3);
-          umma_f16(tmem_base + FT_COL_O + w * FT_D, a_desc, b_desc, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+        for (int kk = 0; kk < FT_N / 16; ++kk) {
+          // B: V rows 16 kk .. 16 kk + 15 (two 1024-B groups); A: 16 keys = 8 TMEM cells of this warpgroup's P region
+          const uint64_t b_desc = umma_desc_mnmajor_sw128(v_addr + kk * 2048);
+          if constexpr (FT_P_IN_TMEM) {
+            umma_f16_ts(tmem_base + FT_COL_O + w * FT_D, tmem_base + FT_COL_P + w * (FT_N / 2) + kk * 8, b_desc, idesc_o,
+                        (j > 0 || kk > 0) ? 1u : 0u);
+          } else {
+            const uint32_t p_addr = smem_u32(smem + FT_OFF_P + w * 2 * FT_TILE);
+            const uint64_t a_desc = umma_desc_kmajor_sw128(p_addr + (kk >> 2) * FT_TILE) + 2 * (kk & 3);
+            umma_f16(tmem_base + FT_COL_O + w * FT_D, a_desc, b_desc, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+          }
         }
+        umma_commit(&o_done[w]);
+#ifdef FT_TIMING
+        tpv_i += clock64() - tp1;
+#endif
       }
-      umma_commit(&o_done[w]);
-    };
-    mbar_wait(q_full, 0);
-    mbar_wait(&kv_full[0], 0);
-    tc_fence_after();
-    issue_s(0, 0);
-    issue_s(1, 0);
-    for (int j = 0; j < n_tiles; ++j) {
-      const uint32_t ph = j & 1;
-      const bool more = j + 1 < n_tiles;
-      if (more) {
-        mbar_wait(&kv_full[(j + 1) % FT_STAGES], ((j + 1) / FT_STAGES) & 1);
-        mbar_wait(&s_free[0], ph);        // warpgroup A has pulled S_A(j) out of TMEM
-        tc_fence_after();
-        issue_s(0, j + 1);
-      }
-      mbar_wait(&p_full[0], ph);
-      tc_fence_after();
-      issue_pv(0, j);
-      if (more) {
-        mbar_wait(&s_free[1], ph);
-        tc_fence_after();
-        issue_s(1, j + 1);
-      }
-      mbar_wait(&p_full[1], ph);
-      tc_fence_after();
-      issue_pv(1, j);
-      umma_commit(&kv_empty[j % FT_STAGES]);  // both warpgroups are done with K(j), V(j)
+      umma_commit(&kv_empty[st]);  // both warpgroups are done with K(j), V(j) (their S(j) completed before P(j) existed)
     }
+#ifdef FT_TIMING
+    if (blockIdx.x == 1 && blockIdx.y == 3 && blockIdx.z == 5)
+      printf("fa PV issuer per tile: wait P %lld | issue %lld\n", tpv_w / n_tiles, tpv_i / n_tiles);
+#endif
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ softmax / correction / epilogue
     const int w = (warp - 4) >> 2;                                   // warpgroup = query tile
@@ -161,11 +192,19 @@ fa_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
     (void)p_buf;
     const float sl2 = 0.125f * 1.44269504088896340736f;              // 64^-0.5 * log2(e)
     float m_run = -INFINITY, l_run = 0.f;
+#ifdef FT_TIMING
+    long long t_w = 0, t_ld = 0, t_max = 0, t_exp = 0, t_od = 0, t_st = 0, tl = clock64();
+    const long long tt0 = tl;
+#define FT_T(acc_) do { const long long n_ = clock64(); acc_ += n_ - tl; tl = n_; } while (0)
+#else
+#define FT_T(acc_)
+#endif
     for (int j = 0; j < n_tiles; ++j) {
       const uint32_t ph = j & 1;
       const int kbase = j * FT_N;
       const bool tail = kbase + FT_N > Tk;
       mbar_wait(&s_full[w], ph);
+      FT_T(t_w);
       tc_fence_after();
       // one pass over TMEM: the whole 128-wide score row of this thread goes to registers
       uint32_t sv[4][32];
@@ -174,6 +213,7 @@ fa_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&s_free[w]);                                       // the tensor core may overwrite S_w now
+      FT_T(t_ld);
       if (tail) {
 #pragma unroll
         for (int c = 0; c < 4; ++c)
@@ -189,6 +229,7 @@ fa_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
       const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       const float alpha = ex2_approx((m_run - mx) * sl2);            // 0 on the first tile (m_run = -inf)
       const float msc = mx * sl2;
+      FT_T(t_max);
       // p = exp2(s * sl2 - m * sl2), packed to bf16 pairs in place (overlaps the P V MMA of the previous tile)
       float ps4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -201,6 +242,7 @@ fa_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
           sv[c][i >> 1] = pack_bf16(e0, e1);                          // slot i/2 <= i: already consumed
         }
       const float psum = (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
+      FT_T(t_exp);
       // O *= alpha (only when some row of this warp moved its max); PV_w(j-1) must have completed first
       if (j > 0) {
         mbar_wait(&o_done[w], (j - 1) & 1);
@@ -221,6 +263,7 @@ fa_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
       }
       l_run = l_run * alpha + psum;
       m_run = mx;
+      FT_T(t_od);
       if constexpr (FT_P_IN_TMEM) {
         // P -> tensor memory: this thread's row, 64 cells of two bf16; the previous reader PV_w(j-1) has completed
         // (o_done was waited for above, or this is the first tile)
@@ -248,7 +291,14 @@ fa_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
       }
       tc_fence_before();
       mbar_arrive(&p_full[w]);
+      FT_T(t_st);
     }
+#ifdef FT_TIMING
+    if (blockIdx.x == 1 && blockIdx.y == 3 && blockIdx.z == 5 && lane == 0 && (warp & 3) == 0)
+      printf("fa wg%d per tile: wait S %lld | tmem ld %lld | max %lld | exp %lld | wait PV(j-1) + rescale %lld | P store %lld ; total %lld\n",
+             w, t_w / n_tiles, t_ld / n_tiles, t_max / n_tiles, t_exp / n_tiles, t_od / n_tiles, t_st / n_tiles,
+             (clock64() - tt0) / n_tiles);
+#endif
     // ---- epilogue: O / l -> bf16 -> global (one 128-byte row segment per thread)
     mbar_wait(&o_done[w], (n_tiles - 1) & 1);
     tc_fence_after();
