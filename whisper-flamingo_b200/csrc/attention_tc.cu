@@ -27,6 +27,12 @@ static constexpr int FT_D = 64;       // head dim
 // (TMA fill + K and V operand reads of two warpgroups + Q) instead of 256 KB - at 128 B/clk the smem-P version spent as
 // long on shared-memory traffic (2048 clk) as on its exponentials.  The freed 64 KB become two more K/V stages.
 static constexpr bool FT_P_IN_TMEM = true;
+#ifndef FT_MXC
+#define FT_MXC 16     // independent FMNMX chains of the row maximum (4: 2262 us, 8: 2258, 16: 2236)
+#endif
+#ifndef FT_LAZY
+#define FT_LAZY 1      // lazy reference maximum (0: 2334 us, 1: 2267)
+#endif
 #ifndef FT_LAG
 #define FT_LAG 400    // clk between the first score tiles of the two warpgroups (0: 2670 us, 400: 2332, 800: 2347, 1200: 2372)
 #endif
@@ -221,13 +227,24 @@ fa_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
           for (int i = 0; i < 32; ++i)
             if (kbase + c * 32 + i >= Tk) sv[c][i] = 0xff800000u;  // -inf: masked key
       }
-      float mx4[4] = {m_run, -INFINITY, -INFINITY, -INFINITY};      // four independent chains (one warp per SMSP:
-#pragma unroll                                                      //  dependency latency is not hidden by TLP)
+      // FT_MXC independent chains (one warp per SMSP: dependency latency is not hidden by TLP)
+      float mxc[FT_MXC];
+#pragma unroll
+      for (int i = 0; i < FT_MXC; ++i) mxc[i] = -INFINITY;
+      mxc[0] = m_run;
+#pragma unroll
       for (int c = 0; c < 4; ++c)
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(sv[c][i]));
-      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-      const float alpha = ex2_approx((m_run - mx) * sl2);            // 0 on the first tile (m_run = -inf)
+        for (int i = 0; i < 32; ++i) mxc[i % FT_MXC] = fmaxf(mxc[i % FT_MXC], __uint_as_float(sv[c][i]));
+      float mx = mxc[0];
+#pragma unroll
+      for (int i = 1; i < FT_MXC; ++i) mx = fmaxf(mx, mxc[i]);
+#if FT_LAZY
+      // the reference of a row only moves when its maximum leaves a window of 2^8 above it (probabilities stay below 256:
+      // exact in the fp32 row sum, harmless in bf16): the O rescale - two TMEM round trips - disappears from most tiles
+      if ((mx - m_run) * sl2 <= 8.0f) mx = m_run;                    // never on the first tile (m_run = -inf)
+#endif
+      const float alpha = ex2_approx((m_run - mx) * sl2);            // 0 on the first tile; 1 when the reference stays
       const float msc = mx * sl2;
       FT_T(t_max);
       // p = exp2(s * sl2 - m * sl2), packed to bf16 pairs in place (overlaps the P V MMA of the previous tile)
