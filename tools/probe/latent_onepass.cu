@@ -1,3 +1,9 @@
+// NOT PART OF THE LIBRARY - kept as the record of a measured dead end (profiles/r02_latent_experiments.txt, section 2).
+// One-pass latent attention with the whole 64-key tile (160 KB at d = 1280) resident in ONE SM: the ring holds a single
+// tile, so load latency, both products and the softmax hand-off of every tile run in series: 210-218 us against 114 us
+// for the two-pass kernel and 102.7 us for the 2-CTA-cluster kernel that replaced it (csrc/latent_pair.cu).  It was
+// parity-green (tests/test_kernels_gpu.py -k latent) when it was wired into csrc/latent.cu.
+//
 // One-token cross-attention over the source rows, ONE pass: the 64-key tile stays in shared memory between the score
 // product and the context product.  Same contract as latent_attn_kernel (latent.cu: q' = Wk_h^T q_h, context
 // c_h = softmax(src q'_h / 8)^T src); replaces the per-step recompute of reference whisper/decoding.py:155-164 for the
