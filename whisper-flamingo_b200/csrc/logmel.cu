@@ -10,8 +10,23 @@
 // iteration.  Kernel 2 (logmel_finish_kernel) applies the max-8 clamp and the affine rescale in
 // place; it is a pure streaming pass whose working set is normally still L2-resident.
 // The intermediate 201 x 3000 complex spectrogram of the reference never touches HBM.
+//
+// logmel_fft2_kernel (round 2, the default) is the same arithmetic laid out the other way round: a LANE is a frame
+// pair and a WARP is a DFT row.  A CTA of 20 warps takes 64 consecutive frames (lane p: frames f0+p and f0+32+p as
+// the real and imaginary part of one complex sequence); warp t runs the 20-point column transform n = 20 n1 + t of
+// 32 pairs at once, then warp k1 the row transform.  Everything indexed by t, k1, n2 or the mel row is therefore
+// warp-uniform: window, twiddles and filter weights are broadcast shared-memory loads at immediate offsets, the
+// transposes are conflict-free [index][lane] arrays, the output row of a mel bin is one coalesced 128-byte store
+// straight from registers, and no per-element integer arithmetic is left (the first kernel spent 44 % of its issue
+// slots on it: 20-thread groups straddling warps, reflect arithmetic on all 800 loads of a pair, a scalar sparse
+// filterbank walk).  The PCM of the next group is staged with cp.async (4-byte, into hop rows padded to 161 words so
+// that a warp's 32 frames hit 32 banks) while the current one is transformed; only the two real spectra's upper
+// halves cross warps (row k1 needs row 20-k1), the power spectrum goes through shared memory once for the filterbank.
 #include "common.cuh"
 #include "kernels.h"
+#include <algorithm>
+#include <cstdlib>
+#include <utility>
 #include <vector>
 
 namespace wf {
@@ -33,6 +48,14 @@ struct MelTables {
   short off[2][128];    // offset into w
   float w[2][MAX_W];
   int nnz[2];
+  // ---- second layout (logmel_fft2_kernel)
+  float2 twt[20][20];          // twt[t][k1] = W400^(t k1)
+  float wint[20][20];          // wint[t][n1] = hann[20 n1 + t]
+  float w4[2][MAX_W];          // filter rows padded to multiples of 4 weights, scaled by 1/4 (|2X|^2 -> |X|^2)
+  short cnt4[2][128];          // quads per row
+  short off4[2][128];          // offset of a row in w4 (multiple of 4)
+  short assign[2][20][8];      // mel rows of warp w (snake deal by length, -1 terminated)
+  int nnz4[2];
 };
 __device__ MelTables g_tab;
 static bool g_filters_set[PerDeviceOnce::MAX_DEV][2] = {};  // the __device__ table exists once per device
@@ -48,6 +71,11 @@ int logmel_set_filters(int n_mels, const float* dense) {
       host.tw[j] = make_float2((float)cos(a), (float)(-sin(a)));
       host.win[j] = (float)(0.5 - 0.5 * cos(a));
     }
+    for (int t = 0; t < 20; ++t)
+      for (int i = 0; i < 20; ++i) {
+        host.twt[t][i] = host.tw[(t * i) % NFFT];
+        host.wint[t][i] = host.win[20 * i + t];
+      }
     g_consts_set = true;
   }
   int off = 0;
@@ -63,6 +91,30 @@ int logmel_set_filters(int n_mels, const float* dense) {
     for (int k = lo; k <= hi; ++k) host.w[set][off++] = dense[m * NBINS + k];
   }
   host.nnz[set] = off;
+  {  // padded rows + a balanced deal of the rows to the 20 warps (longest first, snake order)
+    int o4 = 0;
+    std::vector<int> order(n_mels);
+    for (int m = 0; m < n_mels; ++m) {
+      const int cnt = host.count[set][m], q = (cnt + 3) / 4;
+      WF_REQUIRE(o4 + 4 * q <= MAX_W, "mel filterbank too dense for the padded table");
+      host.off4[set][m] = (short)o4;
+      host.cnt4[set][m] = (short)q;
+      for (int j = 0; j < 4 * q; ++j)
+        host.w4[set][o4 + j] = j < cnt ? 0.25f * host.w[set][host.off[set][m] + j] : 0.f;
+      o4 += 4 * q;
+      order[m] = m;
+    }
+    host.nnz4[set] = o4;
+    std::stable_sort(order.begin(), order.end(),
+                     [&](int a, int b) { return host.cnt4[set][a] > host.cnt4[set][b]; });
+    WF_REQUIRE(n_mels <= 20 * 8, "too many mel rows for the warp assignment table");
+    for (int w = 0; w < 20; ++w)
+      for (int s2 = 0; s2 < 8; ++s2) host.assign[set][w][s2] = -1;
+    for (int i = 0; i < n_mels; ++i) {
+      const int round = i / 20, pos = i % 20;
+      host.assign[set][(round & 1) ? 19 - pos : pos][round] = (short)order[i];
+    }
+  }
   // `host` accumulates both sets; the upload replaces the current device's whole table.  A set uploaded earlier to
   // ANOTHER device only is not valid here until it has been set on this device too.
   WF_CHECK_CUDA(cudaMemcpyToSymbol(g_tab, &host, sizeof(MelTables)));
@@ -238,6 +290,273 @@ logmel_fft_kernel(const float* __restrict__ pcm, long long clip_stride, int n_sa
   if (tid == 0 && block_max > -3.0e38f) atomicMax(max_keys + n_clips, float_key(block_max));
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Second layout: lane = frame pair, warp = DFT row (see the header).  Complex values travel as packed f32x2 register
+// pairs: Blackwell's FADD2 / FMUL2 / FFMA2 do both components in one issue slot.
+static constexpr int NW2 = 20;                   // warps per CTA = rows / columns of the 20 x 20 transform
+static constexpr int TH2 = NW2 * 32;             // 640 threads
+static constexpr int GF2 = 64;                   // frames per group
+static constexpr int PROW = 161;                 // padded hop row of the staged PCM (161 = 1 mod 32)
+static constexpr int PCM_ROWS = 66;
+static constexpr int GSAMP = (GF2 - 1) * HOP + NFFT;   // 10480 samples feed 64 frames
+static constexpr int PK = 204;                   // power-spectrum rows (201 bins + quad padding)
+static constexpr int SLOTS = 8;                  // mel rows per warp, at most
+
+typedef unsigned long long c2;                   // (re, im) or (frame a, frame b) as one f32x2 operand
+__device__ __forceinline__ c2 pk(float x, float y) { c2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y)); return r; }
+__device__ __forceinline__ void upk(c2 v, float& x, float& y) { asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v)); }
+__device__ __forceinline__ c2 add2(c2 a, c2 b) { c2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ c2 sub2(c2 a, c2 b) { c2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ c2 mul2(c2 a, c2 b) { c2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ c2 fma2(c2 a, c2 b, c2 c) {
+  c2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r;
+}
+// -i (a - b) = (a.y - b.y, b.x - a.x): the one place where the components cross
+__device__ __forceinline__ c2 rotsub(c2 a, c2 b) {
+  float ax, ay, bx, by; upk(a, ax, ay); upk(b, bx, by);
+  return pk(ay - by, bx - ax);
+}
+struct Dft5Consts { c2 c1, c2_, s1, s2, ns1; };
+__device__ __forceinline__ void dft4p(c2& a0, c2& a1, c2& a2, c2& a3) {
+  const c2 t0 = add2(a0, a2), t1 = sub2(a0, a2), t2 = add2(a1, a3), t3r = rotsub(a1, a3);
+  a0 = add2(t0, t2);
+  a2 = sub2(t0, t2);
+  a1 = add2(t1, t3r);   // t1 - i t3
+  a3 = sub2(t1, t3r);   // t1 + i t3
+}
+__device__ __forceinline__ void dft5p(c2& a0, c2& a1, c2& a2, c2& a3, c2& a4, const Dft5Consts& k) {
+  const c2 s14 = add2(a1, a4), s23 = add2(a2, a3), d14r = rotsub(a1, a4), d23r = rotsub(a2, a3);
+  const c2 r1 = fma2(s23, k.c2_, fma2(s14, k.c1, a0));
+  const c2 r2 = fma2(s23, k.c1, fma2(s14, k.c2_, a0));
+  const c2 i1r = fma2(d23r, k.s2, mul2(d14r, k.s1));    // -i (s1 d14 + s2 d23)
+  const c2 i2r = fma2(d23r, k.ns1, mul2(d14r, k.s2));   // -i (s2 d14 - s1 d23)
+  a0 = add2(a0, add2(s14, s23));
+  a1 = add2(r1, i1r);
+  a4 = sub2(r1, i1r);
+  a2 = add2(r2, i2r);
+  a3 = sub2(r2, i2r);
+}
+// the 20-point prime-factor transform of dft20() on packed values
+__device__ __forceinline__ void dft20p(c2 (&v)[20], c2 (&o)[20], const Dft5Consts& k) {
+#pragma unroll
+  for (int n2 = 0; n2 < 5; ++n2)
+    dft4p(v[(4 * n2) % 20], v[(5 + 4 * n2) % 20], v[(10 + 4 * n2) % 20], v[(15 + 4 * n2) % 20]);
+#pragma unroll
+  for (int k1 = 0; k1 < 4; ++k1)
+    dft5p(v[(5 * k1) % 20], v[(5 * k1 + 4) % 20], v[(5 * k1 + 8) % 20], v[(5 * k1 + 12) % 20], v[(5 * k1 + 16) % 20], k);
+#pragma unroll
+  for (int k1 = 0; k1 < 4; ++k1)
+#pragma unroll
+    for (int k2 = 0; k2 < 5; ++k2) o[(5 * k1 + 16 * k2) % 20] = v[(5 * k1 + 4 * k2) % 20];
+}
+
+template <int NMELS>
+struct MelSmem2 {
+  c2 S[NFFT * 32];              // [k1][n2][lane] between the stages; its first half is reused as X[row][kk][lane]
+  c2 P[PK * 32];                // [bin][lane]: (|2 X_a|^2, |2 X_b|^2)
+  float pcm[PCM_ROWS * PROW];
+  float2 twt[NFFT];             // [t][k1]
+  c2 win2[NFFT];                // [t][n1]: (h, h)
+  __align__(16) c2 w4[MAX_W];   // (w, w), rows padded to quads
+  int4 slot[NW2][SLOTS];        // {byte offset of the first bin in P, byte offset of the row in w4, quads, mel row or -1}
+};
+
+template <int Q>
+__device__ __forceinline__ void cp_async4_q(uint32_t dst, const float* src) {   // element tid + 640 Q of a group
+  asm volatile("cp.async.ca.shared.global [%0 + %2], [%1 + %3], 4;" ::"r"(dst), "l"(src), "n"(Q * 4 * PROW * 4),
+               "n"(Q * TH2 * 4) : "memory");
+}
+template <int... Q>
+__device__ __forceinline__ void cp_async4_seq(uint32_t dst, const float* src, std::integer_sequence<int, Q...>) {
+  (cp_async4_q<Q>(dst, src), ...);
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ float log10_fast(float x) {   // x >= 1e-10: lg2.approx is within 2^-22 of log2
+  float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return 0.30102999566398120f * r;
+}
+
+template <int NMELS>
+__global__ void __launch_bounds__(TH2, 1)
+logmel_fft2_kernel(const float* __restrict__ pcm, long long clip_stride, int n_samples, int n_frames, int n_clips,
+                   int groups_per_clip, float* __restrict__ out, int* __restrict__ max_keys) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  MelSmem2<NMELS>& sm = *reinterpret_cast<MelSmem2<NMELS>*>(smem_raw);
+  constexpr int SET = NMELS == 80 ? 0 : 1;
+  const int tid = threadIdx.x;
+  const int w = tid >> 5, p = tid & 31;
+  for (int i = tid; i < NFFT; i += TH2) {
+    sm.twt[i] = g_tab.twt[i / 20][i % 20];
+    const float h = g_tab.wint[i / 20][i % 20];
+    sm.win2[i] = pk(h, h);
+  }
+  for (int i = tid; i < g_tab.nnz4[SET]; i += TH2) { const float c = g_tab.w4[SET][i]; sm.w4[i] = pk(c, c); }
+  for (int i = tid; i < NW2 * SLOTS; i += TH2) {
+    const int m = g_tab.assign[SET][i / SLOTS][i % SLOTS];
+    int4 d = make_int4(0, 0, 0, -1);
+    if (m >= 0) d = make_int4(g_tab.start[SET][m] * 32 * 8, g_tab.off4[SET][m] * 8, g_tab.cnt4[SET][m], m);
+    sm.slot[i / SLOTS][i % SLOTS] = d;
+  }
+  for (int i = tid; i < 3 * 32; i += TH2) sm.P[NBINS * 32 + i] = 0ull;   // the quad padding reads bins 201..203
+
+  const long long total_groups = static_cast<long long>(n_clips) * groups_per_clip;
+  const long long g_begin = total_groups * blockIdx.x / gridDim.x;
+  const long long g_end = total_groups * (blockIdx.x + 1) / gridDim.x;
+
+  // stage the 10480 samples of group g: element i = tid + 640 q sits in hop row tid / 160 + 4 q at column tid % 160
+  const int col0 = tid % HOP, row0 = tid / HOP;
+  const uint32_t dst0 = smem_u32(sm.pcm + row0 * PROW + col0);
+  auto stage = [&](long long g) {
+    const int clip = static_cast<int>(g / groups_per_clip);
+    const int f0 = static_cast<int>(g % groups_per_clip) * GF2;
+    const float* x = pcm + clip * clip_stride;
+    const int gbase = f0 * HOP - NFFT / 2;
+    if (gbase >= 0 && gbase + GSAMP <= n_samples) {
+      const float* src = x + gbase + tid;
+      cp_async4_seq(dst0, src, std::make_integer_sequence<int, 16>{});
+      if (tid < GSAMP - 16 * TH2) cp_async4_q<16>(dst0, src);
+    } else {  // first / last group of a clip: reflect at both ends (frames past n_frames read clamped garbage)
+#pragma unroll 1
+      for (int q = 0; q < 17; ++q) {
+        const int i = tid + q * TH2;
+        if (i < GSAMP) {
+          int idx = gbase + i;
+          if (idx < 0) idx = -idx;
+          if (idx >= n_samples) idx = 2 * (n_samples - 1) - idx;
+          idx = max(0, min(idx, n_samples - 1));
+          cp_async4(dst0 + q * (4 * PROW * 4), x + idx);
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  Dft5Consts kc;
+  kc.c1 = pk(0.30901699437494745f, 0.30901699437494745f);
+  kc.c2_ = pk(-0.80901699437494745f, -0.80901699437494745f);
+  kc.s1 = pk(0.95105651629515353f, 0.95105651629515353f);
+  kc.s2 = pk(0.58778525229247314f, 0.58778525229247314f);
+  kc.ns1 = pk(-0.95105651629515353f, -0.95105651629515353f);
+
+  float run_max = -3.0e38f, all_max = -3.0e38f;
+  int cur_clip = -1;
+  auto flush = [&]() {
+    const float m = warp_max(run_max);
+    if (p == 0 && cur_clip >= 0 && m > -3.0e38f) atomicMax(max_keys + cur_clip, float_key(m));
+    all_max = fmaxf(all_max, m);
+  };
+
+  __syncthreads();
+  if (g_begin < g_end) stage(g_begin);
+
+  for (long long g = g_begin; g < g_end; ++g) {
+    const int clip = static_cast<int>(g / groups_per_clip);
+    const int f0 = static_cast<int>(g % groups_per_clip) * GF2;
+    if (clip != cur_clip) { flush(); cur_clip = clip; run_max = -3.0e38f; }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();                                                       // (A) PCM of this group is in place
+
+    c2 v[20], o[20];
+    // ---- stage 1: warp w = column t; z[n] = xa[n] + i xb[n], n = 20 n1 + t, windowed
+    {
+      const float* ps = sm.pcm + p * PROW + w;
+      const c2* wn = sm.win2 + w * 20;
+#pragma unroll
+      for (int n1 = 0; n1 < 20; ++n1) {
+        const int off = (n1 / 8) * PROW + 20 * (n1 % 8);
+        v[n1] = mul2(pk(ps[off], ps[off + 32 * PROW]), wn[n1]);
+      }
+    }
+    dft20p(v, o, kc);
+    {
+      const float2* tw = sm.twt + w * 20;
+      c2* dst = sm.S + w * 32 + p;
+#pragma unroll
+      for (int k1 = 0; k1 < 20; ++k1) {
+        float x, y; upk(o[k1], x, y);
+        const float2 t = tw[k1];
+        dst[k1 * 640] = pk(x * t.x - y * t.y, x * t.y + y * t.x);
+      }
+    }
+    __syncthreads();                                                       // (B)
+    if (g + 1 < g_end) stage(g + 1);                                        // every read of sm.pcm is done
+    // ---- stage 2: warp w = row k1 gathers its 20 columns
+    {
+      const c2* src = sm.S + w * 640 + p;
+#pragma unroll
+      for (int n2 = 0; n2 < 20; ++n2) v[n2] = src[n2 * 32];
+    }
+    __syncthreads();                                                       // (C) S may be overwritten
+    dft20p(v, o, kc);                                                      // o[k2] = Z[w + 20 k2]
+    {
+      c2* X = sm.S + w * 320 + p;
+#pragma unroll
+      for (int kk = 0; kk < 10; ++kk) X[kk * 32] = o[10 + kk];
+    }
+    __syncthreads();                                                       // (D)
+    // ---- the two real spectra: 2 X_a[k] = Z[k] + conj Z[400-k], 2 X_b[k] = -i (Z[k] - conj Z[400-k]); |2X|^2 to P
+    {
+      c2* pp = sm.P + w * 32 + p;
+      auto power = [&](c2 z, c2 c) {   // with c = Z[400-k]: (ar, br) = z + c, (bi, ai) = z - c
+        float ar, br, bi2, ai2;
+        upk(add2(z, c), ar, br);
+        const c2 d = sub2(z, c);
+        upk(mul2(d, d), bi2, ai2);
+        return pk(fmaf(ar, ar, ai2), fmaf(br, br, bi2));
+      };
+      if (w == 0) {   // bins 20 k2, k2 = 0..10; the partner Z[400 - 20 k2] is in this row too
+        const c2* X = sm.S + p;
+#pragma unroll
+        for (int k2 = 0; k2 <= 10; ++k2) pp[k2 * 640] = power(o[k2], k2 == 0 ? o[0] : X[(10 - k2) * 32]);
+      } else {        // bins w + 20 k2, k2 = 0..9; partner = row 20 - w, element 19 - k2
+        const c2* X = sm.S + (20 - w) * 320 + p;
+#pragma unroll
+        for (int k2 = 0; k2 < 10; ++k2) pp[k2 * 640] = power(o[k2], X[(9 - k2) * 32]);
+      }
+    }
+    __syncthreads();                                                       // (E)
+    // ---- mel rows of this warp: filterbank, log10, store, running maximum
+    {
+      const int fa = f0 + p;
+      const bool oka = fa < n_frames, okb = fa + 32 < n_frames;
+      float* dst = out + (static_cast<long long>(clip) * NMELS) * n_frames + fa;
+      const uint32_t pbase = smem_u32(sm.P + p), wbase = smem_u32(sm.w4);
+#pragma unroll 1
+      for (int s = 0; s < SLOTS; ++s) {
+        const int4 d = sm.slot[w][s];
+        if (d.w < 0) break;
+        uint32_t qa = pbase + d.x, wq = wbase + d.y;
+        c2 acc0 = 0ull, acc1 = 0ull;
+#pragma unroll 1
+        for (int j = 0; j < d.z; ++j) {
+          c2 c0, c1, c2v, c3, q0, q1, q2, q3;
+          asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(c0), "=l"(c1) : "r"(wq));
+          asm volatile("ld.shared.v2.b64 {%0, %1}, [%2 + 16];" : "=l"(c2v), "=l"(c3) : "r"(wq));
+          asm volatile("ld.shared.b64 %0, [%1];" : "=l"(q0) : "r"(qa));
+          asm volatile("ld.shared.b64 %0, [%1 + 256];" : "=l"(q1) : "r"(qa));
+          asm volatile("ld.shared.b64 %0, [%1 + 512];" : "=l"(q2) : "r"(qa));
+          asm volatile("ld.shared.b64 %0, [%1 + 768];" : "=l"(q3) : "r"(qa));
+          acc0 = fma2(c0, q0, acc0);
+          acc1 = fma2(c1, q1, acc1);
+          acc0 = fma2(c2v, q2, acc0);
+          acc1 = fma2(c3, q3, acc1);
+          qa += 1024; wq += 32;
+        }
+        float ma, mb;
+        upk(add2(acc0, acc1), ma, mb);
+        const float va = log10_fast(fmaxf(ma, 1e-10f)), vb = log10_fast(fmaxf(mb, 1e-10f));
+        float* o2 = dst + static_cast<long long>(d.w) * n_frames;
+        if (oka) { o2[0] = va; run_max = fmaxf(run_max, va); }
+        if (okb) { o2[32] = vb; run_max = fmaxf(run_max, vb); }
+      }
+    }
+  }
+  flush();
+  if (p == 0 && all_max > -3.0e38f) atomicMax(max_keys + n_clips, float_key(all_max));
+}
+
 // out = (max(out, mx - 8) + 4) / 4 with mx = per-clip max (mode 1) or whole-tensor max (mode 0, the
 // reference's semantics for batched input: audio.py:159).
 __global__ void __launch_bounds__(256)
@@ -252,14 +571,21 @@ logmel_finish_kernel(float* __restrict__ out, long long per_clip, int n_clips, c
   if ((per_clip & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
     float4* p4 = reinterpret_cast<float4*>(p);
     const long long n4 = per_clip >> 2;
-    for (; i < n4; i += stride) {
-      float4 v = p4[i];
+    auto fix = [&](float4 v) {
       v.x = (fmaxf(v.x, floor_v) + 4.0f) * 0.25f;
       v.y = (fmaxf(v.y, floor_v) + 4.0f) * 0.25f;
       v.z = (fmaxf(v.z, floor_v) + 4.0f) * 0.25f;
       v.w = (fmaxf(v.w, floor_v) + 4.0f) * 0.25f;
-      p4[i] = v;
+      return v;
+    };
+    for (; i + 3 * stride < n4; i += 4 * stride) {   // four independent 16-byte loads in flight per thread
+      const float4 v0 = p4[i], v1 = p4[i + stride], v2 = p4[i + 2 * stride], v3 = p4[i + 3 * stride];
+      p4[i] = fix(v0);
+      p4[i + stride] = fix(v1);
+      p4[i + 2 * stride] = fix(v2);
+      p4[i + 3 * stride] = fix(v3);
     }
+    for (; i < n4; i += stride) p4[i] = fix(p4[i]);
   } else {
     for (; i < per_clip; i += stride) p[i] = (fmaxf(p[i], floor_v) + 4.0f) * 0.25f;
   }
@@ -274,19 +600,30 @@ static int launch_logmel(const float* pcm, int n_clips, int n_samples, long long
   const int groups = (n_frames + FRAMES_PER_GROUP - 1) / FRAMES_PER_GROUP;
   const long long total = static_cast<long long>(n_clips) * groups;
   const int smem = static_cast<int>(sizeof(MelSmem<NMELS>));
+  const int smem2 = static_cast<int>(sizeof(MelSmem2<NMELS>));
   static PerDeviceOnce configured;  // function attributes are per device
   if (configured.first_use()) {
     WF_CHECK_CUDA(cudaFuncSetAttribute(logmel_fft_kernel<NMELS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    WF_CHECK_CUDA(cudaFuncSetAttribute(logmel_fft2_kernel<NMELS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
   }
   WF_CHECK_CUDA(cudaMemsetAsync(keys, 0x80, (n_clips + 1) * sizeof(int), stream));
-  const long long max_grid = 2LL * num_sms();
-  const int grid = static_cast<int>(total < max_grid ? total : max_grid);
-  logmel_fft_kernel<NMELS><<<grid, THREADS, smem, stream>>>(pcm, clip_stride, n_samples, n_frames, n_clips, groups,
+  static const bool first_layout = getenv("WF_LOGMEL_V1") != nullptr;   // A/B runs only
+  if (first_layout) {
+    const long long max_grid = 2LL * num_sms();
+    const int grid = static_cast<int>(total < max_grid ? total : max_grid);
+    logmel_fft_kernel<NMELS><<<grid, THREADS, smem, stream>>>(pcm, clip_stride, n_samples, n_frames, n_clips, groups,
+                                                             out, keys);
+  } else {
+    const int groups2 = (n_frames + GF2 - 1) / GF2;
+    const long long total2 = static_cast<long long>(n_clips) * groups2;
+    const int grid = static_cast<int>(total2 < num_sms() ? total2 : num_sms());
+    logmel_fft2_kernel<NMELS><<<grid, TH2, smem2, stream>>>(pcm, clip_stride, n_samples, n_frames, n_clips, groups2,
                                                            out, keys);
+  }
   WF_CHECK_LAUNCH();
   const long long per_clip = static_cast<long long>(NMELS) * n_frames;
   long long bx = (per_clip / 4 + 255) / 256;
-  const long long want = (4LL * num_sms() + n_clips - 1) / n_clips;
+  const long long want = (8LL * num_sms() + n_clips - 1) / n_clips;
   if (bx > want) bx = want;
   if (bx < 1) bx = 1;
   dim3 fgrid(static_cast<unsigned>(bx), static_cast<unsigned>(n_clips));
