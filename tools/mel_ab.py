@@ -9,7 +9,7 @@ import whisper
 
 
 def main():
-    tag = "v1" if os.environ.get("WF_LOGMEL_V1") else "v2"
+    tag = "v1" if os.environ.get("WF_LOGMEL_V1") else ("v2" if os.environ.get("WF_LOGMEL_V2") else "v3")
     for n_mels in (80, 128):
         for B in (1, 4, 16, 128, 1024):
             pcm = torch.randn(B, 480000, device="cuda") * 0.1

@@ -557,6 +557,235 @@ logmel_fft2_kernel(const float* __restrict__ pcm, long long clip_stride, int n_s
   if (p == 0 && all_max > -3.0e38f) atomicMax(max_keys + n_clips, float_key(all_max));
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Third layout = the second one at half width, two CTAs per SM.  The 20-warp kernel runs its phases in lock step (one
+// CTA per SM, five barriers per group) and is bound by the shared-memory data pipe (ncu: LSU wavefronts 67 % of peak,
+// issue slots 45 % busy, MIO throttle + short scoreboard the top stalls).  Here a CTA is 10 warps and takes 32 frames
+// (16 pairs); a warp's two half-warps are two DFT columns (t = 2 w + h) and then the two ROWS r and 20 - r of the
+// second stage (warp 0: rows 0 and 10, their own partners), so the conjugate-partner exchange of the real-spectrum
+// split is a lane-xor-16 shuffle instead of a trip through shared memory.  The power spectrum has its own buffer:
+// three barriers per group, 110 KB per CTA, two CTAs with independent barriers per SM.
+static constexpr int NW3 = 10;
+static constexpr int TH3 = NW3 * 32;             // 320 threads
+static constexpr int GF3 = 32;                   // frames per group: lane (h, p) holds frames f0 + p and f0 + 16 + p
+static constexpr int PROW3 = 162;                // hop row padded to 2 mod 32: bank = 2 p + t + const, all 32 distinct
+static constexpr int PCM_ROWS3 = 34;
+static constexpr int GSAMP3 = (GF3 - 1) * HOP + NFFT;   // 5360 samples feed 32 frames
+
+template <int NMELS>
+struct MelSmem3 {
+  c2 S[NFFT * 16];              // [k1][n2][16] between the stages
+  c2 P[PK * 16];                // [bin][16]: (|2 X_a|^2, |2 X_b|^2)
+  float pcm[PCM_ROWS3 * PROW3];
+  __align__(16) float2 twt[NFFT];   // [t][k1]
+  __align__(16) float win[NFFT];    // [t][n1]
+  __align__(16) float w4[MAX_W];    // rows padded to quads
+  int4 slot[NW3][SLOTS][2];     // per half-warp: {byte offset of the first bin in P, byte offset in w4, quads, mel row}
+};
+
+template <int Q>
+__device__ __forceinline__ void cp_async4_q3(uint32_t dst, const float* src) {   // element tid + 320 Q of a group
+  asm volatile("cp.async.ca.shared.global [%0 + %2], [%1 + %3], 4;" ::"r"(dst), "l"(src), "n"(Q * 2 * PROW3 * 4),
+               "n"(Q * TH3 * 4) : "memory");
+}
+template <int... Q>
+__device__ __forceinline__ void cp_async4_seq3(uint32_t dst, const float* src, std::integer_sequence<int, Q...>) {
+  (cp_async4_q3<Q>(dst, src), ...);
+}
+__device__ __forceinline__ c2 shfl16(c2 v) { return __shfl_xor_sync(0xffffffffu, v, 16); }
+// (|2 X_a|^2, |2 X_b|^2) from z = Z[k] and c = Z[400 - k]: (ar, br) = z + c, (bi, ai) = z - c
+__device__ __forceinline__ c2 power2(c2 z, c2 c) {
+  float ar, br, bi2, ai2;
+  upk(add2(z, c), ar, br);
+  const c2 d = sub2(z, c);
+  upk(mul2(d, d), bi2, ai2);
+  return pk(fmaf(ar, ar, ai2), fmaf(br, br, bi2));
+}
+
+template <int NMELS>
+__global__ void __launch_bounds__(TH3, 2)
+logmel_fft3_kernel(const float* __restrict__ pcm, long long clip_stride, int n_samples, int n_frames, int n_clips,
+                   int groups_per_clip, float* __restrict__ out, int* __restrict__ max_keys) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  MelSmem3<NMELS>& sm = *reinterpret_cast<MelSmem3<NMELS>*>(smem_raw);
+  constexpr int SET = NMELS == 80 ? 0 : 1;
+  const int tid = threadIdx.x;
+  const int w = tid >> 5, lane = tid & 31, p = lane & 15, h = lane >> 4;
+  const int t = 2 * w + h;                                       // column of the first stage
+  const int r = w == 0 ? 10 * h : (h ? 20 - w : w);             // row of the second stage; the other half has 20 - r
+  for (int i = tid; i < NFFT; i += TH3) {
+    sm.twt[i] = g_tab.twt[i / 20][i % 20];
+    sm.win[i] = g_tab.wint[i / 20][i % 20];
+  }
+  for (int i = tid; i < g_tab.nnz4[SET]; i += TH3) sm.w4[i] = g_tab.w4[SET][i];
+  for (int i = tid; i < 20 * SLOTS; i += TH3) {   // virtual warp 2 w + h of the 20-way deal
+    const int vw = i / SLOTS, sl = i % SLOTS;
+    const int m = g_tab.assign[SET][vw][sl];
+    int4 d = make_int4(0, 0, 0, -1);
+    if (m >= 0) d = make_int4(g_tab.start[SET][m] * 16 * 8, g_tab.off4[SET][m] * 4, g_tab.cnt4[SET][m], m);
+    sm.slot[vw >> 1][sl][vw & 1] = d;
+  }
+  for (int i = tid; i < 3 * 16; i += TH3) sm.P[NBINS * 16 + i] = 0ull;   // the quad padding reads bins 201..203
+
+  const long long total_groups = static_cast<long long>(n_clips) * groups_per_clip;
+  const long long g_begin = total_groups * blockIdx.x / gridDim.x;
+  const long long g_end = total_groups * (blockIdx.x + 1) / gridDim.x;
+
+  // stage the 5360 samples of group g: element i = tid + 320 q sits in hop row tid / 160 + 2 q at column tid % 160
+  const int col0 = tid % HOP, row0 = tid / HOP;
+  const uint32_t dst0 = smem_u32(sm.pcm + row0 * PROW3 + col0);
+  auto stage = [&](long long g) {
+    const int clip = static_cast<int>(g / groups_per_clip);
+    const int f0 = static_cast<int>(g % groups_per_clip) * GF3;
+    const float* x = pcm + clip * clip_stride;
+    const int gbase = f0 * HOP - NFFT / 2;
+    if (gbase >= 0 && gbase + GSAMP3 <= n_samples) {
+      const float* src = x + gbase + tid;
+      cp_async4_seq3(dst0, src, std::make_integer_sequence<int, 16>{});
+      if (tid < GSAMP3 - 16 * TH3) cp_async4_q3<16>(dst0, src);
+    } else {  // first / last group of a clip: reflect at both ends (frames past n_frames read clamped garbage)
+#pragma unroll 1
+      for (int q = 0; q < 17; ++q) {
+        const int i = tid + q * TH3;
+        if (i < GSAMP3) {
+          int idx = gbase + i;
+          if (idx < 0) idx = -idx;
+          if (idx >= n_samples) idx = 2 * (n_samples - 1) - idx;
+          idx = max(0, min(idx, n_samples - 1));
+          cp_async4(dst0 + q * (2 * PROW3 * 4), x + idx);
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  Dft5Consts kc;
+  kc.c1 = pk(0.30901699437494745f, 0.30901699437494745f);
+  kc.c2_ = pk(-0.80901699437494745f, -0.80901699437494745f);
+  kc.s1 = pk(0.95105651629515353f, 0.95105651629515353f);
+  kc.s2 = pk(0.58778525229247314f, 0.58778525229247314f);
+  kc.ns1 = pk(-0.95105651629515353f, -0.95105651629515353f);
+
+  float run_max = -3.0e38f, all_max = -3.0e38f;
+  int cur_clip = -1;
+  auto flush = [&]() {
+    const float m = warp_max(run_max);
+    if (lane == 0 && cur_clip >= 0 && m > -3.0e38f) atomicMax(max_keys + cur_clip, float_key(m));
+    all_max = fmaxf(all_max, m);
+  };
+
+  __syncthreads();
+  if (g_begin < g_end) stage(g_begin);
+
+  for (long long g = g_begin; g < g_end; ++g) {
+    const int clip = static_cast<int>(g / groups_per_clip);
+    const int f0 = static_cast<int>(g % groups_per_clip) * GF3;
+    if (clip != cur_clip) { flush(); cur_clip = clip; run_max = -3.0e38f; }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();                                   // (A) PCM of this group is in place; S and P are free again
+
+    c2 v[20], o[20];
+    // ---- stage 1: half-warp = column t; z[n] = xa[n] + i xb[n], n = 20 n1 + t, windowed
+    {
+      const float* ps = sm.pcm + p * PROW3 + t;
+      const float4* wn = reinterpret_cast<const float4*>(sm.win + t * 20);
+#pragma unroll
+      for (int n4 = 0; n4 < 5; ++n4) {
+        const float4 hq = wn[n4];
+        const float hw[4] = {hq.x, hq.y, hq.z, hq.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int n1 = 4 * n4 + e;
+          const int off = (n1 / 8) * PROW3 + 20 * (n1 % 8);
+          v[n1] = pk(ps[off] * hw[e], ps[off + 16 * PROW3] * hw[e]);
+        }
+      }
+    }
+    dft20p(v, o, kc);
+    {
+      const float4* tw = reinterpret_cast<const float4*>(sm.twt + t * 20);
+      c2* dst = sm.S + t * 16 + p;
+#pragma unroll
+      for (int k2 = 0; k2 < 10; ++k2) {
+        const float4 f = tw[k2];   // twiddles of k1 = 2 k2 and 2 k2 + 1
+        float x, y;
+        upk(o[2 * k2], x, y);
+        dst[(2 * k2) * 320] = pk(x * f.x - y * f.y, x * f.y + y * f.x);
+        upk(o[2 * k2 + 1], x, y);
+        dst[(2 * k2 + 1) * 320] = pk(x * f.z - y * f.w, x * f.w + y * f.z);
+      }
+    }
+    __syncthreads();                                   // (B)
+    if (g + 1 < g_end) stage(g + 1);                    // every read of sm.pcm is done
+    // ---- stage 2: half-warp = row r gathers its 20 columns
+    {
+      const c2* src = sm.S + r * 320 + p;
+#pragma unroll
+      for (int n2 = 0; n2 < 20; ++n2) v[n2] = src[n2 * 16];
+    }
+    dft20p(v, o, kc);                                  // o[k2] = Z[r + 20 k2]
+    // ---- the two real spectra: 2 X_a[k] = Z[k] + conj Z[400-k], 2 X_b[k] = -i (Z[k] - conj Z[400-k]); |2X|^2 to P.
+    // Row r holds bins r + 20 k2 (k2 < 10); the partner Z[400 - k] is element 19 - k2 of row 20 - r = the other
+    // half-warp.  Rows 0 and 10 (warp 0) are their own partners: element (20 - k2) % 20 in row 0, 19 - k2 in row 10,
+    // and row 0 has the extra bin 200.
+    {
+      c2* pp = sm.P + r * 16 + p;
+      if (w != 0) {
+#pragma unroll
+        for (int k2 = 0; k2 < 10; ++k2) pp[k2 * 320] = power2(o[k2], shfl16(o[19 - k2]));
+      } else {
+#pragma unroll
+        for (int k2 = 0; k2 < 10; ++k2) {
+          const c2 c = h ? o[19 - k2] : o[(20 - k2) % 20];
+          pp[k2 * 320] = power2(o[k2], c);
+        }
+        if (h == 0) pp[10 * 320] = power2(o[10], o[10]);
+      }
+    }
+    __syncthreads();                                   // (E)
+    // ---- mel rows of this half-warp: filterbank, log10, store, running maximum
+    {
+      const int fa = f0 + p;
+      const bool oka = fa < n_frames, okb = fa + 16 < n_frames;
+      float* dst = out + (static_cast<long long>(clip) * NMELS) * n_frames + fa;
+      const uint32_t pbase = smem_u32(sm.P + p), wbase = smem_u32(sm.w4);
+#pragma unroll 1
+      for (int s = 0; s < SLOTS; ++s) {
+        const int4 d = sm.slot[w][s][h];
+        if (__all_sync(0xffffffffu, d.w < 0)) break;
+        uint32_t qa = pbase + d.x, wq = wbase + d.y;
+        const int nq = max(d.z, __shfl_xor_sync(0xffffffffu, d.z, 16));
+        float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+#pragma unroll 1
+        for (int j = 0; j < nq; ++j) {
+          if (j < d.z) {
+            float c0, c1, c2v, c3;
+            float2 q0, q1, q2, q3;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c0), "=f"(c1), "=f"(c2v), "=f"(c3) : "r"(wq));
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(q0.x), "=f"(q0.y) : "r"(qa));
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2 + 128];" : "=f"(q1.x), "=f"(q1.y) : "r"(qa));
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2 + 256];" : "=f"(q2.x), "=f"(q2.y) : "r"(qa));
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2 + 384];" : "=f"(q3.x), "=f"(q3.y) : "r"(qa));
+            a0 = fmaf(c0, q0.x, a0);  b0 = fmaf(c0, q0.y, b0);
+            a1 = fmaf(c1, q1.x, a1);  b1 = fmaf(c1, q1.y, b1);
+            a0 = fmaf(c2v, q2.x, a0); b0 = fmaf(c2v, q2.y, b0);
+            a1 = fmaf(c3, q3.x, a1);  b1 = fmaf(c3, q3.y, b1);
+            qa += 512; wq += 16;
+          }
+        }
+        if (d.w >= 0) {
+          const float va = log10_fast(fmaxf(a0 + a1, 1e-10f)), vb = log10_fast(fmaxf(b0 + b1, 1e-10f));
+          float* o2 = dst + static_cast<long long>(d.w) * n_frames;
+          if (oka) { o2[0] = va; run_max = fmaxf(run_max, va); }
+          if (okb) { o2[16] = vb; run_max = fmaxf(run_max, vb); }
+        }
+      }
+    }
+  }
+  flush();
+  if (lane == 0 && all_max > -3.0e38f) atomicMax(max_keys + n_clips, float_key(all_max));
+}
+
 // out = (max(out, mx - 8) + 4) / 4 with mx = per-clip max (mode 1) or whole-tensor max (mode 0, the
 // reference's semantics for batched input: audio.py:159).
 __global__ void __launch_bounds__(256)
@@ -601,14 +830,23 @@ static int launch_logmel(const float* pcm, int n_clips, int n_samples, long long
   const long long total = static_cast<long long>(n_clips) * groups;
   const int smem = static_cast<int>(sizeof(MelSmem<NMELS>));
   const int smem2 = static_cast<int>(sizeof(MelSmem2<NMELS>));
+  const int smem3 = static_cast<int>(sizeof(MelSmem3<NMELS>));
   static PerDeviceOnce configured;  // function attributes are per device
   if (configured.first_use()) {
     WF_CHECK_CUDA(cudaFuncSetAttribute(logmel_fft_kernel<NMELS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     WF_CHECK_CUDA(cudaFuncSetAttribute(logmel_fft2_kernel<NMELS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+    WF_CHECK_CUDA(cudaFuncSetAttribute(logmel_fft3_kernel<NMELS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
   }
   WF_CHECK_CUDA(cudaMemsetAsync(keys, 0x80, (n_clips + 1) * sizeof(int), stream));
   static const bool first_layout = getenv("WF_LOGMEL_V1") != nullptr;   // A/B runs only
-  if (first_layout) {
+  static const bool second_layout = getenv("WF_LOGMEL_V2") != nullptr;
+  if (!first_layout && !second_layout) {
+    const int groups3 = (n_frames + GF3 - 1) / GF3;
+    const long long total3 = static_cast<long long>(n_clips) * groups3;
+    const int grid = static_cast<int>(total3 < 2LL * num_sms() ? total3 : 2LL * num_sms());
+    logmel_fft3_kernel<NMELS><<<grid, TH3, smem3, stream>>>(pcm, clip_stride, n_samples, n_frames, n_clips, groups3,
+                                                           out, keys);
+  } else if (first_layout) {
     const long long max_grid = 2LL * num_sms();
     const int grid = static_cast<int>(total < max_grid ? total : max_grid);
     logmel_fft_kernel<NMELS><<<grid, THREADS, smem, stream>>>(pcm, clip_stride, n_samples, n_frames, n_clips, groups,
