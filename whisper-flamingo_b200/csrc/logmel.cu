@@ -56,6 +56,11 @@ struct MelTables {
   short off4[2][128];          // offset of a row in w4 (multiple of 4)
   short assign[2][20][8];      // mel rows of warp w (snake deal by length, -1 terminated)
   int nnz4[2];
+  // ---- third layout: the rows of the two half-warps of a warp are padded to a common number of quads
+  float w3[2][MAX_W];
+  short off3[2][128];
+  short nq3[2][128];
+  int nnz3[2];
 };
 __device__ MelTables g_tab;
 static bool g_filters_set[PerDeviceOnce::MAX_DEV][2] = {};  // the __device__ table exists once per device
@@ -114,6 +119,24 @@ int logmel_set_filters(int n_mels, const float* dense) {
       const int round = i / 20, pos = i % 20;
       host.assign[set][(round & 1) ? 19 - pos : pos][round] = (short)order[i];
     }
+    // third layout: virtual warps 2 w and 2 w + 1 walk their slot-s rows in lock step
+    int o3 = 0;
+    for (int vw = 0; vw < 20; vw += 2)
+      for (int s2 = 0; s2 < 8; ++s2) {
+        const int m0 = host.assign[set][vw][s2], m1 = host.assign[set][vw + 1][s2];
+        const int q = std::max(m0 >= 0 ? (int)host.cnt4[set][m0] : 0, m1 >= 0 ? (int)host.cnt4[set][m1] : 0);
+        for (int m : {m0, m1}) {
+          if (m < 0) continue;
+          WF_REQUIRE(o3 + 4 * q <= MAX_W, "mel filterbank too dense for the paired table");
+          WF_REQUIRE(host.start[set][m] + 4 * q <= 236, "mel filterbank rows too uneven for the paired table");
+          host.off3[set][m] = (short)o3;
+          host.nq3[set][m] = (short)q;
+          const int own = 4 * host.cnt4[set][m];
+          for (int j = 0; j < 4 * q; ++j) host.w3[set][o3 + j] = j < own ? host.w4[set][host.off4[set][m] + j] : 0.f;
+          o3 += 4 * q;
+        }
+      }
+    host.nnz3[set] = o3;
   }
   // `host` accumulates both sets; the upload replaces the current device's whole table.  A set uploaded earlier to
   // ANOTHER device only is not valid here until it has been set on this device too.
@@ -571,11 +594,12 @@ static constexpr int GF3 = 32;                   // frames per group: lane (h, p
 static constexpr int PROW3 = 162;                // hop row padded to 2 mod 32: bank = 2 p + t + const, all 32 distinct
 static constexpr int PCM_ROWS3 = 34;
 static constexpr int GSAMP3 = (GF3 - 1) * HOP + NFFT;   // 5360 samples feed 32 frames
+static constexpr int PK3 = 236;                  // power-spectrum rows incl. the padding the paired quad walk may read
 
 template <int NMELS>
 struct MelSmem3 {
   c2 S[NFFT * 16];              // [k1][n2][16] between the stages
-  c2 P[PK * 16];                // [bin][16]: (|2 X_a|^2, |2 X_b|^2)
+  c2 P[PK3 * 16];               // [bin][16]: (|2 X_a|^2, |2 X_b|^2); rows from 201 on stay zero (quad padding)
   float pcm[PCM_ROWS3 * PROW3];
   __align__(16) float2 twt[NFFT];   // [t][k1]
   __align__(16) float win[NFFT];    // [t][n1]
@@ -617,27 +641,28 @@ logmel_fft3_kernel(const float* __restrict__ pcm, long long clip_stride, int n_s
     sm.twt[i] = g_tab.twt[i / 20][i % 20];
     sm.win[i] = g_tab.wint[i / 20][i % 20];
   }
-  for (int i = tid; i < g_tab.nnz4[SET]; i += TH3) sm.w4[i] = g_tab.w4[SET][i];
+  for (int i = tid; i < g_tab.nnz3[SET]; i += TH3) sm.w4[i] = g_tab.w3[SET][i];
   for (int i = tid; i < 20 * SLOTS; i += TH3) {   // virtual warp 2 w + h of the 20-way deal
     const int vw = i / SLOTS, sl = i % SLOTS;
     const int m = g_tab.assign[SET][vw][sl];
     int4 d = make_int4(0, 0, 0, -1);
-    if (m >= 0) d = make_int4(g_tab.start[SET][m] * 16 * 8, g_tab.off4[SET][m] * 4, g_tab.cnt4[SET][m], m);
+    if (m >= 0) d = make_int4(g_tab.start[SET][m] * 16 * 8, g_tab.off3[SET][m] * 4, g_tab.nq3[SET][m], m);
     sm.slot[vw >> 1][sl][vw & 1] = d;
   }
-  for (int i = tid; i < 3 * 16; i += TH3) sm.P[NBINS * 16 + i] = 0ull;   // the quad padding reads bins 201..203
+  for (int i = tid; i < (PK3 - NBINS) * 16; i += TH3) sm.P[NBINS * 16 + i] = 0ull;
 
   const long long total_groups = static_cast<long long>(n_clips) * groups_per_clip;
   const long long g_begin = total_groups * blockIdx.x / gridDim.x;
-  const long long g_end = total_groups * (blockIdx.x + 1) / gridDim.x;
+  const int n_groups = static_cast<int>(total_groups * (blockIdx.x + 1) / gridDim.x - g_begin);
+  int clip = static_cast<int>(g_begin / groups_per_clip);     // of the group being transformed
+  int gi = static_cast<int>(g_begin % groups_per_clip);
 
   // stage the 5360 samples of group g: element i = tid + 320 q sits in hop row tid / 160 + 2 q at column tid % 160
   const int col0 = tid % HOP, row0 = tid / HOP;
   const uint32_t dst0 = smem_u32(sm.pcm + row0 * PROW3 + col0);
-  auto stage = [&](long long g) {
-    const int clip = static_cast<int>(g / groups_per_clip);
-    const int f0 = static_cast<int>(g % groups_per_clip) * GF3;
-    const float* x = pcm + clip * clip_stride;
+  auto stage = [&](int sclip, int sgi) {
+    const int f0 = sgi * GF3;
+    const float* x = pcm + sclip * clip_stride;
     const int gbase = f0 * HOP - NFFT / 2;
     if (gbase >= 0 && gbase + GSAMP3 <= n_samples) {
       const float* src = x + gbase + tid;
@@ -675,11 +700,10 @@ logmel_fft3_kernel(const float* __restrict__ pcm, long long clip_stride, int n_s
   };
 
   __syncthreads();
-  if (g_begin < g_end) stage(g_begin);
+  if (n_groups > 0) stage(clip, gi);
 
-  for (long long g = g_begin; g < g_end; ++g) {
-    const int clip = static_cast<int>(g / groups_per_clip);
-    const int f0 = static_cast<int>(g % groups_per_clip) * GF3;
+  for (int it = 0; it < n_groups; ++it) {
+    const int f0 = gi * GF3;
     if (clip != cur_clip) { flush(); cur_clip = clip; run_max = -3.0e38f; }
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();                                   // (A) PCM of this group is in place; S and P are free again
@@ -716,7 +740,9 @@ logmel_fft3_kernel(const float* __restrict__ pcm, long long clip_stride, int n_s
       }
     }
     __syncthreads();                                   // (B)
-    if (g + 1 < g_end) stage(g + 1);                    // every read of sm.pcm is done
+    const int out_clip = clip;
+    if (++gi == groups_per_clip) { gi = 0; ++clip; }   // the next group
+    if (it + 1 < n_groups) stage(clip, gi);             // every read of sm.pcm is done
     // ---- stage 2: half-warp = row r gathers its 20 columns
     {
       const c2* src = sm.S + r * 320 + p;
@@ -743,39 +769,37 @@ logmel_fft3_kernel(const float* __restrict__ pcm, long long clip_stride, int n_s
       }
     }
     __syncthreads();                                   // (E)
-    // ---- mel rows of this half-warp: filterbank, log10, store, running maximum
+    // ---- mel rows of this half-warp: filterbank, log10, store, running maximum.  The two half-warps of a warp walk
+    // rows padded to the same number of quads (zero weights over finite padding), so the loops carry no guards.
     {
       const int fa = f0 + p;
       const bool oka = fa < n_frames, okb = fa + 16 < n_frames;
-      float* dst = out + (static_cast<long long>(clip) * NMELS) * n_frames + fa;
+      float* dst = out + (static_cast<long long>(out_clip) * NMELS) * n_frames + fa;
       const uint32_t pbase = smem_u32(sm.P + p), wbase = smem_u32(sm.w4);
-#pragma unroll 1
-      for (int s = 0; s < SLOTS; ++s) {
+      constexpr int NS = (NMELS + 19) / 20;
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
         const int4 d = sm.slot[w][s][h];
-        if (__all_sync(0xffffffffu, d.w < 0)) break;
         uint32_t qa = pbase + d.x, wq = wbase + d.y;
-        const int nq = max(d.z, __shfl_xor_sync(0xffffffffu, d.z, 16));
         float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
 #pragma unroll 1
-        for (int j = 0; j < nq; ++j) {
-          if (j < d.z) {
-            float c0, c1, c2v, c3;
-            float2 q0, q1, q2, q3;
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c0), "=f"(c1), "=f"(c2v), "=f"(c3) : "r"(wq));
-            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(q0.x), "=f"(q0.y) : "r"(qa));
-            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2 + 128];" : "=f"(q1.x), "=f"(q1.y) : "r"(qa));
-            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2 + 256];" : "=f"(q2.x), "=f"(q2.y) : "r"(qa));
-            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2 + 384];" : "=f"(q3.x), "=f"(q3.y) : "r"(qa));
-            a0 = fmaf(c0, q0.x, a0);  b0 = fmaf(c0, q0.y, b0);
-            a1 = fmaf(c1, q1.x, a1);  b1 = fmaf(c1, q1.y, b1);
-            a0 = fmaf(c2v, q2.x, a0); b0 = fmaf(c2v, q2.y, b0);
-            a1 = fmaf(c3, q3.x, a1);  b1 = fmaf(c3, q3.y, b1);
-            qa += 512; wq += 16;
-          }
+        for (int j = 0; j < d.z; ++j) {
+          float c0, c1, c2v, c3;
+          float2 q0, q1, q2, q3;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c0), "=f"(c1), "=f"(c2v), "=f"(c3) : "r"(wq));
+          asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(q0.x), "=f"(q0.y) : "r"(qa));
+          asm volatile("ld.shared.v2.f32 {%0, %1}, [%2 + 128];" : "=f"(q1.x), "=f"(q1.y) : "r"(qa));
+          asm volatile("ld.shared.v2.f32 {%0, %1}, [%2 + 256];" : "=f"(q2.x), "=f"(q2.y) : "r"(qa));
+          asm volatile("ld.shared.v2.f32 {%0, %1}, [%2 + 384];" : "=f"(q3.x), "=f"(q3.y) : "r"(qa));
+          a0 = fmaf(c0, q0.x, a0);  b0 = fmaf(c0, q0.y, b0);
+          a1 = fmaf(c1, q1.x, a1);  b1 = fmaf(c1, q1.y, b1);
+          a0 = fmaf(c2v, q2.x, a0); b0 = fmaf(c2v, q2.y, b0);
+          a1 = fmaf(c3, q3.x, a1);  b1 = fmaf(c3, q3.y, b1);
+          qa += 512; wq += 16;
         }
         if (d.w >= 0) {
           const float va = log10_fast(fmaxf(a0 + a1, 1e-10f)), vb = log10_fast(fmaxf(b0 + b1, 1e-10f));
-          float* o2 = dst + static_cast<long long>(d.w) * n_frames;
+          float* o2 = dst + d.w * n_frames;
           if (oka) { o2[0] = va; run_max = fmaxf(run_max, va); }
           if (okb) { o2[16] = vb; run_max = fmaxf(run_max, vb); }
         }
