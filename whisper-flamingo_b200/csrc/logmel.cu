@@ -588,6 +588,10 @@ logmel_fft2_kernel(const float* __restrict__ pcm, long long clip_stride, int n_s
 // second stage (warp 0: rows 0 and 10, their own partners), so the conjugate-partner exchange of the real-spectrum
 // split is a lane-xor-16 shuffle instead of a trip through shared memory.  The power spectrum has its own buffer:
 // three barriers per group, 110 KB per CTA, two CTAs with independent barriers per SM.
+// Measured and rejected: applying the clamp + rescale inside this kernel (device-wide group queue, groups counted per
+// clip, the CTA that completes a clip rewrites its 1 MB from L2): one CTA needs ~70 us per clip whatever the number of
+// loads in flight, and the completions pile up at the end of the grid - 338 us against 226 us at 128 clips, 1866 against
+// 1745 us at 1024.  The second pass stays a kernel of its own (HBM-bound: it reads and writes the output once more).
 static constexpr int NW3 = 10;
 static constexpr int TH3 = NW3 * 32;             // 320 threads
 static constexpr int GF3 = 32;                   // frames per group: lane (h, p) holds frames f0 + p and f0 + 16 + p
@@ -815,7 +819,7 @@ logmel_fft3_kernel(const float* __restrict__ pcm, long long clip_stride, int n_s
 __global__ void __launch_bounds__(256)
 logmel_finish_kernel(float* __restrict__ out, long long per_clip, int n_clips, const int* __restrict__ max_keys,
                      int mode) {
-  const int clip = blockIdx.y;
+  const int clip = gridDim.y - 1 - blockIdx.y;   // newest clips first: their rows may still be in L2
   const float mx = key_float(mode == 1 ? max_keys[clip] : max_keys[n_clips]);
   const float floor_v = mx - 8.0f;
   float* p = out + clip * per_clip;
