@@ -39,6 +39,7 @@
 // ~32 clk per m16n8k16 (141 us).
 // Output c_h = C^T[:, h] / l_h.
 #include "common.cuh"
+#include <cstdlib>
 #include "kernels.h"
 
 namespace wf {
@@ -773,6 +774,199 @@ latent_value_kernel(const __nv_bfloat16* __restrict__ ctx, long long part_stride
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The same projection with TMA-fed operand tiles.  latent_value_kernel moves its 240 - 330 KB per CTA with 16-byte
+// cp.async: ~15 B/clk per SM whatever the ring depth (3 and 6 stages: 7.3 / 11.8 us both) - the LSU path, not latency,
+// bounds it.  Here a fifth warp feeds a ring of 128-column stages with TMA boxes (128-byte swizzle, read back by
+// ldmatrix through the same XOR), the weight boxes of the first stages before the dependency wait; the four MMA warps
+// only wait on mbarriers.  grid (H, ceil(R / 32)), 160 threads; needs d % 128 == 0.
+static constexpr int LVT_STAGES = 6;
+static constexpr int LVT_ROWS = 32;
+static constexpr int LVT_A_ATOM = LVT_ROWS * 128;      // 32 rows x 64 columns, bytes
+static constexpr int LVT_B_ATOM = 64 * 128;            // 64 output columns x 64 columns of K, bytes
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(160)
+latent_value_tma_kernel(const __grid_constant__ CUtensorMap ma0, const __grid_constant__ CUtensorMap ma1,
+                        const __grid_constant__ CUtensorMap mb, const float2* __restrict__ ml,
+                        const float* __restrict__ bv, __nv_bfloat16* __restrict__ o, long long ldo, int R, int H, int d) {
+  constexpr int NP = SPLIT ? 2 : 1;
+  constexpr int A_STAGE = 2 * LVT_A_ATOM;                 // per part
+  constexpr int STAGE = NP * A_STAGE + 2 * LVT_B_ATOM;    // 24 KB, 32 KB in the split form
+  extern __shared__ __align__(1024) uint8_t lvt_smem[];
+  __shared__ __align__(8) uint64_t full[LVT_STAGES], empty[LVT_STAGES];
+  __shared__ float wgt[2][LVT_ROWS];
+  __shared__ int second_flag;
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(lvt_smem) + 1023) & ~static_cast<uintptr_t>(1023));
+  const int h = blockIdx.x, m0 = blockIdx.y * LVT_ROWS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_chunks = d / 128;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < LVT_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 4); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == 4) {   // ---- producer
+    if (lane == 0) {
+      tma_prefetch_desc(&ma0);
+      tma_prefetch_desc(&mb);
+      const int pre = n_chunks < LVT_STAGES ? n_chunks : LVT_STAGES;
+      for (int s = 0; s < pre; ++s) {   // the weights do not depend on the previous kernel
+        uint8_t* st = ring + s * STAGE + NP * A_STAGE;
+        mbar_expect_tx(&full[s], 2 * LVT_B_ATOM);
+        tma_load_2d(st, &mb, &full[s], s * 128, h * 64);
+        tma_load_2d(st + LVT_B_ATOM, &mb, &full[s], s * 128 + 64, h * 64);
+      }
+    }
+    pdl_wait();
+    bool second = false;
+    if (SPLIT) {
+      const int row = m0 + lane;
+      const bool mine = row < R && ml[(static_cast<long long>(R) + row) * 32 + h].y > 0.f;
+      second = __any_sync(0xffffffffu, mine);
+    }
+    if (lane == 0) {
+      for (int kc = 0; kc < n_chunks; ++kc) {
+        const int s = kc % LVT_STAGES;
+        uint8_t* st = ring + s * STAGE;
+        if (kc >= LVT_STAGES) {
+          mbar_wait(&empty[s], ((kc / LVT_STAGES) - 1) & 1);
+          mbar_expect_tx(&full[s], 2 * LVT_B_ATOM);
+          tma_load_2d(st + NP * A_STAGE, &mb, &full[s], kc * 128, h * 64);
+          tma_load_2d(st + NP * A_STAGE + LVT_B_ATOM, &mb, &full[s], kc * 128 + 64, h * 64);
+        }
+        mbar_arrive_expect_tx(&full[s], (SPLIT && second ? 2 : 1) * A_STAGE);
+        tma_load_2d(st, &ma0, &full[s], h * d + kc * 128, m0);
+        tma_load_2d(st + LVT_A_ATOM, &ma0, &full[s], h * d + kc * 128 + 64, m0);
+        if (SPLIT && second) {
+          tma_load_2d(st + A_STAGE, &ma1, &full[s], h * d + kc * 128, m0);
+          tma_load_2d(st + A_STAGE + LVT_A_ATOM, &ma1, &full[s], h * d + kc * 128 + 64, m0);
+        }
+      }
+    }
+    return;
+  }
+
+  // ---- consumers: warp w owns output columns 16 w .. 16 w + 15 of the head
+  pdl_wait();
+  bool second = false;
+  if (SPLIT) {
+    if (warp == 0) {   // blend weights of the two parts of every row: w_p = l_p 2^(m_p - max) / sum
+      const int row = m0 + lane;
+      float w0 = 1.f, w1 = 0.f;
+      bool mine = false;
+      if (row < R) {
+        const float2 p0 = ml[static_cast<long long>(row) * 32 + h];
+        const float2 p1 = ml[(static_cast<long long>(R) + row) * 32 + h];
+        if (p1.y > 0.f) {
+          const float mx = fmaxf(p0.x, p1.x);
+          const float e0 = p0.y * ex2_approx(p0.x - mx), e1 = p1.y * ex2_approx(p1.x - mx);
+          const float inv = 1.0f / (e0 + e1);
+          w0 = e0 * inv;
+          w1 = e1 * inv;
+          mine = true;
+        }
+      }
+      wgt[0][lane] = w0;
+      wgt[1][lane] = w1;
+      const bool any = __any_sync(0xffffffffu, mine);
+      if (lane == 0) second_flag = any ? 1 : 0;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    second = second_flag != 0;
+  }
+  float c[2][2][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) c[mt][nt][e] = 0.f;
+  const uint32_t ring_u = smem_u32(ring);
+  // swizzled byte offsets inside an atom: row r, 16-byte chunk ch -> r * 128 + ((ch ^ (r & 7)) << 4)
+  const int a_row = lane & 15, a_ch = lane >> 4;
+  const int b_ch = lane >> 3;
+  int b_row[2];
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt) b_row[nt] = (warp * 2 + nt) * 8 + (lane & 7);
+  for (int kc = 0; kc < n_chunks; ++kc) {
+    const int s = kc % LVT_STAGES;
+    mbar_wait(&full[s], (kc / LVT_STAGES) & 1);
+    const uint32_t st = ring_u + s * STAGE;
+    if (SPLIT && second) {
+      // The projection is linear in the context: blend the two parts in place (w0 c0 + w1 c1, one more bf16 rounding of
+      // the context) and project once - a second set of mma.sync costs 3 us per launch, the blend 8 FMAs per 16 bytes.
+      uint8_t* a0p = ring + s * STAGE;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int ch = (threadIdx.x + i * 128);          // 16-byte chunk of the 2 x 4 KB of part 0 (same spot in part 1)
+        const int row = (ch & 255) >> 3;
+        const float w0 = wgt[0][row], w1 = wgt[1][row];
+        uint4 x = *reinterpret_cast<const uint4*>(a0p + ch * 16);
+        const uint4 y = *reinterpret_cast<const uint4*>(a0p + A_STAGE + ch * 16);
+        x.x = pack_bf16(w0 * bf16lo(x.x) + w1 * bf16lo(y.x), w0 * bf16hi(x.x) + w1 * bf16hi(y.x));
+        x.y = pack_bf16(w0 * bf16lo(x.y) + w1 * bf16lo(y.y), w0 * bf16hi(x.y) + w1 * bf16hi(y.y));
+        x.z = pack_bf16(w0 * bf16lo(x.z) + w1 * bf16lo(y.z), w0 * bf16hi(x.z) + w1 * bf16hi(y.z));
+        x.w = pack_bf16(w0 * bf16lo(x.w) + w1 * bf16lo(y.w), w0 * bf16hi(x.w) + w1 * bf16hi(y.w));
+        *reinterpret_cast<uint4*>(a0p + ch * 16) = x;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+#pragma unroll
+    for (int kp = 0; kp < 4; ++kp) {   // 32 columns of K each; atom = kp / 2
+      const int ch0 = (kp & 1) * 4;
+      const uint32_t b_atom = st + NP * A_STAGE + (kp >> 1) * LVT_B_ATOM;
+      uint32_t bf[2][4];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const uint32_t addr = b_atom + b_row[nt] * 128 + (((ch0 + b_ch) ^ (b_row[nt] & 7)) << 4);
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(bf[nt][0]), "=r"(bf[nt][1]), "=r"(bf[nt][2]), "=r"(bf[nt][3]) : "r"(addr));
+      }
+      {
+        const uint32_t a_atom = st + (kp >> 1) * LVT_A_ATOM;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          const int r = mt * 16 + a_row;
+          uint32_t a0[4], a1[4];
+          const uint32_t ad0 = a_atom + r * 128 + (((ch0 + a_ch) ^ (r & 7)) << 4);
+          const uint32_t ad1 = a_atom + r * 128 + (((ch0 + 2 + a_ch) ^ (r & 7)) << 4);
+          asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(a0[0]), "=r"(a0[1]), "=r"(a0[2]), "=r"(a0[3]) : "r"(ad0));
+          asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(a1[0]), "=r"(a1[1]), "=r"(a1[2]), "=r"(a1[3]) : "r"(ad1));
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt) {
+            mma_bf16_16816(c[mt][nt], a0, bf[nt][0], bf[nt][1]);
+            mma_bf16_16816(c[mt][nt], a1, bf[nt][2], bf[nt][3]);
+          }
+        }
+      }
+    }
+    if (SPLIT && second) fence_proxy_async_smem();   // the blend wrote the stage the next TMA box overwrites
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+  }
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    const int ra = mt * 16 + g, rb = ra + 8;                // rows of this thread inside the CTA's tile
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      const int col = h * 64 + (warp * 2 + nt) * 8 + 2 * t;
+      const float b0 = bv ? bv[col] : 0.f, b1 = bv ? bv[col + 1] : 0.f;
+      const float v0 = c[mt][nt][0], v1 = c[mt][nt][1], v2 = c[mt][nt][2], v3 = c[mt][nt][3];
+      if (m0 + ra < R) *reinterpret_cast<uint32_t*>(o + (m0 + ra) * ldo + col) = pack_bf16(v0 + b0, v1 + b1);
+      if (m0 + rb < R) *reinterpret_cast<uint32_t*>(o + (m0 + rb) * ldo + col) = pack_bf16(v2 + b0, v3 + b1);
+    }
+  }
+}
+
 int latent_value(const void* ctx, long long part_stride, const float* ml, const void* wv, long long ldw, const float* bv,
                  void* o, long long ldo, int R, int H, cudaStream_t stream) {
   const int d = H * 64;
@@ -781,6 +975,38 @@ int latent_value(const void* ctx, long long part_stride, const float* ml, const 
                  part_stride % 8 == 0,
              "latent value: operands must be 16-byte aligned");
   WF_REQUIRE(H <= 32, "latent value: at most 32 heads");
+  static const bool no_tma = getenv("WF_LATENT_VALUE_TMA") != nullptr && atoi(getenv("WF_LATENT_VALUE_TMA")) == 0;
+  if (d % 128 == 0 && ldw % 8 == 0 && !no_tma) {
+    const bool split = ml != nullptr;
+    CUtensorMap ma0, ma1, mb;
+    int rc = make_map_bf16(&ma0, ctx, R, static_cast<long long>(H) * d, static_cast<long long>(H) * d, LVT_ROWS);
+    if (rc != WF_OK) return rc;
+    ma1 = ma0;
+    if (split) {
+      rc = make_map_bf16(&ma1, reinterpret_cast<const __nv_bfloat16*>(ctx) + part_stride, R, static_cast<long long>(H) * d,
+                         static_cast<long long>(H) * d, LVT_ROWS);
+      if (rc != WF_OK) return rc;
+    }
+    rc = make_map_bf16(&mb, wv, d, d, ldw, 64);
+    if (rc != WF_OK) return rc;
+    const size_t stage = (split ? 2 : 1) * 2 * LVT_A_ATOM + 2 * LVT_B_ATOM;
+    const size_t smem = LVT_STAGES * stage + 1024;
+    static PerDeviceOnce tconf;
+    if (tconf.first_use()) {
+      const int big = LVT_STAGES * (4 * LVT_A_ATOM + 2 * LVT_B_ATOM) + 1024;
+      WF_CHECK_CUDA(cudaFuncSetAttribute(latent_value_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+      WF_CHECK_CUDA(cudaFuncSetAttribute(latent_value_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    }
+    dim3 tgrid(H, (R + LVT_ROWS - 1) / LVT_ROWS);
+    if (split)
+      WF_CHECK_CUDA(launch_pdl(0, latent_value_tma_kernel<true>, tgrid, dim3(160), smem, stream, ma0, ma1, mb,
+                               reinterpret_cast<const float2*>(ml), bv, reinterpret_cast<__nv_bfloat16*>(o), ldo, R, H, d));
+    else
+      WF_CHECK_CUDA(launch_pdl(0, latent_value_tma_kernel<false>, tgrid, dim3(160), smem, stream, ma0, ma1, mb,
+                               reinterpret_cast<const float2*>(ml), bv, reinterpret_cast<__nv_bfloat16*>(o), ldo, R, H, d));
+    count_launch();
+    return WF_OK;
+  }
   const bool wide = H * ((R + 15) / 16) > num_sms();      // 32 rows per CTA
   const int rows = wide ? 32 : 16;
   dim3 grid(H, (R + rows - 1) / rows);
