@@ -175,10 +175,28 @@ def run_product(args):
     def device_step():
         return gather_tokens(hot_path_step(model, pcm_dev, feat_dev, opt))
 
+    copy_stream = torch.cuda.Stream(device=dev)
+
     def e2e_step():
+        # host inputs -> tokens on the host, all through the public API.  The PCM goes up first on the compute stream;
+        # the lip features (393 of the 639 MB) follow on a copy stream while the log-mel frontend and the encoder of
+        # the SAME step run - the decoder is the first consumer of the features (whisper.decode takes encoded audio,
+        # like the reference: whisper/decoding.py:663-676).
+        import whisper
+        main = torch.cuda.current_stream()
         p = pcm_host.to(dev, non_blocking=True)
-        f = feat_host.to(dev, non_blocking=True)
-        toks = gather_tokens(hot_path_step(model, p, f, opt))
+        pcm_up = torch.cuda.Event()
+        pcm_up.record(main)
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(pcm_up)          # one H2D transfer at a time: the PCM is needed first
+            f = feat_host.to(dev, non_blocking=True)
+            feat_up = torch.cuda.Event()
+            feat_up.record(copy_stream)
+        mel = whisper.log_mel_spectrogram(p, n_mels=80, per_clip_max=True)
+        audio = model.embed_audio(mel.to(torch.bfloat16))
+        main.wait_event(feat_up)
+        f.record_stream(main)
+        toks = gather_tokens(whisper.decode(model, audio, opt, x_v=f))
         return toks.cpu()  # device -> host read of the step's result
 
     def timed(fn, steps):
@@ -202,12 +220,12 @@ def run_product(args):
     ms, toks = timed(device_step, args.steps)
     launches = nv.kernel_launch_count() - l0
     clocks = sampler.stop() if sampler else None
-    e2e_step()
-    ms_e2e, toks_e2e = timed(e2e_step, args.steps)
     phases = None
-    if os.environ.get("WF_TIMING", "0") == "1":
+    if os.environ.get("WF_TIMING", "0") == "1":   # of the device-resident run (the e2e step feeds decode() encoded audio)
         from whisper._engine import PhaseTimer
         phases = {k: round(v, 2) for k, v in PhaseTimer.last.items()}
+    e2e_step()
+    ms_e2e, toks_e2e = timed(e2e_step, args.steps)
     assert toks.shape == (B * world, SAMPLE_LEN), toks.shape
     assert torch.equal(toks.cpu(), toks_e2e), "device-resident and end-to-end runs decoded different tokens"
     # data-parallel result check: the gathered matrix holds rank r's own tokens in rows [r * B, (r + 1) * B)

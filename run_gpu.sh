@@ -24,6 +24,8 @@ prof latent_query latent_query 4 2
 prof gemm_skinny gemm_skinny 40 4
 prof fa_tc fa_tc_kernel 2 1
 prof gemm_tc2 gemm_tc2 6 4
+prof logmel logmel 0 2
+timeout 600 python tools/mel_sweep.py > gpurun_out/${TAG}_mel_sweep.txt 2>> $LOG
 timeout 600 python tools/microbench.py gemm attn2 skinny3 mel fa latent > gpurun_out/micro_${TAG}.log 2>&1
 echo "micro rc $?" >> $LOG
 cat $LOG
