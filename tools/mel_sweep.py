@@ -58,6 +58,22 @@ def main():
                   f"{B / t_ref * 1e6:10.0f} {by / t_ref / 1e3:7.0f} | {t_ref / t_wf:8.1f} {diff:10.2e}", flush=True)
             del pcm
             torch.cuda.empty_cache()
+    # (iii) the same reference algorithm on the host cores (B in {1, 16, 64, 256})
+    torch.set_num_threads(os.cpu_count())
+    print(f"\nreference algorithm (torch.stft pipeline) on the host, fp32, {torch.get_num_threads()} threads")
+    for n_mels in (80, 128):
+        filt = mel_filters("cpu", n_mels)
+        for B in (1, 16, 64, 256):
+            pcm = torch.randn(B, 480000) * 0.1
+            torch_stft_logmel(pcm[:1], filt)
+            import time
+            t0 = time.perf_counter()
+            reps = 3 if B <= 16 else 1
+            for _ in range(reps):
+                torch_stft_logmel(pcm, filt)
+            t = (time.perf_counter() - t0) / reps
+            by = B * (480000 * 4 + n_mels * 3000 * 4)
+            print(f"{B:6d} {n_mels:5d} | {t * 1e6:12.0f} us {B / t:10.0f} clips/s {by / t / 1e9:7.2f} GB/s", flush=True)
 
 
 if __name__ == "__main__":
