@@ -793,7 +793,8 @@ template <bool SPLIT>
 __global__ void __launch_bounds__(160)
 latent_value_tma_kernel(const __grid_constant__ CUtensorMap ma0, const __grid_constant__ CUtensorMap ma1,
                         const __grid_constant__ CUtensorMap mb, const float2* __restrict__ ml,
-                        const float* __restrict__ bv, __nv_bfloat16* __restrict__ o, long long ldo, int R, int H, int d) {
+                        const float* __restrict__ bv, __nv_bfloat16* __restrict__ o, long long ldo, int R, int H, int d,
+                        int early) {
   constexpr int NP = SPLIT ? 2 : 1;
   constexpr int A_STAGE = 2 * LVT_A_ATOM;                 // per part
   constexpr int STAGE = NP * A_STAGE + 2 * LVT_B_ATOM;    // 24 KB, 32 KB in the split form
@@ -810,6 +811,7 @@ latent_value_tma_kernel(const __grid_constant__ CUtensorMap ma0, const __grid_co
     mbar_fence_init();
   }
   __syncthreads();
+  if (early) pdl_trigger();   // the out-projection GEMM behind this kernel may place its CTAs and request its weights
 
   if (warp == 4) {   // ---- producer
     if (lane == 0) {
@@ -998,12 +1000,13 @@ int latent_value(const void* ctx, long long part_stride, const float* ml, const 
       WF_CHECK_CUDA(cudaFuncSetAttribute(latent_value_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     }
     dim3 tgrid(H, (R + LVT_ROWS - 1) / LVT_ROWS);
+    static const int early = getenv("WF_LV_EARLY") ? atoi(getenv("WF_LV_EARLY")) : 1;   // measured: decode loop -1.3 .. -2.0 ms per step
     if (split)
       WF_CHECK_CUDA(launch_pdl(0, latent_value_tma_kernel<true>, tgrid, dim3(160), smem, stream, ma0, ma1, mb,
-                               reinterpret_cast<const float2*>(ml), bv, reinterpret_cast<__nv_bfloat16*>(o), ldo, R, H, d));
+                               reinterpret_cast<const float2*>(ml), bv, reinterpret_cast<__nv_bfloat16*>(o), ldo, R, H, d, early));
     else
       WF_CHECK_CUDA(launch_pdl(0, latent_value_tma_kernel<false>, tgrid, dim3(160), smem, stream, ma0, ma1, mb,
-                               reinterpret_cast<const float2*>(ml), bv, reinterpret_cast<__nv_bfloat16*>(o), ldo, R, H, d));
+                               reinterpret_cast<const float2*>(ml), bv, reinterpret_cast<__nv_bfloat16*>(o), ldo, R, H, d, early));
     count_launch();
     return WF_OK;
   }
