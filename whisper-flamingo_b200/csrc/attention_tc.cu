@@ -18,6 +18,19 @@
 
 namespace wf {
 
+// 2^x on the FMA / ALU pipes: round-to-nearest split x = n + f through the 1.5 * 2^23 trick, degree-3 polynomial for 2^f
+// on [-0.5, 0.5] (max relative error 1.0e-4), n added to the exponent field.  x <= 126; anything below -126 gives 2^-126.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -126.0f);
+  const float t = x + 12582912.0f;
+  const float f = x - (t - 12582912.0f);
+  float p = fmaf(f, 0.055922035f, 0.24264008f);
+  p = fmaf(p, f, 0.69312102f);
+  p = fmaf(p, f, 0.99992448f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+
 static constexpr int FT_M = 128;      // queries per softmax warpgroup
 static constexpr int FT_WG = 2;       // warpgroups (query tiles) per CTA: 256 queries share every K/V tile
 static constexpr int FT_N = 128;      // keys per tile
@@ -29,6 +42,11 @@ static constexpr int FT_D = 64;       // head dim
 static constexpr bool FT_P_IN_TMEM = true;
 #ifndef FT_MXC
 #define FT_MXC 16     // independent FMNMX chains of the row maximum (4: 2262 us, 8: 2258, 16: 2236)
+#endif
+#ifndef FT_POLY
+#define FT_POLY 0      // every FT_POLY-th pair of exponentials on the FMA / ALU pipes instead of MUFU.  Measured, B = 128
+                       // x 20 heads x 1500: 0 (all MUFU) 2238 us = 659 TFLOP/s, 4: 2324 us, 3: 2432 us, 2: 2679 us - the
+                       // softmax warps are bound by their issue slots, not by the MUFU pipe; MUFU stays the cheapest exp
 #endif
 #ifndef FT_LAZY
 #define FT_LAZY 1      // lazy reference maximum (0: 2334 us, 1: 2267)
@@ -253,8 +271,12 @@ fa_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
       for (int c = 0; c < 4; ++c)
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const float e0 = ex2_approx(fmaf(__uint_as_float(sv[c][i]), sl2, -msc));
-          const float e1 = ex2_approx(fmaf(__uint_as_float(sv[c][i + 1]), sl2, -msc));
+          const float x0 = fmaf(__uint_as_float(sv[c][i]), sl2, -msc), x1 = fmaf(__uint_as_float(sv[c][i + 1]), sl2, -msc);
+          // every FT_POLY-th pair takes the FMA / ALU pipes instead of MUFU (two softmax warps share a scheduler's
+          // MUFU pipe: 8 clk per warp instruction; the polynomial is 8 instructions, 1e-4 relative - P is bf16)
+          const bool poly = FT_POLY > 0 && ((i >> 1) % (FT_POLY > 0 ? FT_POLY : 1)) == (FT_POLY > 0 ? FT_POLY : 1) - 1;
+          const float e0 = poly ? ex2_poly(x0) : ex2_approx(x0);
+          const float e1 = poly ? ex2_poly(x1) : ex2_approx(x1);
           ps4[(i >> 1) & 3] += e0 + e1;
           sv[c][i >> 1] = pack_bf16(e0, e1);                          // slot i/2 <= i: already consumed
         }

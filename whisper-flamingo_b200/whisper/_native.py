@@ -113,7 +113,8 @@ EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
 
 def lib_path() -> str:
-    return os.path.normpath(_LIB_PATH)
+    # WF_LIB: another build of the same library (A/B runs of kernel variants); the default is the in-tree lib/libwf.so
+    return os.path.normpath(os.environ.get("WF_LIB") or _LIB_PATH)
 
 
 def load() -> C.CDLL:
