@@ -48,6 +48,9 @@ static constexpr bool FT_P_IN_TMEM = true;
                        // x 20 heads x 1500: 0 (all MUFU) 2238 us = 659 TFLOP/s, 4: 2324 us, 3: 2432 us, 2: 2679 us - the
                        // softmax warps are bound by their issue slots, not by the MUFU pipe; MUFU stays the cheapest exp
 #endif
+#ifndef FT_PACK
+#define FT_PACK 1      // packed f32x2 scale / row sums and three-input maxima in the softmax (it is issue bound)
+#endif
 #ifndef FT_LAZY
 #define FT_LAZY 1      // lazy reference maximum (0: 2334 us, 1: 2267)
 #endif
@@ -253,7 +256,12 @@ fa_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
 #pragma unroll
       for (int c = 0; c < 4; ++c)
 #pragma unroll
+#if FT_PACK
+        for (int i = 0; i < 32; i += 2)
+          mxc[(i >> 1) % FT_MXC] = fmax3(mxc[(i >> 1) % FT_MXC], __uint_as_float(sv[c][i]), __uint_as_float(sv[c][i + 1]));
+#else
         for (int i = 0; i < 32; ++i) mxc[i % FT_MXC] = fmaxf(mxc[i % FT_MXC], __uint_as_float(sv[c][i]));
+#endif
       float mx = mxc[0];
 #pragma unroll
       for (int i = 1; i < FT_MXC; ++i) mx = fmaxf(mx, mxc[i]);
@@ -266,6 +274,26 @@ fa_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
       const float msc = mx * sl2;
       FT_T(t_max);
       // p = exp2(s * sl2 - m * sl2), packed to bf16 pairs in place (overlaps the P V MMA of the previous tile)
+#if FT_PACK
+      uint64_t ps2[4] = {0ull, 0ull, 0ull, 0ull};
+      const uint64_t sl2p = f2_pack(sl2, sl2), nmsc = f2_pack(-msc, -msc);
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float x0, x1;
+          f2_unpack(f2_fma(f2_pack(__uint_as_float(sv[c][i]), __uint_as_float(sv[c][i + 1])), sl2p, nmsc), x0, x1);
+          const float e0 = ex2_approx(x0), e1 = ex2_approx(x1);
+          ps2[(i >> 1) & 3] = f2_add(ps2[(i >> 1) & 3], f2_pack(e0, e1));
+          sv[c][i >> 1] = pack_bf16(e0, e1);                          // slot i/2 <= i: already consumed
+        }
+      float psum;
+      {
+        float a, b;
+        f2_unpack(f2_add(f2_add(ps2[0], ps2[1]), f2_add(ps2[2], ps2[3])), a, b);
+        psum = a + b;
+      }
+#else
       float ps4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int c = 0; c < 4; ++c)
@@ -281,6 +309,7 @@ fa_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
           sv[c][i >> 1] = pack_bf16(e0, e1);                          // slot i/2 <= i: already consumed
         }
       const float psum = (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
+#endif
       FT_T(t_exp);
       // O *= alpha (only when some row of this warp moved its max); PV_w(j-1) must have completed first
       if (j > 0) {
