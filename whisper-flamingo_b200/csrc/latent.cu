@@ -779,7 +779,8 @@ latent_value_kernel(const __nv_bfloat16* __restrict__ ctx, long long part_stride
 // cp.async: ~15 B/clk per SM whatever the ring depth (3 and 6 stages: 7.3 / 11.8 us both) - the LSU path, not latency,
 // bounds it.  Here a fifth warp feeds a ring of 128-column stages with TMA boxes (128-byte swizzle, read back by
 // ldmatrix through the same XOR), the weight boxes of the first stages before the dependency wait; the four MMA warps
-// only wait on mbarriers.  grid (H, ceil(R / 32)), 160 threads; needs d % 128 == 0.
+// only wait on mbarriers.  grid (H, ceil(R / 32)), 160 threads; needs d % 128 == 0 (always true on the latent path: it
+// takes an even number of 64-wide heads); WF_LATENT_VALUE_TMA=0 selects the cp.async kernel for A/B runs.
 static constexpr int LVT_STAGES = 6;
 static constexpr int LVT_ROWS = 32;
 static constexpr int LVT_A_ATOM = LVT_ROWS * 128;      // 32 rows x 64 columns, bytes
