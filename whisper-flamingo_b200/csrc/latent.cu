@@ -577,24 +577,37 @@ latent_query_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const __
 #pragma unroll
   for (int k = 0; k < 4; ++k) ldmatrix_x4(af[k], &As[(warp * 16 + (lane & 15)) * LQ_LD + k * 16 + (lane >> 4) * 8]);
   const int g = lane >> 2, t = lane & 3;
-  const int row_lo = m0 + warp * 16 + g;
+  // The 16 x 128 outputs of a warp leave in two halves of 64 columns, staged in the warp's own rows of As (its A
+  // fragments are in registers by now) so that every store instruction writes four full 128-byte row segments
+  // (fragment layout: 16-byte pieces of eight different rows per instruction).
+  __nv_bfloat16* stage = &As[(warp * 16) * LQ_LD];
+  __syncwarp();
 #pragma unroll
-  for (int nt = 0; nt < 16; ++nt) {
-    float c[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int half = 0; half < 2; ++half) {
 #pragma unroll
-    for (int kp = 0; kp < 2; ++kp) {
-      uint32_t bf[4];
-      ldmatrix_x4(bf, &Bs[(nt * 8 + (lane & 7)) * LQ_LD + kp * 32 + (lane >> 3) * 8]);
-      mma_bf16_16816(c, af[2 * kp], bf[0], bf[1]);
-      mma_bf16_16816(c, af[2 * kp + 1], bf[2], bf[3]);
+    for (int nq = 0; nq < 8; ++nq) {
+      const int nt = half * 8 + nq;
+      float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int kp = 0; kp < 2; ++kp) {
+        uint32_t bf[4];
+        ldmatrix_x4(bf, &Bs[(nt * 8 + (lane & 7)) * LQ_LD + kp * 32 + (lane >> 3) * 8]);
+        mma_bf16_16816(c, af[2 * kp], bf[0], bf[1]);
+        mma_bf16_16816(c, af[2 * kp + 1], bf[2], bf[3]);
+      }
+      *reinterpret_cast<uint32_t*>(&stage[g * LQ_LD + nq * 8 + 2 * t]) = pack_bf16(c[0], c[1]);
+      *reinterpret_cast<uint32_t*>(&stage[(g + 8) * LQ_LD + nq * 8 + 2 * t]) = pack_bf16(c[2], c[3]);
     }
-    const int n = n0 + nt * 8 + 2 * t;
-    if (n < d) {
-      if (row_lo < R)
-        *reinterpret_cast<uint32_t*>(qp + (static_cast<long long>(row_lo) * H + h) * d + n) = pack_bf16(c[0], c[1]);
-      if (row_lo + 8 < R)
-        *reinterpret_cast<uint32_t*>(qp + (static_cast<long long>(row_lo + 8) * H + h) * d + n) = pack_bf16(c[2], c[3]);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = i * 4 + (lane >> 3), ch = lane & 7;         // row of the warp's 16, 16-byte chunk of the 128-byte half row
+      const int row = m0 + warp * 16 + r, n = n0 + half * 64 + ch * 8;
+      if (row < R && n < d)
+        *reinterpret_cast<uint4*>(qp + (static_cast<long long>(row) * H + h) * d + n) =
+            *reinterpret_cast<const uint4*>(&stage[r * LQ_LD + ch * 8]);
     }
+    __syncwarp();
   }
 }
 
