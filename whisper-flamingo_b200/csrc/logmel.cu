@@ -587,7 +587,7 @@ logmel_fft2_kernel(const float* __restrict__ pcm, long long clip_stride, int n_s
 // (16 pairs); a warp's two half-warps are two DFT columns (t = 2 w + h) and then the two ROWS r and 20 - r of the
 // second stage (warp 0: rows 0 and 10, their own partners), so the conjugate-partner exchange of the real-spectrum
 // split is a lane-xor-16 shuffle instead of a trip through shared memory.  The power spectrum has its own buffer:
-// three barriers per group, 110 KB per CTA, two CTAs with independent barriers per SM.
+// two barriers per group, 110 KB per CTA, two CTAs with independent barriers per SM.
 // Measured and rejected: applying the clamp + rescale inside this kernel (device-wide group queue, groups counted per
 // clip, the CTA that completes a clip rewrites its 1 MB from L2): one CTA needs ~70 us per clip whatever the number of
 // loads in flight, and the completions pile up at the end of the grid - 338 us against 226 us at 128 clips, 1866 against
@@ -705,12 +705,15 @@ logmel_fft3_kernel(const float* __restrict__ pcm, long long clip_stride, int n_s
 
   __syncthreads();
   if (n_groups > 0) stage(clip, gi);
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();                                     // PCM of the first group is in place
 
   for (int it = 0; it < n_groups; ++it) {
     const int f0 = gi * GF3;
     if (clip != cur_clip) { flush(); cur_clip = clip; run_max = -3.0e38f; }
-    asm volatile("cp.async.wait_all;" ::: "memory");
-    __syncthreads();                                   // (A) PCM of this group is in place; S and P are free again
+    // (no barrier here: barrier E of the previous group already orders everything the next stages touch - every
+    // thread waited for its PCM copies before it, the S reads of the second stage and the P writes precede it, and
+    // the next P writes come after barrier B, which no warp passes before all have left the filterbank)
 
     c2 v[20], o[20];
     // ---- stage 1: half-warp = column t; z[n] = xa[n] + i xb[n], n = 20 n1 + t, windowed
@@ -772,6 +775,7 @@ logmel_fft3_kernel(const float* __restrict__ pcm, long long clip_stride, int n_s
         if (h == 0) pp[10 * 320] = power2(o[10], o[10]);
       }
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");    // the next group's PCM (requested after barrier B)
     __syncthreads();                                   // (E)
     // ---- mel rows of this half-warp: filterbank, log10, store, running maximum.  The two half-warps of a warp walk
     // rows padded to the same number of quads (zero weights over finite padding), so the loops carry no guards.
