@@ -11,9 +11,9 @@ int main() {
   const int smem = 200 * 1024;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-  for (int cs : {1, 2, 4, 8, 16}) {
+  for (int cs : {1, 2, 3, 4, 5, 6, 7, 8, 16}) {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(cs * 64);
+    cfg.gridDim = dim3(cs * 60);
     cfg.blockDim = dim3(384);
     cfg.dynamicSmemBytes = smem;
     cudaLaunchAttribute at[1];

@@ -335,14 +335,14 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       // warp reads 1 KB of CONTIGUOUS remote shared memory per partial tile (a row-per-thread mapping measured 8 GB/s
       // over DSMEM: 32 different 128-byte lines per request) and stores coalesced 16-byte pieces of output rows.
       const int et = (warp - 4) * 32 + lane;
-      const int rows_per = BM / CS;
+      const int rows_per = (BM + CS - 1) / CS;   // CS need not divide the tile height (clusters of 5 or 6)
       constexpr int GPR = BN / 8;
       const uint32_t dump_local = smem_u32(dump);
       for (int it = et; it < rows_per * GPR; it += EPI_THREADS_SK) {
         const int row = rank * rows_per + it / GPR;     // row inside the tile
         const int col = (it % GPR) * 8;
         const int n0 = n_blk * BN + col;
-        if (m0 + row >= M || n0 >= N) continue;
+        if (row >= BM || m0 + row >= M || n0 >= N) continue;
         const uint32_t off = static_cast<uint32_t>((row * Cfg::DUMP_LD + col) * 4);
         float4 t[8][2];
 #pragma unroll
@@ -450,22 +450,31 @@ bool skinny_plan(int M, int N, int K, int tile_hint, int* bn_out, int* cs_out, i
   const int sms = num_sms();
   const int rounds = (K + SK_KA * SK_BK - 1) / (SK_KA * SK_BK);
   const int bns[4] = {32, 64, 128, 256};
-  int cs = rounds >= 32 ? 4 : 1;
-  if (force_cs) cs = force_cs;
-  while (cs > 1 && cs > rounds) cs >>= 1;
+  // cluster sizes to try, widest first.  6 CTAs need not divide the tile height (the row slices of the reduction are
+  // ceil(128 / 6) rows) and 22 such clusters fit the chip (profiles/r02_probe_cluster_occupancy.txt): N = 1280, K = 5120
+  // 9.87 us (cs 4, 80 CTAs) -> 9.57 us (cs 6, 120 CTAs); 5: 9.62, 3: 10.44, 8 does not fit (160 CTAs)
+  int cand[5] = {6, 4, 2, 1, 0};
+  if (rounds < 32) { cand[0] = 1; cand[1] = 0; }
+  if (force_cs) { cand[0] = force_cs; cand[1] = force_cs > 1 ? 1 : 0; cand[2] = 0; }
   bool found = false;
-  for (;; cs >>= 1) {
+  for (int ci = 0; cand[ci] != 0 && !found; ++ci) {
+    const int cs = cand[ci];
+    if (cs > 1 && cs > rounds) continue;
     for (int i = 0; i < 4 && !found; ++i) {
       const int bn = bns[i];
       if (tile_hint && bn != tile_hint) continue;
+      if (cs == 6 && bn > 64 && !tile_hint) continue;   // measured only where it keeps the narrow tiles
       const int tiles = (N + bn - 1) / bn;
       if (tiles * cs * m_tiles > sms) continue;
+      // clusters are placed inside a GPC: on the 148-SM part 33 clusters of 4 and 22 of 6 are resident at once
+      // (tools/probe/cluster_occ.cu); more would run as a second wave
+      const int max_clusters = cs == 6 ? sms * 22 / 148 : cs == 4 ? sms * 33 / 148 : sms / cs;
+      if (tiles * m_tiles > max_clusters) continue;
       *bn_out = bn;
       *cs_out = cs;
       *bm_out = SK_BM;
       found = true;
     }
-    if (found || cs == 1) break;
   }
   // 64-row tiles on twice the CTAs (no K split): taken when a CTA then pulls fewer bytes, (BM + BN) x K x 2
   if (force_bm != 128 && (!found || *cs_out == 1)) {
