@@ -48,6 +48,11 @@ static constexpr bool FT_P_IN_TMEM = true;
                        // x 20 heads x 1500: 0 (all MUFU) 2238 us = 659 TFLOP/s, 4: 2324 us, 3: 2432 us, 2: 2679 us - the
                        // softmax warps are bound by their issue slots, not by the MUFU pipe; MUFU stays the cheapest exp
 #endif
+// Measured and rejected (round 2): PERSISTENT CTAs (one per SM over the (query tile, head, clip) items, all barrier phases on
+// a global tile counter, double-buffered Q, an o_free barrier so that producer and score issuer run into the next item
+// during the epilogue): tokens identical, 2322 us (635 TFLOP/s) against 2200 us with one CTA per item; 2268 us with the
+// warpgroup lag re-applied at every item, 2306 us with setmaxnreg (56 / 216 registers for the helper / softmax
+// warpgroups).  The 2.5 us a fresh CTA waits for its first Q / K / V are evidently not the loss they look like.
 #ifndef FT_PACK
 #define FT_PACK 1      // packed f32x2 scale / row sums and three-input maxima in the softmax (it is issue bound)
 #endif
