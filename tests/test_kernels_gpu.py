@@ -49,6 +49,67 @@ def test_logmel_gaussian_and_chirp_vs_oracle_and_golden(nv, n_mels):
     assert np.abs(c.reshape(-1)[idx] - g[f"chirp{n_mels}_samples"]).max() <= 2e-4
 
 
+_VARIANT_SCRIPT = r"""
+import os, sys, math
+import numpy as np, torch
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[2])
+import whisper
+from whisper import _native as nv
+from oracle import mel as omel
+what = sys.argv[3]
+if what == "logmel":
+    g = torch.Generator().manual_seed(5)
+    pcm = torch.randn(3, 480000, generator=g) * 0.1
+    worst = 0.0
+    for n_mels in (80, 128):
+        got = whisper.log_mel_spectrogram(pcm.cuda(), n_mels=n_mels, per_clip_max=True).cpu().numpy()
+        want = omel.log_mel_spectrogram(pcm.numpy(), n_mels, per_clip_max=True)
+        worst = max(worst, float(np.abs(got - want).max()))
+        c = whisper.log_mel_spectrogram(torch.from_numpy(omel.chirp_kat()).cuda(), n_mels=n_mels).cpu().numpy()
+        worst = max(worst, float(np.abs(c - omel.log_mel_spectrogram(omel.chirp_kat(), n_mels)).max()) / 1.2)
+    print("RESULT", worst)
+else:
+    H, B, T = 20, 90, 300
+    d = 64 * H
+    g = torch.Generator().manual_seed(9)
+    r = lambda *s, sc=1.0: (torch.randn(*s, generator=g) * sc).cuda()
+    bf = torch.bfloat16
+    q, src = r(B, d).to(bf), r(B, T, d).to(bf)
+    wk, wv, bv = r(d, d, sc=2.0 / math.sqrt(d)).to(bf), r(d, d, sc=1.0 / math.sqrt(d)).to(bf), r(d, sc=0.1)
+    qp = torch.empty(B, H, d, dtype=bf, device="cuda")
+    ctx = torch.zeros(2, B, H, d, dtype=bf, device="cuda")
+    ml = torch.zeros(2, B, 32, 2, device="cuda")
+    out = torch.empty(B, d, dtype=bf, device="cuda")
+    nv.latent_query(q, wk.t().contiguous(), qp, H)
+    nv.latent_attention(qp, src, ctx, H, ml=ml)
+    nv.latent_value(ctx, wv, bv, out, H, ml=ml)
+    k = (src.float() @ wk.float().T).view(B, T, H, 64).permute(0, 2, 1, 3)
+    v = (src.float() @ wv.float().T + bv).view(B, T, H, 64).permute(0, 2, 1, 3)
+    w = torch.softmax((q.float().view(B, H, 1, 64) @ k.transpose(-1, -2)) * 0.125, dim=-1)
+    ref = (w @ v).reshape(B, d)
+    print("RESULT", float((out.float() - ref).norm() / ref.norm()))
+"""
+
+
+@pytest.mark.parametrize("env,what,bound", [("WF_LOGMEL_V1", "logmel", 1e-4), ("WF_LOGMEL_V2", "logmel", 1e-4),
+                                            ("WF_LATENT_VALUE_TMA=0", "latent", 1.5e-2)])
+def test_selectable_kernel_variants_stay_correct(nv, env, what, bound):
+    """The A/B variants kept in the library (round-1 log-mel kernel, the 20-warp form of the new layout, the cp.async
+    value projection) are chosen once per process through the environment: run each in a subprocess against the oracle."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ)
+    key, _, val = env.partition("=")
+    e[key] = val or "1"
+    r = subprocess.run([sys.executable, "-c", _VARIANT_SCRIPT, os.path.join(root, "whisper-flamingo_b200"), root, what],
+                       env=e, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    err = float([l for l in r.stdout.splitlines() if l.startswith("RESULT")][-1].split()[1])
+    assert err <= bound, (env, err)
+
+
 def test_logmel_batched_semantics_padding_and_cpu_input(nv):
     import whisper
     from whisper._synthetic import synthetic_pcm
