@@ -53,6 +53,8 @@ static constexpr bool FT_P_IN_TMEM = true;
 // during the epilogue): tokens identical, 2322 us (635 TFLOP/s) against 2200 us with one CTA per item; 2268 us with the
 // warpgroup lag re-applied at every item, 2306 us with setmaxnreg (56 / 216 registers for the helper / softmax
 // warpgroups).  The 2.5 us a fresh CTA waits for its first Q / K / V are evidently not the loss they look like.
+// Also measured: probabilities in fp16 through ex2.approx.f16x2 - ptxas emits TWO scalar MUFU.EX2.F16 per f16x2 (no
+// two-for-one on sm_100a), and tcgen05.mma kind::f16 with an fp16 A (P) and a bf16 B (V) is an illegal instruction.
 #ifndef FT_PACK
 #define FT_PACK 1      // packed f32x2 scale / row sums and three-input maxima in the softmax (it is issue bound)
 #endif
