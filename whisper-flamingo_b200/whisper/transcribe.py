@@ -208,6 +208,7 @@ def transcribe_batch(
     word_timestamps: bool = False,
     x_v: Optional[Sequence[Optional[torch.Tensor]]] = None,
     max_batch: int = 128,
+    batch_bucket: int = 16,
     **decode_options,
 ) -> List[dict]:
     """Long-form transcription of MANY recordings at once: in every round the current 30-s window of each unfinished
@@ -277,11 +278,20 @@ def transcribe_batch(
             kwargs = _temperature_kwargs(decode_options, t)
             kwargs["language"] = language
             kwargs["prompt"] = prompts[pending[0]]
-            sel = torch.tensor(pending, device=device)
-            whole = len(pending) == len(idx)
+            # Batch sizes are bucketed (multiples of `batch_bucket`, padded with repeats of the last row whose results
+            # are dropped): the batch shrinks as recordings end and every fallback rung has its own row count - each
+            # distinct size would otherwise build a new decode session (arena + CUDA-graph capture).  Rows are
+            # independent of each other, so the real rows decode exactly as they would alone.
+            rows = list(pending)
+            bucket = -(-len(rows) // batch_bucket) * batch_bucket
+            if batch_bucket > 1 and bucket <= max_batch:
+                rows = rows + [rows[-1]] * (bucket - len(rows))
+            whole = rows == list(range(len(idx)))
+            sel = torch.tensor(rows, device=device)
             out = model.decode(mel_b if whole else mel_b.index_select(0, sel), DecodingOptions(**kwargs, temperature=t),
                                x_v=None if feat_b is None else (feat_b if whole else feat_b.index_select(0, sel)),
-                               prompts=[prompts[j] for j in pending])
+                               prompts=[prompts[j] for j in rows])
+            out = out[: len(pending)]
             again = []
             for j, r in zip(pending, out):
                 results[j] = r
