@@ -278,12 +278,15 @@ def transcribe_batch(
             kwargs = _temperature_kwargs(decode_options, t)
             kwargs["language"] = language
             kwargs["prompt"] = prompts[pending[0]]
-            # Batch sizes are bucketed (multiples of `batch_bucket`, padded with repeats of the last row whose results
+            # Batch sizes are bucketed (multiples of `batch_bucket`, powers of two below it; padded with repeats of the last row whose results
             # are dropped): the batch shrinks as recordings end and every fallback rung has its own row count - each
             # distinct size would otherwise build a new decode session (arena + CUDA-graph capture).  Rows are
             # independent of each other, so the real rows decode exactly as they would alone.
             rows = list(pending)
-            bucket = -(-len(rows) // batch_bucket) * batch_bucket
+            if len(rows) >= batch_bucket:
+                bucket = -(-len(rows) // batch_bucket) * batch_bucket
+            else:                                   # below one bucket: powers of two (one recording stays one row)
+                bucket = 1 << (len(rows) - 1).bit_length()
             if batch_bucket > 1 and bucket <= max_batch:
                 rows = rows + [rows[-1]] * (bucket - len(rows))
             whole = rows == list(range(len(idx)))
