@@ -67,3 +67,16 @@ def test_shard_range_covers_everything_once():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_transcribe_batch_row_buckets():
+    """Host logic of the long-form driver: batch sizes are padded to few distinct values so that decode sessions and
+    CUDA graphs are reused while the batch shrinks (whisper/transcribe.py:_bucket_rows)."""
+    from whisper.transcribe import _bucket_rows
+    assert [_bucket_rows(n, 16, 128) for n in (1, 2, 3, 5, 8, 9, 15, 16, 17, 33, 64, 113, 128)] == \
+        [1, 2, 4, 8, 8, 16, 16, 16, 32, 48, 64, 128, 128]
+    assert _bucket_rows(120, 16, 120) == 120          # the bucket would exceed max_batch: no padding
+    assert _bucket_rows(7, 1, 128) == 7 and _bucket_rows(0, 16, 128) == 0
+    for n in range(1, 129):
+        b = _bucket_rows(n, 16, 128)
+        assert n <= b <= max(2 * n, n + 15)

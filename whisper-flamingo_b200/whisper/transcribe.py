@@ -194,6 +194,15 @@ def transcribe(
                             word_timestamps=word_timestamps, x_v=None if x_v is None else [x_v], **decode_options)[0]
 
 
+def _bucket_rows(n: int, batch_bucket: int, max_batch: int) -> int:
+    """Rows a decode call of n windows is padded to: the next multiple of `batch_bucket`, a power of two below one
+    bucket (a single recording stays a single row), never more than `max_batch`; `batch_bucket` <= 1 turns it off."""
+    if batch_bucket <= 1 or n <= 0:
+        return n
+    bucket = -(-n // batch_bucket) * batch_bucket if n >= batch_bucket else 1 << (n - 1).bit_length()
+    return bucket if bucket <= max_batch else n
+
+
 def transcribe_batch(
     model: "Whisper",
     audios: Sequence[Union[str, np.ndarray, torch.Tensor]],
@@ -283,12 +292,7 @@ def transcribe_batch(
             # distinct size would otherwise build a new decode session (arena + CUDA-graph capture).  Rows are
             # independent of each other, so the real rows decode exactly as they would alone.
             rows = list(pending)
-            if len(rows) >= batch_bucket:
-                bucket = -(-len(rows) // batch_bucket) * batch_bucket
-            else:                                   # below one bucket: powers of two (one recording stays one row)
-                bucket = 1 << (len(rows) - 1).bit_length()
-            if batch_bucket > 1 and bucket <= max_batch:
-                rows = rows + [rows[-1]] * (bucket - len(rows))
+            rows = rows + [rows[-1]] * (_bucket_rows(len(rows), batch_bucket, max_batch) - len(rows))
             whole = rows == list(range(len(idx)))
             sel = torch.tensor(rows, device=device)
             out = model.decode(mel_b if whole else mel_b.index_select(0, sel), DecodingOptions(**kwargs, temperature=t),
